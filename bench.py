@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MCMC balanced-colouring sweep (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5|small]
+
+metric  : vertex-updates / second of one synchronous MCMC sweep (edges/s alongside), whole job over all N GPUs
+workload: BASELINE config 3 -- Erdos-Renyi n = 100 M, mean degree 16, nCol = maxDeg (numColRatio 1.0) -- which fits
+          one B200 (6.8 GB of CSR); synthetic, generated on the device(s), never crossing PCIe.
+step    : one sweep over all n vertices starting from the uniform random colouring (every vertex active, ~31 % of
+          them conflicting -- the most expensive sweep of a chain).  The colouring is reset between steps outside
+          the timed region; the kernel is timed with CUDA events on the stream it is launched on.
+e2e     : the same sweep through the reference-shaped host API with HOST buffers: colouring H2D from pinned memory
+          (mcmcb200_init_colors), sweep, counters (mcmcb200_status) and colouring D2H (mcmcb200_get_colors).
+roofline: algorithmic bytes 8*nnz + 12*n + 4 per sweep (SURVEY 8d / DESIGN.md) over the live kernel time, against the
+          measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the UNMODIFIED reference CPU sampler (oracle/_ref, else the C port) on a bounded
+          sample of the same workload, single thread (the reference has no threading).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, mean degree, description)
+    "c3": (100_000_000, 16, "BASELINE config 3: Erdos-Renyi n=100M, mean degree 16, nCol=maxDeg"),
+    "c2": (1_000_000, 32, "BASELINE config 2: Erdos-Renyi n=1M, mean degree 32, nCol=maxDeg"),
+    "c5": (10_000_000, 16, "BASELINE config 5: Erdos-Renyi n=10M, mean degree 16, nCol=maxDeg"),
+    "small": (200_000, 16, "smoke-sized Erdos-Renyi n=200k, mean degree 16"),
+}
+GRAPH_SEED = 42
+CHAIN_SEED = 1
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def gen_graph_device(n, deg, device):
+    import torch
+    from mcmc_colorer_b200.graphgen import er_graph_torch
+    rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=device)
+    assert nnz < 2 ** 31, "this bench keeps CSR offsets in int32 tensors"
+    rowptr = rowptr64.to(torch.int32)
+    del rowptr64
+    torch.cuda.synchronize()
+    return rowptr, neighs, nnz, max_deg
+
+
+def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=1, warmup=0):
+    """Times the reference CPU sampler (oracle/_ref: the unmodified ColoringMCMC_CPU methods; else the C port) on the
+    first m vertices of the same graph, single thread (the reference has no threading at all).  m is sized by a short
+    calibration so that the whole call costs about target_seconds of CPU work.
+    Returns (vertex-updates/s, kind, sample description, per-step seconds, m)."""
+    import numpy as np
+    from oracle.pyoracle import Port, Ref
+    P = Port()
+    use_ref = Ref.available()
+    colors = P.init_colors(CHAIN_SEED, n, nCol)
+    u = P.tape(CHAIN_SEED, 1, n)
+
+    def run_sample(m, steps, warmup):
+        e_m = int(rowptr[m].item())
+        cumul = np.empty(n + 1, np.uint32)
+        cumul[:m + 1] = rowptr[:m + 1].cpu().numpy().astype(np.uint32)
+        cumul[m + 1:] = e_m                               # vertices outside the sample: empty rows, never visited
+        nb = neighs[:max(e_m, 1)].cpu().numpy().astype(np.uint32)[:e_m]
+        out = []
+        if use_ref:
+            R = Ref()
+            g = R.graph_from_csr(cumul, nb, float(nnz) / n / n)
+            h = R.mcmc(g, nCol, CHAIN_SEED)
+            for i in range(warmup + steps):
+                R.set_colors(h, colors)
+                sec = R.sweep_range_timed(h, u, 0, m)     # the reference's own per-vertex loop, timed inside the harness
+                if i >= warmup:
+                    out.append(sec)
+            R.L.ref_mcmc_free(h)
+            R.L.ref_graph_free(g)
+        else:
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                P.sweep(cumul, nb, nCol, 1e-8, colors, u, 0, vb=0, ve=m)
+                if i >= warmup:
+                    out.append(time.perf_counter() - t0)
+        return out
+
+    m0 = min(n, 500_000)
+    rate0 = m0 / run_sample(m0, 1, 0)[0]
+    m = int(min(n, max(100_000, rate0 * target_seconds / max(1, steps + warmup))))
+    secs = run_sample(m, steps, warmup)
+    rate = float(np.mean([m / s for s in secs]))
+    kind = "reference" if use_ref else "port"
+    sample = (f"first {m} of {n} vertices of the same graph ({int(rowptr[m].item())} directed edges), "
+              f"full {n}-entry colour array, first sweep from the uniform random colouring")
+    return rate, kind, sample, secs, m
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, deg, desc = WORKLOADS[args.workload]
+    if args.n:
+        n = args.n
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    if dev == "cpu":
+        import numpy as np
+        from mcmc_colorer_b200.graphgen import er_graph_numpy
+        n = min(n, 2_000_000)
+        cumul, nb = er_graph_numpy(n, deg, GRAPH_SEED)
+        rowptr, neighs = torch.from_numpy(cumul.astype(np.int64)), torch.from_numpy(nb.astype(np.int64))
+        nnz, max_deg = len(nb), int(np.diff(cumul.astype(np.int64)).max())
+    else:
+        rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev)
+    nCol = max_deg
+    rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=max(20.0, 6.0 * (args.steps + args.warmup)),
+                                                     steps=args.steps, warmup=args.warmup)
+    ms = 1e3 * sum(secs) / len(secs)
+    line = {"impl": "reference", "metric": "vertex_updates_per_sec", "value": rate, "unit": "vertex-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 colours / f32 CDF", "data": "synthetic",
+            "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": "uniform",
+                       "step": "bounded sample of one sweep: " + sample},
+            "cpu_baseline": {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": "vertex-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "edges_per_sec": rate * nnz / n, "host_cores_available": os.cpu_count()}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the vertex count (debugging)")
+    ap.add_argument("--proposal", default="uniform", choices=["uniform", "dynamic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import mcmc_colorer_b200 as mc
+    from mcmc_colorer_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libmcmcb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        from mcmc_colorer_b200 import multigpu
+        return multigpu.bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSampler)
+
+    n, deg, desc = WORKLOADS[args.workload]
+    if args.n:
+        n = args.n
+    t_gen = time.perf_counter()
+    rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev)
+    t_gen = time.perf_counter() - t_gen
+    nCol = max_deg                                        # numColRatio 1.0: nCol = maxDeg (main.cu:162)
+    proposal = mc.PROPOSAL_UNIFORM if args.proposal == "uniform" else mc.PROPOSAL_DYNAMIC
+    prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal,
+                                convergence=mc.CONVERGE_VERTICES if proposal == mc.PROPOSAL_UNIFORM else mc.CONVERGE_EDGES,
+                                seed=CHAIN_SEED)
+    ch = mc.Chain(params=prm, device=local_rank, flags=mc.FLAG_NO_EARLY_STOP, n_global=n, v_begin=0, v_end=n,
+                  device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz))
+
+    # ---- device-resident timing: `value` ----
+    for _ in range(args.warmup):
+        ch.init_colors(None)
+        ch.sweep(1)
+        ch.synchronize()
+    launches0 = ch.launch_count()
+    kernel_ms = []
+    with ClockSampler(local_rank) as clocks:
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            ch.init_colors(None)                          # untimed: reset to the uniform random colouring
+            torch.cuda.synchronize()
+            l0 = ch.launch_count()
+            ch.sweep(1)                                   # one launch of sweep_kernel, CUDA events on its stream
+            kernel_ms.append(ch.last_sweep_ms())
+            launches_per_step = ch.launch_count() - l0
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall
+        # a chain of consecutive sweeps (no reset), for the time-to-colouring side of the metric
+        ch.init_colors(None)
+        ch.sweep(10)
+        chain_ms = ch.last_sweep_ms() / 10.0
+    st = ch.status()
+    ms_per_step = float(np.mean(kernel_ms))
+    value = n / (ms_per_step * 1e-3)
+    alg_bytes = 8 * nnz + 12 * n + 4
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the host API with host buffers ----
+    pinned_in = torch.empty(n, dtype=torch.int32).pin_memory()
+    pinned_out = torch.empty(n, dtype=torch.int32).pin_memory()
+    ch.init_colors(None)
+    ch.get_colors_ptr(pinned_in.data_ptr())
+    e2e_t = []
+    for i in range(max(2, args.warmup) + min(args.steps, 5)):
+        t0 = time.perf_counter()
+        ch.init_colors_ptr(pinned_in.data_ptr())          # H2D 4n bytes from pinned memory
+        ch.sweep(1)
+        s2 = ch.status()                                  # counters D2H
+        ch.get_colors_ptr(pinned_out.data_ptr())          # D2H 4n bytes
+        dt = time.perf_counter() - t0
+        if i >= max(2, args.warmup):
+            e2e_t.append(dt)
+    e2e_value = n / float(np.mean(e2e_t))
+
+    line = {
+        "metric": "vertex_updates_per_sec", "value": value, "unit": "vertex-updates/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 colours / u32 ids / f32 CDF", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": args.proposal,
+                   "step": "one sweep from the uniform random colouring (all vertices active)",
+                   "l2": "inputs (CSR %.1f GB) larger than L2; no flush needed" % ((4 * nnz + 4 * n) / 1e9),
+                   "graph_gen_s": round(t_gen, 2)},
+        "edges_per_sec": value * nnz / n,
+        "chain_ms_per_sweep": chain_ms,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "mcmcb200::sweep_kernel", "launch_ms": ms_per_step},
+        "e2e": {"value": e2e_value, "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n,
+                "d2h_bytes_per_step": 4 * n + 40 + 8 * nCol, "ms_per_step": 1e3 * float(np.mean(e2e_t))},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks.summary(),
+        "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
+    }
+    if not args.no_cpu_baseline:
+        rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample,
+                                "host_cores_available": os.cpu_count()}
+    ch.close()
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,167 @@
+/*
+ * mcmcb200.h -- C ABI of the B200-native MCMC balanced-colouring sweep (libmcmcb200.so).
+ *
+ * The reference (Topopiccione/MCMC_Colorer) has no FFI layer: main.cu constructs the C++ classes
+ * directly.  This header is the boundary a maintainer binds instead of those classes' device code;
+ * each entry point cites the reference interface it replaces (paths relative to reference src/).
+ * INTEGRATION.md shows the reference-side patch (the ColoringMCMC<nodeW,edgeW> shim over this ABI).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MCMCB200_E* code; nothing aborts, no exception
+ *     crosses the boundary (the reference's cudaCheck prints and abort()s, GPUutils/GPUutils.h:20-26);
+ *   - plain pointers and sizes only; host arrays stay owned by the caller and may be freed after the call;
+ *   - one handle = one Markov chain on one CUDA device; a handle is not thread-safe, distinct handles
+ *     are independent;
+ *   - there is NO CPU fallback: without a CUDA device every entry point that needs one fails with
+ *     MCMCB200_ENODEVICE.
+ *
+ * RNG contract (replaces GPURand/curandState, GPUutils/GPURandomizer.cu:8-13,85-96, and
+ * std::default_random_engine, graph_coloring/coloringMCMC_CPU.cpp:53-55): stateless Philox4x32-10,
+ *   counter = (global vertex id, purpose, sweep, 0), key = (seed & 0xffffffff, seed >> 32), draw = word 0;
+ *   purpose 0: sweep draw, sweep = 1,2,...   UNIFORM: u = (x >> 8) * 2^-24 in [0,1)
+ *                                           DYNAMIC: u = ((x >> 8) + 1) * 2^-24 in (0,1]
+ *   purpose 1: initial colour, sweep = 0    colour = (x * nCol) >> 32
+ * so trajectories do not depend on the GPU count or on the launch shape.
+ */
+#ifndef MCMCB200_H
+#define MCMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCMCB200_ABI_VERSION 1
+
+enum {
+	MCMCB200_OK          =  0,
+	MCMCB200_EINVAL      = -1,  /* bad argument (null pointer, nCol == 0, colour >= nCol, ...) */
+	MCMCB200_ENODEVICE   = -2,  /* no usable CUDA device / wrong architecture */
+	MCMCB200_ECUDA       = -3,  /* a CUDA runtime call failed; mcmcb200_last_cuda_error() has the text */
+	MCMCB200_ENOMEM      = -4,  /* host or device allocation failed */
+	MCMCB200_EUNSUPPORTED= -5,  /* configuration outside this build (e.g. nnz >= 2^32) */
+	MCMCB200_ETAPE       = -6,  /* replay tape exhausted */
+	MCMCB200_ESTATE      = -7   /* call out of order (e.g. sweep before init_colors) */
+};
+
+enum { MCMCB200_PROPOSAL_UNIFORM = 0,   /* coloringMCMC_standard.cu:9-82 == CPU fill_p, coloringMCMC_CPU.cpp:392-481 */
+       MCMCB200_PROPOSAL_DYNAMIC = 1 }; /* coloringMCMC_balance.cu:79-143 + coloringMCMC_utils.cu:64-70 (shipped GPU default) */
+
+/* Superset of ColoringMCMCParams (graph_coloring/coloring.h:65-74; defaults main.cu:160-168). */
+typedef struct mcmcb200_params {
+	uint32_t nCol;            /* number of colours, coloring.h:67 */
+	float    epsilon;         /* coloring.h:70, main.cu:163 (1e-8f) */
+	float    lambda;          /* coloring.h:69 -- carried for the log; dead unless HASTINGS (coloringMCMC.h:41) */
+	float    numColorRatio;   /* coloring.h:68 -- carried for the log */
+	float    ratioFreezed;    /* coloring.h:71 -- carried for the log */
+	uint32_t tabooIteration;  /* coloring.h:72 */
+	uint32_t maxRip;          /* coloring.h:66 */
+	uint32_t tailcut;         /* coloring.h:73: z = max(50, n/2000) (coloringMCMC_main.cu:150-157) */
+	uint32_t proposal;        /* MCMCB200_PROPOSAL_* */
+	uint32_t convergence;     /* 0: stop on violating VERTICES <= z (CPU, coloringMCMC_CPU.cpp:136)
+	                             1: stop on conflicting EDGES <= z (GPU, coloringMCMC_main.cu:169) */
+	uint64_t seed;
+	int32_t  device;          /* CUDA device ordinal; -1 = current device */
+	uint32_t flags;           /* MCMCB200_FLAG_* */
+} mcmcb200_params;
+
+#define MCMCB200_FLAG_NO_FUSED_FINALIZE 1u  /* caller reduces the sweep counters across ranks itself (multi-GPU) */
+#define MCMCB200_FLAG_NO_EARLY_STOP     2u  /* sweeps keep advancing after C_t became proper (tape replay, benchmarking);
+                                               mcmcb200_status still reports `converged` for the current colouring */
+
+typedef struct mcmcb200_status_s {
+	uint32_t sweep;              /* index t of the current colouring C_t (= sweeps performed) */
+	int32_t  converged;          /* 1 iff the count selected by params.convergence of C_t is <= z */
+	uint64_t conflictEdges;      /* #{ {v,u} in E : C[v]==C[u] }   (coloringMCMC_utils.cu:103-119,184-198) */
+	uint64_t violatingVertices;  /* #{ v : exists u in N(v), C[u]==C[v] }   (coloringMCMC_CPU.cpp:328-351) */
+	uint32_t usedColors;         /* #{ c : classSize[c] > 0 } */
+	uint32_t countsSweep;        /* colouring index the two counts above refer to (== sweep unless no sweep ran yet) */
+	uint64_t z;                  /* tail-cut threshold in force */
+} mcmcb200_status_t;
+
+typedef struct mcmcb200_handle mcmcb200_handle;
+
+/* Replaces Graph(Graph*) H2D copy (graph/graphGPU.cu:210-226) + ColoringMCMC ctor allocations
+ * (coloringMCMC_main.cu:5-60).  CSR as GraphStruct (graph/graph.h:37-45): cumulDegs[n+1], neighs[nnz] with
+ * nnz counting both directions.  Copies the CSR to the device. */
+int mcmcb200_create(mcmcb200_handle ** out, uint32_t n, uint64_t nnz, const uint32_t * cumulDegs,
+                    const uint32_t * neighs, const mcmcb200_params * p);
+
+/* Vertex-partitioned variant (one handle per GPU/rank): this handle owns global vertices [vBegin, vEnd) of an
+ * nGlobal-vertex graph.  cumulDegs holds vEnd-vBegin+1 entries (any base; differences are used), neighs the
+ * owned rows only, with GLOBAL neighbour ids.  The colour array is replicated (nGlobal entries). */
+int mcmcb200_create_partition(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd,
+                              const uint32_t * cumulDegs, const uint32_t * neighs, const mcmcb200_params * p);
+
+/* Same, adopting a CSR that already lives in DEVICE memory (no copy; the caller keeps it alive and unchanged
+ * until destroy).  d_cumulDegs[0] must be 0 and d_neighs must be 32-byte aligned and readable up to the next
+ * multiple of 8 elements (the sweep streams it with 256-bit loads). */
+int mcmcb200_create_device_csr(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd,
+                               uint64_t nnzLocal, const uint32_t * d_cumulDegs, const uint32_t * d_neighs,
+                               const mcmcb200_params * p);
+
+void mcmcb200_destroy(mcmcb200_handle * h);
+
+/* Replaces initColoring (coloringMCMC_utils.cu:24-33) / the ctor draw (coloringMCMC_CPU.cpp:54,61).
+ * colors == NULL: Philox uniform initial colouring (RNG contract above).  Otherwise n (nGlobal) host colours,
+ * each < nCol.  Resets sweep to 0, taboo to 0 and the replay position. */
+int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors);
+
+/* Replay mode (parity tests): sweep k (k = 0,1,...) draws u[k*n + v] for vertex v instead of Philox.
+ * sweeps == 0 or u == NULL returns to Philox. */
+int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps);
+
+/* Run up to k synchronous sweeps C_t -> C_{t+1} (the loop body of ColoringMCMC::run, coloringMCMC_main.cu:159-269,
+ * == ColoringMCMC_CPU::run, coloringMCMC_CPU.cpp:136-270), asynchronously on the handle's stream, with no host
+ * round trip in between.  A sweep that finds C_t converged leaves C_t current and turns the rest into no-ops. */
+int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k);
+
+/* Synchronises and reports the counters of the current colouring (replaces calcConflicts' D2H + host sum,
+ * coloringMCMC_utils.cu:184-198, and violation_count).  If no sweep has looked at the current colouring yet,
+ * a counting pass runs first. */
+int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out);
+
+int mcmcb200_get_colors(mcmcb200_handle * h, uint32_t * out /* [nGlobal] */);
+/* class sizes of the current colouring (replaces the D2H + host histogram of coloringMCMC_main.cu:211-214) */
+int mcmcb200_get_class_sizes(mcmcb200_handle * h, uint64_t * out /* [nCol] */);
+/* per-sweep history of the counters: out[2*t] = conflictEdges(C_t), out[2*t+1] = violatingVertices(C_t), t < count */
+int mcmcb200_get_history(mcmcb200_handle * h, uint64_t * out, uint32_t cap, uint32_t * count);
+
+/* Tail cutting (coloringMCMC_main.cu:271-290 + tailCutting<<<1,1>>>, coloringMCMC_utils.cu:73-101): greedy repair
+ * of the remaining conflicts, colours tried in ascending class size.  rounds returns the passes used. */
+int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds);
+
+/* -------- parity / debug -------- */
+/* Pure function of a colouring, evaluated by the sweep kernel's own counting path on the handle's graph. */
+int mcmcb200_conflicts_of(mcmcb200_handle * h, const uint32_t * colors, uint64_t * edges, uint64_t * vertices);
+/* Occupancy bitmask of vertex v (global id, must be owned) w.r.t. the current colouring, as built by the sweep
+ * kernel: bit c of word c/32 set iff a neighbour has colour c.  words = ceil(nCol/32). */
+int mcmcb200_debug_occupancy(mcmcb200_handle * h, uint32_t v, uint32_t * maskWords);
+/* All owned vertices at once: masks[(v-vBegin)*words64 + w] (64-bit words, words64 = ceil(nCol/64)) and
+ * same[v-vBegin] = number of neighbours sharing v's colour. */
+int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t * same);
+
+/* -------- multi-GPU plumbing (one process per GPU; the exchange itself is torch.distributed / NCCL) -------- */
+enum { MCMCB200_VIEW_COLORS_CUR = 0,   /* device colour array of the current colouring (element size below) */
+       MCMCB200_VIEW_COLORS_NEXT = 1,  /* device colour array the next sweep writes (owned slice only) */
+       MCMCB200_VIEW_COUNTERS = 2 };   /* int64[2 + nCol]: directed conflicts, violating vertices, class-size deltas */
+int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_t * bytes, uint32_t * elemBytes);
+/* With MCMCB200_FLAG_NO_FUSED_FINALIZE: mcmcb200_sweep(h,1) stops after the local pass; the caller all-gathers the
+ * NEXT colour slices, all-reduces COUNTERS (both on mcmcb200_stream) and then calls mcmcb200_finalize_sweep. */
+int mcmcb200_finalize_sweep(mcmcb200_handle * h);
+int mcmcb200_stream(mcmcb200_handle * h, void ** cudaStream);
+int mcmcb200_synchronize(mcmcb200_handle * h);
+/* elapsed milliseconds (CUDA events on the handle's stream) of the kernels launched by the last mcmcb200_sweep */
+int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms);
+/* number of kernels this library launched on behalf of the handle so far */
+int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches);
+
+const char * mcmcb200_strerror(int code);
+const char * mcmcb200_last_cuda_error(void);
+int mcmcb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMCB200_H */

@@ -1,0 +1,77 @@
+// Device helpers: Philox4x32-10, cache-hinted loads, warp reductions.  sm_100a only.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcmcb200 {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Stateless: replaces the 48-byte-per-vertex curandState of
+// the reference (GPUutils/GPURandomizer.cu:8-13) -- 0 bytes of RNG state traffic per sweep.
+// counter = (vertex, purpose, sweep, 0), key = (seed_lo, seed_hi); word 0 is the draw (include/mcmcb200.h).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint32_t sweep, uint32_t vertex, uint32_t purpose) {
+	uint32_t c0 = vertex, c1 = purpose, c2 = sweep, c3 = 0u;
+	uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+	for (int r = 0; r < 10; ++r) {
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	return c0;
+}
+
+// u in [0,1) (UNIFORM, like uniform_real_distribution<float>) or (0,1] (DYNAMIC, like curand_uniform)
+__device__ __forceinline__ float draw_to_uniform(uint32_t x, bool openAtZero) {
+	const uint32_t m = (x >> 8) + (openAtZero ? 1u : 0u);
+	return __uint2float_rn(m) * 5.9604644775390625e-8f;   // exact: m <= 2^24, power-of-two scale
+}
+
+// ---------------------------------------------------------------------------------------------
+// Loads.  The CSR neighbour stream is read exactly once per sweep: 256-bit, L1 no-allocate, L2 evict-first
+// (SASS: LDG.E.NA.EFL2.256.CONSTANT).  The colour gathers are the only data with reuse: L2 evict-last policy.
+// ---------------------------------------------------------------------------------------------
+struct U32x8 { uint32_t v[8]; };
+
+__device__ __forceinline__ U32x8 ld_stream_256(const uint32_t * p /* 32-byte aligned */) {
+	U32x8 r;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+		: "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+template <typename ColT> __device__ __forceinline__ uint32_t ld_color(const ColT * p, uint64_t pol);
+template <> __device__ __forceinline__ uint32_t ld_color<uint8_t>(const uint8_t * p, uint64_t pol) {
+	uint32_t r;
+	asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+	return r;
+}
+template <> __device__ __forceinline__ uint32_t ld_color<uint16_t>(const uint16_t * p, uint64_t pol) {
+	uint32_t r;
+	asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+	return r;
+}
+
+__device__ __forceinline__ uint64_t warp_reduce_or64(uint64_t x) {
+	const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)x);
+	const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32));
+	return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ uint64_t warp_reduce_add64(uint64_t x) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+	return x;
+}
+
+} // namespace mcmcb200

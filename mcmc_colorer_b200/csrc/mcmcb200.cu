@@ -1,0 +1,636 @@
+// libmcmcb200.so -- C ABI (include/mcmcb200.h) over the sm_100a sweep kernels.  No torch types, no CPU fallback.
+#include "../../include/mcmcb200.h"
+#include "sweep_kernel.cuh"
+#include "tailcut_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace mcmcb200;
+
+static_assert(sizeof(mcmcb200_params) == 56, "ABI: mcmcb200_params layout (mirrored by capi.Params)");
+static_assert(sizeof(mcmcb200_status_t) == 40, "ABI: mcmcb200_status_t layout (mirrored by capi.Status)");
+
+namespace {
+
+thread_local char g_lastCudaError[512] = "";
+
+int cuda_fail(cudaError_t e, const char * what, int line) {
+	snprintf(g_lastCudaError, sizeof(g_lastCudaError), "%s failed at mcmcb200.cu:%d: %s (%s)", what, line,
+	         cudaGetErrorName(e), cudaGetErrorString(e));
+	return (e == cudaErrorMemoryAllocation) ? MCMCB200_ENOMEM
+	     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? MCMCB200_ENODEVICE
+	     : MCMCB200_ECUDA;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__); } while (0)
+
+constexpr uint32_t kColorPad = 65536;   // slack so equal-sized all-gather chunks always fit
+
+} // namespace
+
+struct mcmcb200_handle {
+	mcmcb200_params p{};
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint32_t nGlobal = 0, vBegin = 0, vEnd = 0, nLocal = 0;
+	uint64_t nnzLocal = 0;
+	int W = 1, colBytes = 1;
+	uint32_t * d_rowptr = nullptr;
+	uint32_t * d_neighs = nullptr;
+	bool ownsCsr = true;
+	void * d_colors[2] = {nullptr, nullptr};
+	void * d_colorsTmp = nullptr;        // conflicts_of scratch colouring
+	uint16_t * d_taboo = nullptr;
+	float * d_tape = nullptr;
+	uint32_t tapeSweeps = 0, tapeBase = 0;
+	DevState * d_state = nullptr;
+	unsigned long long * d_scratch = nullptr, * d_hist[2] = {nullptr, nullptr}, * d_history = nullptr, * d_countOut = nullptr;
+	uint32_t historyCap = 0;
+	uint32_t * d_stage32 = nullptr;      // nGlobal u32 staging for the uint32 host interface
+	uint32_t * h_pinned = nullptr;       // pinned bounce buffer for colours (nGlobal u32)
+	bool colorsInit = false;
+	bool pendingCountOnly = false;
+	uint32_t hostSweepUpper = 0;         // upper bound of the device-side sweep index
+	int gridBlocks = 0;
+	size_t smemBytes = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool timed = false;
+	uint64_t launches = 0;
+	uint64_t z = 0;
+	int smCount = 0;
+};
+
+namespace {
+
+template <int W, typename ColT>
+cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
+	sweep_kernel<W, ColT><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a) {
+	h->launches++;
+	switch (h->W) {
+	case 1: return launch_sweep_t<1, uint8_t>(h, a);
+	case 2: return launch_sweep_t<2, uint8_t>(h, a);
+	case 4: return launch_sweep_t<4, uint8_t>(h, a);
+	default: return launch_sweep_t<8, uint16_t>(h, a);
+	}
+}
+
+template <int W, typename ColT>
+cudaError_t occupancy_t(int * blocks, size_t smem) {
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, sweep_kernel<W, ColT>, kThreads, smem);
+}
+
+cudaError_t sweep_occupancy(mcmcb200_handle * h, int * blocks) {
+	switch (h->W) {
+	case 1: return occupancy_t<1, uint8_t>(blocks, h->smemBytes);
+	case 2: return occupancy_t<2, uint8_t>(blocks, h->smemBytes);
+	case 4: return occupancy_t<4, uint8_t>(blocks, h->smemBytes);
+	default: return occupancy_t<8, uint16_t>(blocks, h->smemBytes);
+	}
+}
+
+SweepArgs make_args(mcmcb200_handle * h) {
+	SweepArgs a{};
+	a.rowptr = h->d_rowptr; a.neighs = h->d_neighs;
+	a.nLocal = h->nLocal; a.vBegin = h->vBegin; a.nGlobal = h->nGlobal; a.nCol = h->p.nCol;
+	a.numTiles = (h->nLocal + kTileV - 1) / kTileV;
+	a.eps = h->p.epsilon; a.tabooIter = h->p.tabooIteration; a.proposal = h->p.proposal; a.seed = h->p.seed;
+	a.colors[0] = h->d_colors[0]; a.colors[1] = h->d_colors[1];
+	a.colorsOverride = nullptr;
+	a.taboo = h->d_taboo;
+	a.tape = h->tapeSweeps ? h->d_tape : nullptr; a.tapeBase = h->tapeBase;
+	a.st = h->d_state; a.scratch = h->d_scratch; a.hist[0] = h->d_hist[0]; a.hist[1] = h->d_hist[1];
+	a.history = h->d_history; a.historyCap = h->historyCap;
+	a.countOnly = 0; a.countOut = nullptr;
+	a.fuseFinalize = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) ? 0u : 1u;
+	a.noEarlyStop = (h->p.flags & MCMCB200_FLAG_NO_EARLY_STOP) ? 1u : 0u;
+	a.dbgMasks = nullptr; a.dbgSame = nullptr;
+	return a;
+}
+
+int check_params(const mcmcb200_params * p, uint32_t nGlobal) {
+	if (!p || p->nCol == 0 || nGlobal == 0) return MCMCB200_EINVAL;
+	if (p->proposal > 1u || p->convergence > 1u) return MCMCB200_EINVAL;
+	if (!(p->epsilon >= 0.0f)) return MCMCB200_EINVAL;
+	if (p->nCol > 64u * kMaxColWords) return MCMCB200_EUNSUPPORTED;   // wide-palette path: not in this build
+	if (p->tabooIteration > 65535u) return MCMCB200_EUNSUPPORTED;
+	if (p->proposal == MCMCB200_PROPOSAL_DYNAMIC && p->nCol < 2) return MCMCB200_EINVAL;
+	return MCMCB200_OK;
+}
+
+int select_device(const mcmcb200_params * p, int * devOut, int * smCount) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "no CUDA device: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return MCMCB200_ENODEVICE;
+	}
+	int dev = p->device;
+	if (dev < 0) CU(cudaGetDevice(&dev));
+	if (dev >= count) return MCMCB200_ENODEVICE;
+	CU(cudaSetDevice(dev));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major != 10) {   // the library holds sm_100a SASS only
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "device %d is sm_%d%d; libmcmcb200 is built for sm_100a only",
+		         dev, prop.major, prop.minor);
+		return MCMCB200_ENODEVICE;
+	}
+	*devOut = dev; *smCount = prop.multiProcessorCount;
+	return MCMCB200_OK;
+}
+
+// common tail of the three create variants: everything except the CSR
+int alloc_chain_state(mcmcb200_handle * h) {
+	const uint32_t nCol = h->p.nCol;
+	h->W = nCol <= 64 ? 1 : nCol <= 128 ? 2 : nCol <= 256 ? 4 : 8;
+	h->colBytes = nCol <= 256 ? 1 : 2;
+	h->z = h->p.tailcut ? std::max<uint64_t>(50, h->nGlobal / 2000) : 0;   // coloringMCMC_main.cu:150-157
+	h->historyCap = std::max<uint32_t>(h->p.maxRip + 2u, 1024u);
+	CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+	const size_t colElems = (size_t)h->nGlobal + kColorPad;
+	for (int i = 0; i < 2; ++i) {
+		CU(cudaMalloc(&h->d_colors[i], colElems * h->colBytes));
+		CU(cudaMemsetAsync(h->d_colors[i], 0, colElems * h->colBytes, h->stream));
+	}
+	if (h->p.tabooIteration) CU(cudaMalloc(&h->d_taboo, sizeof(uint16_t) * std::max<size_t>(h->nLocal, 1)));
+	CU(cudaMalloc(&h->d_state, sizeof(DevState)));
+	CU(cudaMalloc(&h->d_scratch, sizeof(unsigned long long) * (nCol + 2)));
+	CU(cudaMalloc(&h->d_hist[0], sizeof(unsigned long long) * nCol));
+	CU(cudaMalloc(&h->d_hist[1], sizeof(unsigned long long) * nCol));
+	CU(cudaMalloc(&h->d_history, sizeof(unsigned long long) * 2 * h->historyCap));
+	CU(cudaMalloc(&h->d_countOut, sizeof(unsigned long long) * 2));
+	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (nCol + 2), h->stream));
+	CU(cudaMemsetAsync(h->d_history, 0, sizeof(unsigned long long) * 2 * h->historyCap, h->stream));
+	h->smemBytes = sweep_smem_bytes(nCol, h->W, h->colBytes);
+	int perSM = 0;
+	CU(sweep_occupancy(h, &perSM));
+	if (perSM < 1) return MCMCB200_EUNSUPPORTED;
+	const uint32_t numTiles = (h->nLocal + kTileV - 1) / kTileV;
+	h->gridBlocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>(numTiles, (uint32_t)(perSM * h->smCount)));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int reset_state(mcmcb200_handle * h) {
+	DevState s{};
+	s.sweep = 0; s.convergedAt = -1; s.ticket = 0; s.tileCounter = 0;
+	s.convergence = h->p.convergence; s.countsSweep = 0xffffffffu; s.z = h->z;
+	s.lastDirected = 0; s.lastViol = 0; s.errorFlag = 0;
+	CU(cudaMemcpyAsync(h->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (h->p.nCol + 2), h->stream));
+	if (h->d_taboo) CU(cudaMemsetAsync(h->d_taboo, 0, sizeof(uint16_t) * std::max<size_t>(h->nLocal, 1), h->stream));
+	h->hostSweepUpper = 0; h->tapeBase = 0; h->pendingCountOnly = false;
+	return MCMCB200_OK;
+}
+
+int ensure_stage(mcmcb200_handle * h) {
+	if (!h->d_stage32) CU(cudaMalloc(&h->d_stage32, sizeof(uint32_t) * (size_t)h->nGlobal));
+	return MCMCB200_OK;
+}
+
+int narrow_into(mcmcb200_handle * h, const uint32_t * hostColors, void * dst) {
+	int rc = ensure_stage(h); if (rc) return rc;
+	CU(cudaMemcpyAsync(h->d_stage32, hostColors, sizeof(uint32_t) * (size_t)h->nGlobal, cudaMemcpyHostToDevice, h->stream));
+	const uint32_t n = h->nGlobal, blocks = (n + 255) / 256;
+	if (h->colBytes == 1) narrow_colors_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>(h->d_stage32, (uint8_t *)dst, n, h->p.nCol, h->d_state);
+	else narrow_colors_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>(h->d_stage32, (uint16_t *)dst, n, h->p.nCol, h->d_state);
+	h->launches++;
+	CU(cudaGetLastError());
+	return MCMCB200_OK;
+}
+
+int compute_class_sizes(mcmcb200_handle * h, const void * colors, unsigned long long * hist) {
+	CU(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * h->p.nCol, h->stream));
+	const int blocks = std::max(1, std::min<int>(h->smCount * 4, (int)((h->nGlobal + 255) / 256)));
+	const size_t smem = sizeof(unsigned int) * h->p.nCol;
+	if (h->colBytes == 1) class_sizes_kernel<uint8_t><<<blocks, 256, smem, h->stream>>>((const uint8_t *)colors, h->nGlobal, h->p.nCol, hist);
+	else class_sizes_kernel<uint16_t><<<blocks, 256, smem, h->stream>>>((const uint16_t *)colors, h->nGlobal, h->p.nCol, hist);
+	h->launches++;
+	CU(cudaGetLastError());
+	return MCMCB200_OK;
+}
+
+int read_state(mcmcb200_handle * h, DevState * s) {
+	CU(cudaMemcpyAsync(s, h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd, uint64_t nnzLocal,
+                  const uint32_t * cumulDegs, const uint32_t * neighs /* first owned edge */, bool deviceCsr,
+                  const mcmcb200_params * p) {
+	if (!out) return MCMCB200_EINVAL;
+	*out = nullptr;
+	int rc = check_params(p, nGlobal); if (rc) return rc;
+	if (vBegin > vEnd || vEnd > nGlobal || !cumulDegs || (nnzLocal && !neighs)) return MCMCB200_EINVAL;
+	if (nnzLocal >= 0xfffffff0ull) return MCMCB200_EUNSUPPORTED;   // 32-bit CSR offsets, like the reference (graph.h:19-20)
+	int dev = 0, sms = 0;
+	rc = select_device(p, &dev, &sms); if (rc) return rc;
+	mcmcb200_handle * h = new (std::nothrow) mcmcb200_handle;
+	if (!h) return MCMCB200_ENOMEM;
+	h->p = *p; h->device = dev; h->smCount = sms;
+	h->nGlobal = nGlobal; h->vBegin = vBegin; h->vEnd = vEnd; h->nLocal = vEnd - vBegin; h->nnzLocal = nnzLocal;
+	auto fail = [&](int code) { mcmcb200_destroy(h); return code; };
+	if (deviceCsr) {
+		if ((reinterpret_cast<uintptr_t>(neighs) & 31u) != 0) return fail(MCMCB200_EINVAL);
+		h->ownsCsr = false;
+		h->d_rowptr = const_cast<uint32_t *>(cumulDegs);
+		h->d_neighs = const_cast<uint32_t *>(neighs);
+	} else {
+		h->ownsCsr = true;
+		// rebase the offsets to 0 and validate monotonicity / ids on the host (cheap, once)
+		std::vector<uint32_t> rp((size_t)h->nLocal + 1);
+		const uint32_t base = cumulDegs[0];
+		for (size_t i = 0; i <= h->nLocal; ++i) {
+			if (cumulDegs[i] < base || (i && cumulDegs[i] < cumulDegs[i - 1])) return fail(MCMCB200_EINVAL);
+			rp[i] = cumulDegs[i] - base;
+		}
+		if (rp[h->nLocal] != nnzLocal) return fail(MCMCB200_EINVAL);
+		for (uint64_t e = 0; e < nnzLocal; ++e) if (neighs[e] >= nGlobal) return fail(MCMCB200_EINVAL);
+		cudaError_t e1 = cudaMalloc(&h->d_rowptr, sizeof(uint32_t) * ((size_t)h->nLocal + 1));
+		if (e1 != cudaSuccess) return fail(cuda_fail(e1, "cudaMalloc(rowptr)", __LINE__));
+		const size_t padded = ((size_t)nnzLocal + 15) & ~(size_t)7;   // 256-bit loads may touch up to 7 ids past the end
+		e1 = cudaMalloc(&h->d_neighs, sizeof(uint32_t) * std::max<size_t>(padded, 8));
+		if (e1 != cudaSuccess) return fail(cuda_fail(e1, "cudaMalloc(neighs)", __LINE__));
+		e1 = cudaMemset(h->d_neighs, 0, sizeof(uint32_t) * std::max<size_t>(padded, 8));
+		if (e1 == cudaSuccess) e1 = cudaMemcpy(h->d_rowptr, rp.data(), sizeof(uint32_t) * rp.size(), cudaMemcpyHostToDevice);
+		if (e1 == cudaSuccess && nnzLocal) e1 = cudaMemcpy(h->d_neighs, neighs, sizeof(uint32_t) * nnzLocal, cudaMemcpyHostToDevice);
+		if (e1 != cudaSuccess) return fail(cuda_fail(e1, "CSR upload", __LINE__));
+	}
+	rc = alloc_chain_state(h);
+	if (rc) return fail(rc);
+	rc = reset_state(h);
+	if (rc) return fail(rc);
+	*out = h;
+	return MCMCB200_OK;
+}
+
+int run_count_pass(mcmcb200_handle * h, const void * overrideColors, unsigned long long * countOut,
+                   unsigned long long * dbgMasks, uint32_t * dbgSame) {
+	SweepArgs a = make_args(h);
+	a.countOnly = 1; a.colorsOverride = overrideColors; a.countOut = countOut;
+	a.dbgMasks = dbgMasks; a.dbgSame = dbgSame; a.fuseFinalize = 1; a.tape = nullptr;
+	CU(launch_sweep(h, a));
+	return MCMCB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int mcmcb200_abi_version(void) { return MCMCB200_ABI_VERSION; }
+
+const char * mcmcb200_last_cuda_error(void) { return g_lastCudaError; }
+
+const char * mcmcb200_strerror(int code) {
+	switch (code) {
+	case MCMCB200_OK: return "ok";
+	case MCMCB200_EINVAL: return "invalid argument";
+	case MCMCB200_ENODEVICE: return "no usable sm_100a CUDA device (libmcmcb200 has no CPU fallback)";
+	case MCMCB200_ECUDA: return "CUDA runtime error (see mcmcb200_last_cuda_error)";
+	case MCMCB200_ENOMEM: return "out of memory";
+	case MCMCB200_EUNSUPPORTED: return "configuration not supported by this build";
+	case MCMCB200_ETAPE: return "replay tape exhausted";
+	case MCMCB200_ESTATE: return "call out of order";
+	default: return "unknown error";
+	}
+}
+
+int mcmcb200_create(mcmcb200_handle ** out, uint32_t n, uint64_t nnz, const uint32_t * cumulDegs,
+                    const uint32_t * neighs, const mcmcb200_params * p) {
+	if (!cumulDegs) return MCMCB200_EINVAL;
+	return create_common(out, n, 0, n, nnz, cumulDegs, neighs ? neighs + cumulDegs[0] : nullptr, false, p);
+}
+
+int mcmcb200_create_partition(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd,
+                              const uint32_t * cumulDegs, const uint32_t * neighs, const mcmcb200_params * p) {
+	if (!cumulDegs || vBegin > vEnd) return MCMCB200_EINVAL;
+	const uint64_t nnzLocal = (uint64_t)cumulDegs[vEnd - vBegin] - cumulDegs[0];
+	return create_common(out, nGlobal, vBegin, vEnd, nnzLocal, cumulDegs, neighs, false, p);
+}
+
+int mcmcb200_create_device_csr(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd,
+                               uint64_t nnzLocal, const uint32_t * d_cumulDegs, const uint32_t * d_neighs,
+                               const mcmcb200_params * p) {
+	return create_common(out, nGlobal, vBegin, vEnd, nnzLocal, d_cumulDegs, d_neighs, true, p);
+}
+
+void mcmcb200_destroy(mcmcb200_handle * h) {
+	if (!h) return;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->ownsCsr) { cudaFree(h->d_rowptr); cudaFree(h->d_neighs); }
+	cudaFree(h->d_colors[0]); cudaFree(h->d_colors[1]); cudaFree(h->d_colorsTmp); cudaFree(h->d_taboo);
+	cudaFree(h->d_tape); cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
+	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
+	if (h->h_pinned) cudaFreeHost(h->h_pinned);
+	if (h->ev0) cudaEventDestroy(h->ev0);
+	if (h->ev1) cudaEventDestroy(h->ev1);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	cudaGetLastError();
+	delete h;
+}
+
+int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors) {
+	if (!h) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	int rc = reset_state(h); if (rc) return rc;
+	if (colors) {
+		rc = narrow_into(h, colors, h->d_colors[0]); if (rc) return rc;
+	} else {
+		const uint32_t n = h->nGlobal, blocks = (n + 255) / 256;
+		if (h->colBytes == 1) init_colors_philox_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>((uint8_t *)h->d_colors[0], n, h->p.nCol, h->p.seed);
+		else init_colors_philox_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>((uint16_t *)h->d_colors[0], n, h->p.nCol, h->p.seed);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	rc = compute_class_sizes(h, h->d_colors[0], h->d_hist[0]); if (rc) return rc;
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	if (s.errorFlag) { h->colorsInit = false; return MCMCB200_EINVAL; }   // a colour >= nCol
+	h->colorsInit = true;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps) {
+	if (!h) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	cudaFree(h->d_tape); h->d_tape = nullptr; h->tapeSweeps = 0;
+	if (!u || sweeps == 0) return MCMCB200_OK;
+	const size_t bytes = sizeof(float) * (size_t)sweeps * h->nGlobal;
+	CU(cudaMalloc(&h->d_tape, bytes));
+	CU(cudaMemcpy(h->d_tape, u, bytes, cudaMemcpyHostToDevice));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	h->tapeSweeps = sweeps; h->tapeBase = s.sweep;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k) {
+	if (!h) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
+	if (split && k != 1) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	CU(cudaEventRecord(h->ev0, h->stream));
+	for (uint32_t i = 0; i < k; ++i) {
+		if (h->tapeSweeps && (h->hostSweepUpper - h->tapeBase) >= h->tapeSweeps) {
+			CU(cudaEventRecord(h->ev1, h->stream)); h->timed = true;
+			return MCMCB200_ETAPE;
+		}
+		SweepArgs a = make_args(h);
+		CU(launch_sweep(h, a));
+		h->hostSweepUpper++;
+	}
+	CU(cudaEventRecord(h->ev1, h->stream));
+	h->timed = true;
+	h->pendingCountOnly = false;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_finalize_sweep(mcmcb200_handle * h) {
+	if (!h) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	SweepArgs a = make_args(h);
+	a.countOnly = h->pendingCountOnly ? 1u : 0u;
+	finalize_kernel<<<1, kThreads, 0, h->stream>>>(a);
+	h->launches++;
+	CU(cudaGetLastError());
+	h->pendingCountOnly = false;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
+	if (s.countsSweep != s.sweep) {
+		if (split) {
+			// multi-GPU: launch the local counting pass; the caller all-reduces COUNTERS, calls finalize_sweep and asks again
+			SweepArgs a = make_args(h);
+			a.countOnly = 1; a.fuseFinalize = 0; a.tape = nullptr;
+			CU(launch_sweep(h, a));
+			h->pendingCountOnly = true;
+			memset(out, 0, sizeof(*out));
+			out->sweep = s.sweep; out->countsSweep = 0xffffffffu; out->z = s.z;
+			return MCMCB200_OK;
+		}
+		rc = run_count_pass(h, nullptr, nullptr, nullptr, nullptr); if (rc) return rc;
+		rc = read_state(h, &s); if (rc) return rc;
+	}
+	std::vector<unsigned long long> hist(h->p.nCol);
+	CU(cudaMemcpyAsync(hist.data(), h->d_hist[s.sweep & 1], sizeof(unsigned long long) * h->p.nCol, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	uint32_t used = 0;
+	for (unsigned long long c : hist) used += c != 0;
+	out->sweep = s.sweep;
+	out->conflictEdges = s.lastDirected >> 1;
+	out->violatingVertices = s.lastViol;
+	out->usedColors = used;
+	out->countsSweep = s.countsSweep;
+	out->z = s.z;
+	const uint64_t metric = s.convergence == 0 ? s.lastViol : (s.lastDirected >> 1);
+	out->converged = metric <= s.z ? 1 : 0;
+	if (s.errorFlag) return MCMCB200_EINVAL;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_colors(mcmcb200_handle * h, uint32_t * out) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	rc = ensure_stage(h); if (rc) return rc;
+	const uint32_t n = h->nGlobal, blocks = (n + 255) / 256;
+	if (h->colBytes == 1) widen_colors_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>((const uint8_t *)h->d_colors[s.sweep & 1], h->d_stage32, n);
+	else widen_colors_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>((const uint16_t *)h->d_colors[s.sweep & 1], h->d_stage32, n);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, h->d_stage32, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_class_sizes(mcmcb200_handle * h, uint64_t * out) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	CU(cudaMemcpyAsync(out, h->d_hist[s.sweep & 1], sizeof(uint64_t) * h->p.nCol, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_history(mcmcb200_handle * h, uint64_t * out, uint32_t cap, uint32_t * count) {
+	if (!h || !out || !count) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	uint32_t have = (s.countsSweep == 0xffffffffu) ? 0u : std::min<uint32_t>(s.countsSweep + 1u, h->historyCap);
+	have = std::min(have, cap);
+	if (have) CU(cudaMemcpy(out, h->d_history, sizeof(uint64_t) * 2 * have, cudaMemcpyDeviceToHost));
+	*count = have;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_conflicts_of(mcmcb200_handle * h, const uint32_t * colors, uint64_t * edges, uint64_t * vertices) {
+	if (!h || !colors) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	if (!h->d_colorsTmp) CU(cudaMalloc(&h->d_colorsTmp, ((size_t)h->nGlobal + kColorPad) * h->colBytes));
+	CU(cudaStreamSynchronize(h->stream));
+	uint32_t zero = 0;
+	CU(cudaMemcpyAsync(&h->d_state->errorFlag, &zero, sizeof(zero), cudaMemcpyHostToDevice, h->stream));
+	int rc = narrow_into(h, colors, h->d_colorsTmp); if (rc) return rc;
+	rc = run_count_pass(h, h->d_colorsTmp, h->d_countOut, nullptr, nullptr); if (rc) return rc;
+	unsigned long long res[2];
+	CU(cudaMemcpyAsync(res, h->d_countOut, sizeof(res), cudaMemcpyDeviceToHost, h->stream));
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	if (s.errorFlag) {
+		CU(cudaMemcpy(&h->d_state->errorFlag, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+		return MCMCB200_EINVAL;
+	}
+	const bool whole = h->vBegin == 0 && h->vEnd == h->nGlobal;
+	if (edges) *edges = whole ? (res[0] >> 1) : res[0];   // a partition reports its directed count (sum over ranks = 2*edges)
+	if (vertices) *vertices = res[1];
+	return MCMCB200_OK;
+}
+
+int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t * same) {
+	if (!h || !masks || !same) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	unsigned long long * d_m = nullptr; uint32_t * d_s = nullptr;
+	const size_t nm = (size_t)std::max<uint32_t>(h->nLocal, 1) * h->W;
+	CU(cudaMalloc(&d_m, sizeof(unsigned long long) * nm));
+	cudaError_t e = cudaMalloc(&d_s, sizeof(uint32_t) * std::max<uint32_t>(h->nLocal, 1));
+	if (e != cudaSuccess) { cudaFree(d_m); return cuda_fail(e, "cudaMalloc(dbgSame)", __LINE__); }
+	DevState s;
+	int rc = read_state(h, &s);
+	if (!rc) rc = run_count_pass(h, h->d_colors[s.sweep & 1], h->d_countOut, d_m, d_s);
+	if (!rc) {
+		e = cudaStreamSynchronize(h->stream);
+		if (e == cudaSuccess) e = cudaMemcpy(masks, d_m, sizeof(unsigned long long) * (size_t)h->nLocal * h->W, cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess) e = cudaMemcpy(same, d_s, sizeof(uint32_t) * h->nLocal, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) rc = cuda_fail(e, "debug copy", __LINE__);
+	}
+	cudaFree(d_m); cudaFree(d_s);
+	return rc;
+}
+
+int mcmcb200_debug_occupancy(mcmcb200_handle * h, uint32_t v, uint32_t * maskWords) {
+	if (!h || !maskWords || v < h->vBegin || v >= h->vEnd) return MCMCB200_EINVAL;
+	std::vector<uint64_t> masks((size_t)h->nLocal * h->W);
+	std::vector<uint32_t> same(h->nLocal);
+	int rc = mcmcb200_debug_all_occupancy(h, masks.data(), same.data()); if (rc) return rc;
+	const uint32_t words = (h->p.nCol + 31) / 32;
+	for (uint32_t w = 0; w < words; ++w) {
+		const uint64_t m = masks[(size_t)(v - h->vBegin) * h->W + (w >> 1)];
+		maskWords[w] = (uint32_t)(m >> (32 * (w & 1)));
+	}
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds) {
+	if (!h) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	if (h->vBegin != 0 || h->vEnd != h->nGlobal) return MCMCB200_EUNSUPPORTED;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	void * cur = h->d_colors[s.sweep & 1];
+	unsigned long long * hist = h->d_hist[s.sweep & 1];
+	const uint32_t nCol = h->p.nCol, n = h->nLocal;
+	// colours in ascending class size (coloringMCMC_main.cu:272-277); ties by colour index (contract)
+	std::vector<unsigned long long> hh(nCol);
+	CU(cudaMemcpy(hh.data(), hist, sizeof(unsigned long long) * nCol, cudaMemcpyDeviceToHost));
+	std::vector<uint32_t> order(nCol);
+	for (uint32_t i = 0; i < nCol; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hh[a] < hh[b]; });
+	uint32_t * d_order = nullptr, * d_list = nullptr, * d_counters = nullptr; uint8_t * d_pending = nullptr, * d_ready = nullptr;
+	auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_list); cudaFree(d_counters); cudaFree(d_pending); cudaFree(d_ready); };
+	cudaError_t e = cudaMalloc(&d_order, sizeof(uint32_t) * nCol);
+	if (e == cudaSuccess) e = cudaMalloc(&d_list, sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+	if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(uint32_t) * 2);
+	if (e == cudaSuccess) e = cudaMalloc(&d_pending, std::max<uint32_t>(n, 1));
+	if (e == cudaSuccess) e = cudaMalloc(&d_ready, std::max<uint32_t>(n, 1));
+	if (e == cudaSuccess) e = cudaMemcpy(d_order, order.data(), sizeof(uint32_t) * nCol, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "tailcut workspace", __LINE__); }
+	uint32_t used = 0;
+	for (; used < maxRounds; ++used) {                                     // while (conflictCounter > 0), _main.cu:279
+		uint32_t flagged = 0;
+		const int ce = launch_tailcut_pass(h->stream, h->colBytes, h->d_rowptr, h->d_neighs, n, nCol, cur, hist, d_order,
+		                                   d_pending, d_ready, d_list, d_counters, &flagged, &h->launches);
+		if (ce) { cleanup(); return cuda_fail((cudaError_t)ce, "tailcut pass", __LINE__); }
+		if (flagged == 0) break;                                           // no conflicting edge left
+	}
+	cleanup();
+	// the colouring changed under the counters: force a recount at the next status
+	const uint32_t stale = 0xffffffffu; const int32_t notConv = -1;
+	CU(cudaMemcpyAsync(&h->d_state->countsSweep, &stale, sizeof(stale), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(&h->d_state->convergedAt, &notConv, sizeof(notConv), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	if (rounds) *rounds = used;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_t * bytes, uint32_t * elemBytes) {
+	if (!h || !devPtr) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	const uint64_t colBytesTotal = ((uint64_t)h->nGlobal + kColorPad) * h->colBytes;
+	switch (which) {
+	case MCMCB200_VIEW_COLORS_CUR:  *devPtr = h->d_colors[s.sweep & 1]; if (bytes) *bytes = colBytesTotal; if (elemBytes) *elemBytes = h->colBytes; break;
+	case MCMCB200_VIEW_COLORS_NEXT: *devPtr = h->d_colors[(s.sweep + 1) & 1]; if (bytes) *bytes = colBytesTotal; if (elemBytes) *elemBytes = h->colBytes; break;
+	case MCMCB200_VIEW_COUNTERS:    *devPtr = h->d_scratch; if (bytes) *bytes = sizeof(unsigned long long) * (h->p.nCol + 2); if (elemBytes) *elemBytes = 8; break;
+	default: return MCMCB200_EINVAL;
+	}
+	return MCMCB200_OK;
+}
+
+int mcmcb200_stream(mcmcb200_handle * h, void ** cudaStreamOut) {
+	if (!h || !cudaStreamOut) return MCMCB200_EINVAL;
+	*cudaStreamOut = (void *)h->stream;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_synchronize(mcmcb200_handle * h) {
+	if (!h) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms) {
+	if (!h || !ms) return MCMCB200_EINVAL;
+	if (!h->timed) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	CU(cudaEventSynchronize(h->ev1));
+	CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches) {
+	if (!h || !launches) return MCMCB200_EINVAL;
+	*launches = h->launches;
+	return MCMCB200_OK;
+}
+
+} // extern "C"

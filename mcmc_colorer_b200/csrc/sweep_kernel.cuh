@@ -1,0 +1,497 @@
+// The fused MCMC sweep kernel (sm_100a).  One launch = one synchronous sweep C_t -> C_{t+1} over the owned
+// vertex range, including the convergence counters and the colour-class-size update -- no host round trip.
+//
+// Reference functions replaced by this one kernel (paths relative to reference src/):
+//   conflictCounter + sumReduction + host sum      graph_coloring/coloringMCMC_utils.cu:103-198
+//   cudaMemset(colorsChecker, n*nCol)              graph_coloring/coloringMCMC_main.cu:174
+//   D2H colouring + host histogram + H2D           graph_coloring/coloringMCMC_main.cu:211-214
+//   genDynamicDistribution                         graph_coloring/coloringMCMC_utils.cu:64-70
+//   selectStarColoring (UNIFORM)                   graph_coloring/coloringMCMC_standard.cu:9-82
+//   selectStarColoringBalanceDynamic (DYNAMIC)     graph_coloring/coloringMCMC_balance.cu:79-143
+//   CPU twin: count_free_colors / fill_p / extract_new_color / violation_count
+//                                                  graph_coloring/coloringMCMC_CPU.cpp:328-528
+//
+// Work decomposition ("degree binning" happens inside the kernel, per tile, no preprocessing pass):
+//   * persistent CTAs pull tiles of kTileV consecutive vertices from an atomic counter;
+//   * PHASE 1 (edge-parallel, CTA-wide): the tile's contiguous slice of `neighs` is streamed with 256-bit
+//     evict-first loads; every thread immediately gathers the colours of its 8 neighbours (evict-last hint,
+//     narrow u8/u16 colours) and parks them in shared memory in CSR order.  Perfectly coalesced and load
+//     balanced whatever the degree distribution;
+//   * PHASE 2 builds each vertex' neighbour-colour occupancy bitmask from shared memory:
+//       deg <= kLightMaxDeg  : one thread per vertex,
+//       deg <= kCapEdges     : one warp per vertex (ballot-free OR + __reduce_or_sync),
+//       deg >  kCapEdges     : whole CTA per vertex (hub), gathers straight from global;
+//   * PHASE 3 (thread per vertex): conflict flag, free-colour count (popc), taboo gate, Philox draw,
+//     sequential float32 CDF walk over the bitmask (bit-exact with the reference's running sum), colour write;
+//   * epilogue: warp-shuffle + one atomic per CTA for the counters, shared-memory class-size deltas, and the
+//     last CTA to finish applies the deltas, records the history and decides convergence on the device.
+#pragma once
+#include "device_utils.cuh"
+
+namespace mcmcb200 {
+
+constexpr int kThreads     = 256;   // threads per CTA
+constexpr int kTileV       = 256;   // vertices per tile (one per thread in phase 3)
+constexpr int kCapEdges    = 8192;  // neighbour colours staged per sub-tile
+constexpr int kLightMaxDeg = 64;    // thread-per-vertex up to here, warp-per-vertex above
+constexpr int kMaxColWords = 8;     // nCol <= 512 on the bitmask-in-registers path
+
+struct DevState {
+	uint32_t sweep;          // index t of the current colouring C_t
+	int32_t  convergedAt;    // -1, or t once the selected count of C_t was <= z
+	uint32_t ticket;         // CTAs finished in the running launch
+	uint32_t tileCounter;    // dynamic tile scheduler
+	uint32_t convergence;    // 0: violating vertices, 1: conflicting edges
+	uint32_t countsSweep;    // colouring index lastDirected/lastViol describe (0xffffffff: none)
+	uint64_t z;              // threshold
+	uint64_t lastDirected;   // sum_v #{u in N(v): C[u]==C[v]}  == 2 * conflicting edges
+	uint64_t lastViol;       // violating vertices
+	uint32_t errorFlag;      // sticky device-side error (colour out of range, ...)
+	uint32_t pad;
+};
+
+struct SweepArgs {
+	const uint32_t * rowptr;     // [nLocal+1], rowptr[0]==0
+	const uint32_t * neighs;     // owned rows, GLOBAL neighbour ids, 32-byte aligned
+	uint32_t nLocal, vBegin, nGlobal, nCol;
+	uint32_t numTiles;
+	float    eps;
+	uint32_t tabooIter;
+	uint32_t proposal;
+	uint64_t seed;
+	void *   colors[2];          // ColT[nGlobal (padded)], colouring t lives in colors[t&1]
+	const void * colorsOverride; // count-only: evaluate this colouring instead
+	uint16_t * taboo;            // [nLocal] or nullptr
+	const float * tape;          // [tapeSweeps][nGlobal] or nullptr
+	uint32_t tapeBase;           // sweep index of tape row 0
+	DevState * st;
+	unsigned long long * scratch; // [2 + nCol]: directed conflicts, violating vertices, class-size deltas (two's complement)
+	unsigned long long * hist[2]; // class sizes of colouring t in hist[t&1]
+	unsigned long long * history; // [historyCap][2]
+	uint32_t historyCap;
+	uint32_t countOnly;          // 1: counters only, nothing is modified
+	unsigned long long * countOut; // count-only result [2]
+	uint32_t fuseFinalize;       // last CTA runs finalize_sweep
+	uint32_t noEarlyStop;        // keep sweeping even when C_t is already proper (replay / benchmarking)
+	unsigned long long * dbgMasks; // optional [nLocal][W]
+	uint32_t * dbgSame;          // optional [nLocal]
+};
+
+__host__ __device__ inline size_t sweep_smem_bytes(uint32_t nCol, int W, int colBytes) {
+	size_t b = 0;
+	b += sizeof(uint32_t) * (kTileV + 4);                 // s_rp
+	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);  // s_S
+	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);      // s_dist
+	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);        // s_hist
+	b += sizeof(uint32_t) * kTileV;                       // s_same
+	b += sizeof(uint32_t) * 8;                            // s_ctl
+	b += sizeof(uint16_t) * kTileV;                       // s_heavy
+	b = (b + 15) & ~(size_t)15;
+	b += sizeof(unsigned long long) * (size_t)kTileV * W; // s_mask
+	b += (size_t)colBytes * (kCapEdges + 16);             // s_col
+	return (b + 15) & ~(size_t)15;
+}
+
+// finalize: executed by ONE CTA after all counters of the sweep are in `scratch` (fused: the last CTA of the
+// sweep kernel; multi-GPU: a 1-CTA kernel after the cross-rank all-reduce).
+__device__ __forceinline__ void finalize_sweep_device(const SweepArgs & a) {
+	DevState * st = a.st;
+	const unsigned long long directed = __ldcg(a.scratch + 0);
+	const unsigned long long viol = __ldcg(a.scratch + 1);
+	const uint32_t t = st->sweep;
+	if (a.countOut != nullptr) {                       // count-only on an arbitrary colouring
+		if (threadIdx.x == 0) { a.countOut[0] = directed; a.countOut[1] = viol; }
+	} else {
+		const unsigned long long metric = (st->convergence == 0) ? viol : (directed >> 1);
+		const bool conv = (metric <= st->z) && !a.noEarlyStop;
+		if (!a.countOnly && !conv) {
+			const unsigned long long * hc = a.hist[t & 1];
+			unsigned long long * hn = a.hist[(t + 1) & 1];
+			for (uint32_t k = threadIdx.x; k < a.nCol; k += blockDim.x) hn[k] = hc[k] + __ldcg(a.scratch + 2 + k);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			if (t < a.historyCap) { a.history[2 * (size_t)t] = directed >> 1; a.history[2 * (size_t)t + 1] = viol; }
+			st->lastDirected = directed; st->lastViol = viol; st->countsSweep = t;
+			if (!a.countOnly) {
+				if (conv) st->convergedAt = (int32_t)t;
+				else st->sweep = t + 1;
+			}
+		}
+	}
+	__syncthreads();
+	for (uint32_t k = threadIdx.x; k < a.nCol + 2; k += blockDim.x) a.scratch[k] = 0ull;
+	if (threadIdx.x == 0) { st->ticket = 0; st->tileCounter = 0; }
+}
+
+__global__ void finalize_kernel(SweepArgs a) { finalize_sweep_device(a); }
+
+template <int W, typename ColT>
+__global__ void __launch_bounds__(kThreads)
+sweep_kernel(const SweepArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const uint32_t nCol = a.nCol;
+	uint32_t * s_rp   = reinterpret_cast<uint32_t *>(smem_raw);
+	float *    s_S    = reinterpret_cast<float *>(s_rp + kTileV + 4);
+	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
+	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
+	uint32_t * s_same = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
+	uint32_t * s_ctl  = s_same + kTileV;
+	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8);
+	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + kTileV) - smem_raw);
+	off = (off + 15) & ~(size_t)15;
+	unsigned long long * s_mask = reinterpret_cast<unsigned long long *>(smem_raw + off);
+	ColT * s_col = reinterpret_cast<ColT *>(s_mask + (size_t)kTileV * W);
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	DevState * st = a.st;
+	if (!a.countOnly && st->convergedAt >= 0) return;      // converged earlier in this batch of launches: no-op
+
+	const uint32_t t = st->sweep;
+	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
+	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
+	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
+	const bool isDyn = a.proposal == 1u;
+	const float eps = a.eps;
+	// "stay" weight 1 - (nCol-1)*eps, two roundings like the reference's x86 build (coloringMCMC_CPU.cpp:406,474)
+	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
+	const uint64_t polLast = make_policy_evict_last();
+
+	// ---- prologue: per-CTA tables ----
+	for (uint32_t k = tid; k < nCol; k += kThreads) s_hist[k] = 0;
+	if (tid == 0) {   // S[k] = eps added k times sequentially (the running sum over k epsilon-weighted colours)
+		float s = 0.0f; s_S[0] = 0.0f;
+		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
+	}
+	if (isDyn && !a.countOnly) {   // genDynamicDistribution, coloringMCMC_utils.cu:69
+		const unsigned long long * hc = a.hist[t & 1];
+		const float nF = __uint2float_rn(a.nGlobal), dF = __uint2float_rn(nCol - 1u);
+		for (uint32_t k = tid; k < nCol; k += kThreads)
+			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(__uint2float_rn((uint32_t)hc[k]), nF)), dF);
+	}
+	unsigned long long accDirected = 0ull, accViol = 0ull;
+
+	// ---- persistent tile loop ----
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_ctl[0] = atomicAdd(&st->tileCounter, 1u);
+		__syncthreads();
+		const uint32_t tile = s_ctl[0];
+		if (tile >= a.numTiles) break;
+		const uint32_t v0 = tile * kTileV;
+		const uint32_t nv = min((uint32_t)kTileV, a.nLocal - v0);
+		for (uint32_t i = tid; i <= nv; i += kThreads) s_rp[i] = a.rowptr[v0 + i];
+		const bool haveV = (uint32_t)tid < nv;
+		const uint32_t gv = a.vBegin + v0 + tid;                   // global vertex id of this thread's slot
+		const uint32_t own = haveV ? (uint32_t)cur[gv] : 0u;
+		__syncthreads();
+		const uint32_t myBeg = haveV ? s_rp[tid] : 0u;
+		const uint32_t deg = haveV ? (s_rp[tid + 1] - myBeg) : 0u;
+
+		uint32_t done = 0;
+		while (done < nv) {
+			const uint32_t base = s_rp[done];
+			const bool fits = haveV && (uint32_t)tid >= done && (s_rp[tid + 1] - base) <= (uint32_t)kCapEdges;
+			const uint32_t cnt = __syncthreads_count(fits);
+
+			unsigned long long m[W];
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] = 0ull;
+			uint32_t same = 0;
+			bool mine;
+
+			if (cnt == 0) {
+				// ---------------- hub: one vertex, whole CTA, no staging ----------------
+				const uint32_t hubSlot = done;
+				const uint32_t hOwn = (uint32_t)cur[a.vBegin + v0 + hubSlot];
+				const uint32_t e0 = base, e1 = s_rp[hubSlot + 1];
+				if (tid < W) s_mask[(size_t)hubSlot * W + tid] = 0ull;
+				if (tid == 0) s_same[hubSlot] = 0u;
+				__syncthreads();
+				for (uint32_t e = e0 + tid; e < e1; e += kThreads) {
+					const uint32_t c = ld_color<ColT>(cur + a.neighs[e], polLast);
+					same += (c == hOwn);
+#pragma unroll
+					for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+				}
+#pragma unroll
+				for (int w = 0; w < W; ++w) {
+					const unsigned long long r = warp_reduce_or64(m[w]);
+					if (lane == 0 && r) atomicOr(&s_mask[(size_t)hubSlot * W + w], r);
+				}
+				same = __reduce_add_sync(0xffffffffu, same);
+				if (lane == 0 && same) atomicAdd(&s_same[hubSlot], same);
+				__syncthreads();
+				mine = (uint32_t)tid == hubSlot;
+				if (mine) {
+#pragma unroll
+					for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)hubSlot * W + w];
+					same = s_same[hubSlot];
+				}
+				done += 1;
+			} else {
+				// ---------------- PHASE 1: stream neighs, gather colours into shared memory ----------------
+				const uint32_t e0 = base, e1 = s_rp[done + cnt];
+				const uint32_t ea = e0 & ~7u;                       // 32-byte aligned start of the stream
+				const uint32_t nOct = (e1 - ea + 7u) >> 3;
+				for (uint32_t o = tid; o < nOct; o += 2 * kThreads) {
+					const uint32_t o2 = o + kThreads;
+					const bool has2 = o2 < nOct;
+					const U32x8 nbA = ld_stream_256(a.neighs + ea + 8u * o);
+					U32x8 nbB;
+					if (has2) nbB = ld_stream_256(a.neighs + ea + 8u * o2);
+					uint32_t cA[8], cB[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+						cA[j] = (ea + 8u * o + j < e1) ? ld_color<ColT>(cur + nbA.v[j], polLast) : 0u;
+					if (has2) {
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+							cB[j] = (ea + 8u * o2 + j < e1) ? ld_color<ColT>(cur + nbB.v[j], polLast) : 0u;
+					}
+					if (sizeof(ColT) == 1) {
+						uint2 pk;
+						pk.x = cA[0] | (cA[1] << 8) | (cA[2] << 16) | (cA[3] << 24);
+						pk.y = cA[4] | (cA[5] << 8) | (cA[6] << 16) | (cA[7] << 24);
+						*reinterpret_cast<uint2 *>(s_col + 8u * o) = pk;
+						if (has2) {
+							pk.x = cB[0] | (cB[1] << 8) | (cB[2] << 16) | (cB[3] << 24);
+							pk.y = cB[4] | (cB[5] << 8) | (cB[6] << 16) | (cB[7] << 24);
+							*reinterpret_cast<uint2 *>(s_col + 8u * o2) = pk;
+						}
+					} else {
+						uint4 pk;
+						pk.x = cA[0] | (cA[1] << 16); pk.y = cA[2] | (cA[3] << 16);
+						pk.z = cA[4] | (cA[5] << 16); pk.w = cA[6] | (cA[7] << 16);
+						*reinterpret_cast<uint4 *>(s_col + 8u * o) = pk;
+						if (has2) {
+							pk.x = cB[0] | (cB[1] << 16); pk.y = cB[2] | (cB[3] << 16);
+							pk.z = cB[4] | (cB[5] << 16); pk.w = cB[6] | (cB[7] << 16);
+							*reinterpret_cast<uint4 *>(s_col + 8u * o2) = pk;
+						}
+					}
+				}
+				if (tid == 0) s_ctl[1] = 0u;
+				__syncthreads();
+
+				// ---------------- PHASE 2a: thread-per-vertex masks (light) ----------------
+				mine = haveV && (uint32_t)tid >= done && (uint32_t)tid < done + cnt;
+				const bool heavy = mine && deg > (uint32_t)kLightMaxDeg;
+				if (mine && !heavy) {
+					const ColT * p = s_col + (myBeg - ea);
+					for (uint32_t i = 0; i < deg; ++i) {
+						const uint32_t c = p[i];
+						same += (c == own);
+						if (W == 1) m[0] |= 1ull << c;
+						else {
+#pragma unroll
+							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						}
+					}
+				} else if (heavy) {
+					s_heavy[atomicAdd(&s_ctl[1], 1u)] = (uint16_t)tid;
+				}
+				__syncthreads();
+				const uint32_t nHeavy = s_ctl[1];
+				// ---------------- PHASE 2b: warp-per-vertex masks (heavy) ----------------
+				if (nHeavy) {
+					for (uint32_t h = warp; h < nHeavy; h += kThreads / 32) {
+						const uint32_t slot = s_heavy[h];
+						const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
+						const uint32_t hOwn = (uint32_t)cur[a.vBegin + v0 + slot];
+						const ColT * p = s_col + (hb - ea);
+						unsigned long long hm[W];
+#pragma unroll
+						for (int w = 0; w < W; ++w) hm[w] = 0ull;
+						uint32_t hs = 0;
+						for (uint32_t i = lane; i < hd; i += 32) {
+							const uint32_t c = p[i];
+							hs += (c == hOwn);
+#pragma unroll
+							for (int w = 0; w < W; ++w) hm[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						}
+#pragma unroll
+						for (int w = 0; w < W; ++w) {
+							const unsigned long long r = warp_reduce_or64(hm[w]);
+							if (lane == 0) s_mask[(size_t)slot * W + w] = r;
+						}
+						hs = __reduce_add_sync(0xffffffffu, hs);
+						if (lane == 0) s_same[slot] = hs;
+					}
+					__syncthreads();
+					if (heavy) {
+#pragma unroll
+						for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)tid * W + w];
+						same = s_same[tid];
+					}
+				}
+				done += cnt;
+			}
+
+			// ---------------- PHASE 3: thread-per-vertex proposal, draw, colour write ----------------
+			if (mine) {
+				const uint32_t slot = tid;
+				const uint32_t v = a.vBegin + v0 + slot;
+				const uint32_t myOwn = own;
+				const bool viol = same > 0u;                      // occ[C[v]]  (violation_count, coloringMCMC_CPU.cpp:342-348)
+				accDirected += same;
+				accViol += viol ? 1ull : 0ull;
+				if (a.dbgMasks) {
+#pragma unroll
+					for (int w = 0; w < W; ++w) a.dbgMasks[(size_t)(v0 + slot) * W + w] = m[w];
+					a.dbgSame[v0 + slot] = same;
+				}
+				if (!a.countOnly) {
+					uint32_t newc = myOwn;
+					bool tabooed = false;
+					uint32_t tb = 0;
+					if (a.tabooIter) {                            // TABOO gate, coloringMCMC_CPU.cpp:496-501
+						tb = a.taboo[v0 + slot];
+						if (tb > 0u) { a.taboo[v0 + slot] = (uint16_t)(tb - 1u); tabooed = true; }
+					}
+					if (!tabooed) {
+						uint32_t Zn = 0;
+#pragma unroll
+						for (int w = 0; w < W; ++w) Zn += __popcll(m[w]);
+						const uint32_t Zp = nCol - Zn;            // free colours (count_free_colors :382)
+						if (isDyn && Zp == 0u) {
+							newc = myOwn;                         // coloringMCMC_balance.cu:111-115: no draw, taboo untouched
+						} else {
+							float u;
+							if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
+							else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
+							const bool stay = !viol || Zp == 0u;  // :472-478 / :402-411
+							bool doneSel = false;
+							if (stay) {
+								// fast path: everything before `own` weighs eps (table S), own weighs stayW
+								const float sOwn = s_S[myOwn];
+								const float tOwn = __fadd_rn(sOwn, stayW);
+								const bool notBefore = isDyn ? (sOwn < u) : (sOwn <= u);
+								const bool hit = isDyn ? (tOwn >= u) : (tOwn > u);
+								if (notBefore && hit) { newc = myOwn; doneSel = true; }
+							}
+							if (!doneSel) {
+								float freeW = stayW, r = 0.0f;
+								if (!stay) {
+									if (!isDyn) {                 // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
+										freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
+									} else {                      // reminder / Zp, coloringMCMC_balance.cu:104-109,124
+										float rem = 0.0f;
+#pragma unroll
+										for (int w = 0; w < W; ++w) {
+											unsigned long long bits = m[w];
+											while (bits) {
+												const int b = __ffsll((long long)bits) - 1;
+												bits &= bits - 1ull;
+												rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
+											}
+										}
+										r = __fdiv_rn(rem, __uint2float_rn(Zp));
+									}
+								}
+								// sequential CDF walk (coloringMCMC_CPU.cpp:510-514 / coloringMCMC_balance.cu:123-136)
+								float cdf = 0.0f;
+								uint32_t idx = nCol - 1u;         // overflow contract: clamp to nCol-1
+								bool found = false;
+#pragma unroll
+								for (int w = 0; w < W; ++w) {
+									if (!found && (uint32_t)(w * 64) < nCol) {
+										const unsigned long long word = m[w];
+										const uint32_t lim = min(64u, nCol - (uint32_t)(w * 64));
+										for (uint32_t b = 0; b < lim; ++b) {
+											const uint32_t k = (uint32_t)(w * 64) + b;
+											const bool isEps = stay ? (k != myOwn) : (((word >> b) & 1ull) != 0ull);
+											float q;
+											if (isEps) q = eps;
+											else if (stay) q = stayW;
+											else if (isDyn) q = __fadd_rn(s_dist[k], r);
+											else q = freeW;
+											cdf = __fadd_rn(cdf, q);
+											const bool stop = isDyn ? (cdf >= u) : (cdf > u);
+											if (stop) { idx = k; found = true; break; }
+										}
+									}
+								}
+								newc = idx;
+							}
+							if (a.tabooIter) a.taboo[v0 + slot] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);  // :526
+						}
+					}
+					nxt[v] = (ColT)newc;
+					if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
+				}
+			}
+		} // sub-tiles
+	} // tiles
+
+	// ---- epilogue: counters ----
+	accDirected = warp_reduce_add64(accDirected);
+	accViol = warp_reduce_add64(accViol);
+	__syncthreads();
+	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_mask);   // reuse
+	if (lane == 0) { s_red[warp] = accDirected; s_red[8 + warp] = accViol; }
+	__syncthreads();
+	if (tid == 0) {
+		unsigned long long d = 0, vv = 0;
+		for (int w = 0; w < kThreads / 32; ++w) { d += s_red[w]; vv += s_red[8 + w]; }
+		if (d) atomicAdd(a.scratch + 0, d);
+		if (vv) atomicAdd(a.scratch + 1, vv);
+	}
+	if (!a.countOnly) {
+		for (uint32_t k = tid; k < nCol; k += kThreads) {
+			const int dlt = s_hist[k];
+			if (dlt) atomicAdd(a.scratch + 2 + k, (unsigned long long)(long long)dlt);
+		}
+	}
+	if (a.fuseFinalize) {
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) s_ctl[2] = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+		__syncthreads();
+		if (s_ctl[2]) {
+			__threadfence();
+			finalize_sweep_device(a);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------
+template <typename ColT>
+__global__ void init_colors_philox_kernel(ColT * colors, uint32_t n, uint32_t nCol, uint64_t seed) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n) return;
+	// uniform colour in [0,nCol) -- replaces initColoring (coloringMCMC_utils.cu:24-33) without its nCol overshoot
+	colors[v] = (ColT)__umulhi(philox_draw(seed, 0u, v, 1u), nCol);
+}
+
+template <typename ColT>
+__global__ void narrow_colors_kernel(const uint32_t * src, ColT * dst, uint32_t n, uint32_t nCol, DevState * st) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n) return;
+	const uint32_t c = src[v];
+	if (c >= nCol) { st->errorFlag = 1u; dst[v] = 0; }
+	else dst[v] = (ColT)c;
+}
+
+template <typename ColT>
+__global__ void widen_colors_kernel(const ColT * src, uint32_t * dst, uint32_t n) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v < n) dst[v] = (uint32_t)src[v];
+}
+
+// class sizes of a colouring (used at init only; the sweeps keep them current through deltas)
+template <typename ColT>
+__global__ void class_sizes_kernel(const ColT * colors, uint32_t n, uint32_t nCol, unsigned long long * hist) {
+	extern __shared__ unsigned int s_h[];
+	for (uint32_t k = threadIdx.x; k < nCol; k += blockDim.x) s_h[k] = 0u;
+	__syncthreads();
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+		atomicAdd(&s_h[colors[v]], 1u);
+	__syncthreads();
+	for (uint32_t k = threadIdx.x; k < nCol; k += blockDim.x)
+		if (s_h[k]) atomicAdd(hist + k, (unsigned long long)s_h[k]);
+}
+
+} // namespace mcmcb200

@@ -59,6 +59,10 @@ uint32_t orc_init_color(uint64_t seed, uint32_t vertex, uint32_t nCol) {
 	return (uint32_t)(((uint64_t)orc_draw_bits(seed, 0u, vertex, 1u) * (uint64_t)nCol) >> 32);
 }
 
+void orc_init_colors(uint64_t seed, uint32_t vb, uint32_t ve, uint32_t nCol, uint32_t * out) {
+	for (uint32_t v = vb; v < ve; v++) out[v - vb] = orc_init_color(seed, v, nCol);
+}
+
 void orc_fill_tape(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, int proposal, float * u) {
 	for (uint32_t v = vb; v < ve; v++) u[v - vb] = orc_draw_uniform(seed, sweep, v, proposal);
 }

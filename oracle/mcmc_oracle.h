@@ -28,6 +28,7 @@ void     orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 uint32_t orc_draw_bits(uint64_t seed, uint32_t sweep, uint32_t vertex, uint32_t purpose);
 float    orc_draw_uniform(uint64_t seed, uint32_t sweep, uint32_t vertex, int proposal);
 uint32_t orc_init_color(uint64_t seed, uint32_t vertex, uint32_t nCol);
+void     orc_init_colors(uint64_t seed, uint32_t vb, uint32_t ve, uint32_t nCol, uint32_t * out /* [ve-vb] */);
 void     orc_fill_tape(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, int proposal, float * u /* [ve-vb] */);
 
 /* graph/graphCPU.cpp:290-404  Graph::setupRnd2 -- libc rand() exact Erdos-Renyi generator.

@@ -51,6 +51,7 @@ class Port:
         L.orc_draw_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_init_color.restype = C.c_uint32
         L.orc_init_color.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+        L.orc_init_colors.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
         L.orc_fill_tape.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _f32p]
         L.orc_setup_rnd2.restype = C.c_int
         L.orc_setup_rnd2.argtypes = [C.c_uint32, C.c_float, _u32p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -85,7 +86,9 @@ class Port:
         return u
 
     def init_colors(self, seed, n, nCol):
-        return np.array([self.L.orc_init_color(seed, v, nCol) for v in range(n)], np.uint32)
+        out = np.empty(n, np.uint32)
+        self.L.orc_init_colors(seed, 0, n, nCol, out)
+        return out
 
     # -- graph ------------------------------------------------------------------------------------
     def setup_rnd2(self, n, prob, srand=1):

@@ -62,10 +62,12 @@ struct RefMCMC : public ColoringMCMC_CPU<float, float> {
 	// Sweep vertices [vb, ve) of the current colouring with an external draw tape u[0..n).
 	// do_swap=1 performs the std::swap(C, Cstar) of coloringMCMC_CPU.cpp:259.
 	// Returns the violating-vertex count of C *before* the sweep (the value run() tests, :136/:152).
+	double lastLoopSeconds = 0;   // wall time of the per-vertex loop of the last sweep_tape (the :183-204 loop only)
 	size_t sweep_tape(const float * u, size_t vb, size_t ve, int do_swap, uint64_t * overflowCount) {
 		Cviol = violation_count(C, Cviols);                                   // :152
 		for (size_t i = 0; i < nNodes; i++) nodeProbab[i] = u[i];              // :139 (draws replaced by the tape)
 		if (vb > 0 || ve < nNodes) Cstar = C;                                  // partial sweeps leave the rest unchanged
+		auto t0 = std::chrono::steady_clock::now();
 		for (size_t i = vb; i < ve; i++) {                                     // :183
 			size_t Zvcomp = count_free_colors(i, C, freeColors);               // :191
 			size_t Zv = nCol - Zvcomp;                                         // :192
@@ -85,6 +87,7 @@ struct RefMCMC : public ColoringMCMC_CPU<float, float> {
 			}
 			extract_new_color(i, p, nodeProbab, q, Cstar);                     // :198
 		}
+		lastLoopSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 		size_t before = Cviol;
 		if (do_swap) std::swap(C, Cstar);                                      // :259
 		return before;
@@ -255,13 +258,12 @@ uint64_t ref_mcmc_sweep_tape(void * hp, const float * u, uint64_t * overflowCoun
 	return m->sweep_tape(u, 0, m->colours().size(), 1, overflowCount);
 }
 
-// partial sweep over [vb, ve) (used for bounded CPU-baseline samples); returns seconds spent in the vertex loop + counts
+// partial sweep over [vb, ve) (bounded CPU-baseline samples); returns the seconds spent in the reference's
+// per-vertex loop (count_free_colors + fill_p + extract_new_color, coloringMCMC_CPU.cpp:183-204) for those vertices
 double ref_mcmc_sweep_range_timed(void * hp, const float * u, uint64_t vb, uint64_t ve) {
 	RefMCMC * m = ((RefHandle *)hp)->mcmc;
-	auto t0 = std::chrono::steady_clock::now();
 	m->sweep_tape(u, vb, ve, 1, nullptr);
-	auto t1 = std::chrono::steady_clock::now();
-	return std::chrono::duration<double>(t1 - t0).count();
+	return m->lastLoopSeconds;
 }
 
 // free-running chain with the object's own std::default_random_engine (pins of SURVEY 8c)

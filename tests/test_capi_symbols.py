@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library loads, exports every symbol include/mcmcb200.h declares, and refuses to compute
+without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mcmc_colorer_b200 import capi as m
+    if not os.path.exists(m.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return m
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "mcmcb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcmcb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(capi):
+    assert header_symbols() == sorted(capi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(capi):
+    L = capi.lib()
+    for s in header_symbols():
+        assert hasattr(L, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mcmcb200_\w+)", out))
+    assert exported == set(header_symbols())
+    assert L.mcmcb200_abi_version() == 1
+    assert b"invalid" in L.mcmcb200_strerror(-1)
+
+
+def test_library_holds_sm100a_sass_only(capi):
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, out
+
+
+def test_struct_layouts_match_header(capi):
+    # mcmcb200_params: 10 x 4 bytes, u64 seed, i32 device, u32 flags = 56; mcmcb200_status_t = 40
+    assert ctypes.sizeof(capi.Params) == 56
+    assert ctypes.sizeof(capi.Status) == 40
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    from mcmc_colorer_b200 import Chain, ColoringMCMCParams, McmcError
+    with pytest.raises(McmcError) as e:
+        Chain(np.array([0, 1, 2], np.uint32), np.array([1, 0], np.uint32), ColoringMCMCParams(nCol=3))
+    assert e.value.code == capi.ENODEVICE
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mcmc_colorer_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle", "").replace("oracle's", ""), os.path.join(dp, f)

@@ -1,0 +1,386 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI (libmcmcb200.so via
+mcmc_colorer_b200.capi) and is compared with the CPU oracle (oracle/, test infrastructure) on the same seeded
+inputs, against the committed golden fixtures generated from the unmodified reference, and -- at large sizes --
+through size-independent properties.  Integer / index / colour results are compared bit-exactly."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import DYNAMIC, UNIFORM
+
+pytestmark = pytest.mark.gpu
+
+EPS = 1e-8
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def mc():
+    import mcmc_colorer_b200 as m
+    return m
+
+
+def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence=0, tailcut=False, max_rip=250,
+               replay=False):
+    prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=convergence, tabooIteration=taboo,
+                                seed=seed, tailcut=tailcut, maxRip=max_rip)
+    # replay=True: keep sweeping past convergence, like the oracle's tape harness does
+    return mc.Chain(cumul, neighs, prm, device=0, flags=mc.FLAG_NO_EARLY_STOP if replay else 0)
+
+
+@pytest.fixture(scope="module")
+def c1_graph(port):
+    return port.setup_rnd2(1000, 0.1, srand=1)
+
+
+@pytest.fixture(scope="module")
+def pins(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "c1_pins.json")))
+
+
+def unpack_masks(masks64, nCol):
+    """uint64[n][W] -> uint8[n][nCol]"""
+    b = np.unpackbits(np.ascontiguousarray(masks64).view(np.uint8), axis=1, bitorder="little")
+    return b[:, :nCol]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parity gate 1: conflict counts and neighbour-colour occupancy, bit-exact for a given colouring
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nCol", [137, 68, 45, 300, 64, 65, 128, 129, 256, 257, 512])
+def test_counts_and_occupancy_c1(mc, port, c1_graph, nCol):
+    cumul, neighs = c1_graph
+    n = 1000
+    ch = make_chain(mc, cumul, neighs, nCol)
+    for cseed in (1, 2):
+        c = port.init_colors(cseed, n, nCol)
+        ch.init_colors(c)
+        st = ch.status()
+        viol, flags = port.violation_count(cumul, neighs, c, want_flags=True)
+        assert st.violatingVertices == viol
+        assert st.conflictEdges == port.conflict_edges(cumul, neighs, c)
+        assert st.sweep == 0 and st.countsSweep == 0
+        masks, same = ch.debug_all_occupancy()
+        occ = unpack_masks(masks, nCol)
+        for v in range(0, n, 7):
+            o, free = port.occupancy(v, cumul, neighs, c, nCol)
+            assert np.array_equal(occ[v], o), v
+        assert np.array_equal((same > 0).astype(np.uint8), flags)
+        assert np.array_equal(mc.occupancy_bits(ch.debug_occupancy(5), nCol), port.occupancy(5, cumul, neighs, c, nCol)[0])
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c, nCol))
+        assert np.array_equal(ch.get_colors(), c)
+        # pure-function variant on a different colouring leaves the chain untouched
+        c2 = port.init_colors(cseed + 10, n, nCol)
+        e, vv = ch.conflicts_of(c2)
+        assert e == port.conflict_edges(cumul, neighs, c2) and vv == port.violation_count(cumul, neighs, c2)
+        assert np.array_equal(ch.get_colors(), c)
+    ch.close()
+
+
+def test_golden_small_fixture_counts(mc, golden_dir):
+    z = np.load(os.path.join(golden_dir, "small_traj.npz"))
+    cumul, neighs = z["cumul"], z["neighs"]
+    for tag in ("a", "b", "c", "ovf"):
+        nCol = int(z[f"{tag}_nCol"])
+        ch = make_chain(mc, cumul, neighs, nCol)
+        ch.init_colors(z[f"{tag}_c0"])
+        assert ch.status().violatingVertices == int(z[f"{tag}_viol0"])
+        masks, same = ch.debug_all_occupancy()
+        assert np.array_equal(unpack_masks(masks, nCol), z[f"{tag}_occ0"])      # reference count_free_colors rows
+        assert np.array_equal((same > 0).astype(np.uint8), z[f"{tag}_flags0"])  # reference Cviols
+        ch.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parity gate 2: replay of a fixed draw tape gives bit-exact colour trajectories
+# ------------------------------------------------------------------------------------------------------------
+def test_golden_small_fixture_trajectories(mc, golden_dir):
+    z = np.load(os.path.join(golden_dir, "small_traj.npz"))
+    cumul, neighs = z["cumul"], z["neighs"]
+    for tag in ("a", "b", "c", "ovf"):
+        nCol, ti = int(z[f"{tag}_nCol"]), int(z[f"{tag}_taboo_iter"])
+        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True)
+        ch.init_colors(z[f"{tag}_c0"])
+        ch.set_tape(z[f"{tag}_tapes"])
+        for s in range(10):
+            ch.sweep(1)
+            assert np.array_equal(ch.get_colors(), z[f"{tag}_colors"][s]), (tag, s)
+        hist = ch.history()
+        assert np.array_equal(hist[:10, 1], z[f"{tag}_viol_before"])            # violating vertices before each sweep
+        # the same 10 sweeps as one batch of launches without host round trips
+        ch.init_colors(z[f"{tag}_c0"])
+        ch.set_tape(z[f"{tag}_tapes"])
+        ch.sweep(10)
+        assert ch.status().sweep == 10 and np.array_equal(ch.get_colors(), z[f"{tag}_colors"][9]), tag
+        ch.close()
+
+
+def test_c1_golden_tape_trajectories(mc, port, pins, c1_graph):
+    cumul, neighs = c1_graph
+    n = 1000
+    for tr in pins["tape_trajectories"]:
+        nCol, ti = tr["nCol"], tr["tabooIteration"]
+        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True)
+        c0 = port.init_colors(tr["color_seed"], n, nCol)
+        assert sha(c0) == tr["start_sha256"]
+        ch.init_colors(c0)
+        ch.set_tape(np.stack([port.tape(tr["tape_seed"], s, n) for s in range(1, 13)]))
+        for s, step in enumerate(tr["steps"]):
+            assert ch.status().violatingVertices == step["viol_before"]
+            ch.sweep(1)
+            assert sha(ch.get_colors()) == step["colors_sha256"], (nCol, ti, s)
+        ch.close()
+
+
+@pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
+@pytest.mark.parametrize("nCol,taboo", [(137, 0), (100, 2), (60, 0), (40, 3), (300, 0)])
+def test_random_tapes_vs_port(mc, port, c1_graph, proposal, nCol, taboo):
+    cumul, neighs = c1_graph
+    n = 1000
+    rng = np.random.default_rng(nCol * 10 + taboo + proposal)
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, taboo=taboo, replay=True)
+    c = rng.integers(0, nCol, n).astype(np.uint32)
+    tapes = rng.random((12, n), dtype=np.float32)
+    if proposal == DYNAMIC:
+        tapes = np.maximum(tapes, np.float32(2.0 ** -24))
+    tapes[3, ::5] = np.nextafter(np.float32(1), np.float32(0))   # force CDF overflows
+    tapes[4, ::7] = tapes[4, ::7] * np.float32(1e-6)             # tiny draws: the epsilon head of the walk
+    ch.init_colors(c)
+    ch.set_tape(tapes)
+    tb = np.zeros(n, np.uint32) if taboo else None
+    for s in range(12):
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, EPS, c, tapes[s], proposal, taboo=tb, taboo_iter=taboo)
+        got = ch.get_colors()
+        assert np.array_equal(got, c), (s, np.flatnonzero(got != c)[:10])
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c, nCol))
+    ch.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Philox: the device draws equal the oracle's, so free-running chains are bit-identical end to end
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("proposal,conv", [(UNIFORM, 0), (DYNAMIC, 1)])
+def test_free_running_chain_equals_port(mc, port, c1_graph, proposal, conv):
+    cumul, neighs = c1_graph
+    n = 1000
+    for nCol, seed in [(137, 1234), (68, 5), (45, 77)]:
+        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=seed, convergence=conv)
+        ch.init_colors(None)
+        c0 = port.init_colors(seed, n, nCol)
+        assert np.array_equal(ch.get_colors(), c0)
+        want, sweeps, cnt, hit = port.run(cumul, neighs, nCol, EPS, c0, seed, proposal)
+        ch.sweep(60)                               # one batch; stops advancing on the device when proper
+        st = ch.status()
+        assert st.converged == 1 and st.sweep == sweeps and cnt == 0
+        assert st.conflictEdges == 0 and st.violatingVertices == 0
+        assert np.array_equal(ch.get_colors(), want)
+        assert st.usedColors == int((port.class_sizes(want, nCol) > 0).sum())
+        ch.close()
+
+
+def test_philox_draws_medium_graph(mc, port):
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    n = 200_000
+    cumul, neighs = er_graph_numpy(n, 16, seed=3)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    for proposal in (UNIFORM, DYNAMIC):
+        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=9, convergence=proposal)
+        ch.init_colors(None)
+        c = port.init_colors(9, n, nCol)
+        assert np.array_equal(ch.get_colors(), c)
+        for s in range(1, 5):
+            u = port.tape(9, s, n, proposal)
+            ch.sweep(1)
+            c, _ = port.sweep(cumul, neighs, nCol, EPS, c, u, proposal)
+            assert np.array_equal(ch.get_colors(), c), (proposal, s)
+        st = ch.status()
+        assert st.violatingVertices == port.violation_count(cumul, neighs, c)
+        assert st.conflictEdges == port.conflict_edges(cumul, neighs, c)
+        ch.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# degree binning: light (thread), heavy (warp) and hub (CTA) vertices, ragged tiles, empty rows
+# ------------------------------------------------------------------------------------------------------------
+def skewed_graph(n, hubs, seed):
+    """random sparse graph + a few hubs adjacent to (almost) everything, + isolated vertices"""
+    rng = np.random.default_rng(seed)
+    m = n * 3
+    a, b = rng.integers(0, n - 50, m), rng.integers(0, n - 50, m)      # last 50 vertices stay isolated
+    pairs = [(a, b)]
+    for h, deg in hubs:
+        others = rng.choice(n - 50, size=deg, replace=False)
+        pairs.append((np.full(deg, h), others))
+    a = np.concatenate([p[0] for p in pairs]).astype(np.int64)
+    b = np.concatenate([p[1] for p in pairs]).astype(np.int64)
+    keep = a != b
+    lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
+    from mcmc_colorer_b200.graphgen import _csr_from_undirected_numpy
+    return _csr_from_undirected_numpy(lo, hi, n)
+
+
+@pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
+def test_skewed_degrees_all_bins(mc, port, proposal):
+    n = 30_001                                          # not a multiple of the tile size
+    cumul, neighs = skewed_graph(n, hubs=[(0, 20_000), (257, 9_000), (258, 8_190), (700, 3_000), (9_999, 100), (29_000, 66)], seed=4)
+    deg = np.diff(cumul.astype(np.int64))
+    assert deg.max() > 8192 and (deg == 0).sum() >= 50 and ((deg > 64) & (deg <= 8192)).sum() >= 3
+    nCol = 200
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=21)
+    ch.init_colors(None)
+    c = port.init_colors(21, n, nCol)
+    masks, same = ch.debug_all_occupancy()
+    occ = unpack_masks(masks, nCol)
+    for v in [0, 1, 257, 258, 259, 700, 9_999, 29_000, 29_990, n - 1] + list(range(3, n, 997)):
+        assert np.array_equal(occ[v], port.occupancy(v, cumul, neighs, c, nCol)[0]), v
+    st = ch.status()
+    assert st.violatingVertices == port.violation_count(cumul, neighs, c)
+    assert st.conflictEdges == port.conflict_edges(cumul, neighs, c)
+    for s in range(1, 4):
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, EPS, c, port.tape(21, s, n, proposal), proposal)
+        assert np.array_equal(ch.get_colors(), c), s
+    ch.close()
+
+
+def test_empty_and_tiny_graphs(mc, port):
+    # no edges at all
+    cumul = np.zeros(11, np.uint32)
+    ch = make_chain(mc, cumul, np.zeros(0, np.uint32), 4, seed=1)
+    ch.init_colors(np.arange(10, dtype=np.uint32) % 4)
+    st = ch.status()
+    assert st.converged == 1 and st.conflictEdges == 0 and st.violatingVertices == 0
+    ch.sweep(3)
+    assert ch.status().sweep == 0                       # already proper: sweeps are no-ops
+    ch.close()
+    # triangle with 2 colours can never be proper; chain must keep running without error, nobody has a free colour
+    cumul = np.array([0, 2, 4, 6], np.uint32)
+    neighs = np.array([1, 2, 0, 2, 0, 1], np.uint32)
+    for proposal in (UNIFORM, DYNAMIC):
+        ch = make_chain(mc, cumul, neighs, 2, proposal=proposal, seed=3)
+        c = np.array([0, 1, 1], np.uint32)
+        ch.init_colors(c)
+        for s in range(1, 6):
+            ch.sweep(1)
+            c, _ = port.sweep(cumul, neighs, 2, EPS, c, port.tape(3, s, 3, proposal), proposal)
+            assert np.array_equal(ch.get_colors(), c)
+        assert ch.status().converged == 0
+        ch.close()
+    # single vertex
+    ch = make_chain(mc, np.array([0, 0], np.uint32), np.zeros(0, np.uint32), 1)
+    ch.init_colors(None)
+    assert ch.status().converged == 1
+    ch.close()
+
+
+def test_argument_errors(mc, c1_graph):
+    cumul, neighs = c1_graph
+    from mcmc_colorer_b200 import capi
+    with pytest.raises(mc.McmcError) as e:
+        make_chain(mc, cumul, neighs, 0)
+    assert e.value.code == capi.EINVAL
+    with pytest.raises(mc.McmcError) as e:
+        make_chain(mc, cumul, neighs, 100_000)          # wide palettes are not in this build
+    assert e.value.code == capi.EUNSUPPORTED
+    bad = neighs.copy(); bad[5] = 5000
+    with pytest.raises(mc.McmcError):
+        make_chain(mc, cumul, bad, 50)
+    ch = make_chain(mc, cumul, neighs, 50)
+    with pytest.raises(mc.McmcError) as e:
+        ch.sweep(1)                                     # before init_colors
+    assert e.value.code == capi.ESTATE
+    with pytest.raises(mc.McmcError) as e:
+        ch.init_colors(np.full(1000, 50, np.uint32))    # colour == nCol
+    assert e.value.code == capi.EINVAL
+    ch.init_colors(np.zeros(1000, np.uint32))
+    ch.set_tape(np.zeros((2, 1000), np.float32))
+    ch.sweep(2)
+    with pytest.raises(mc.McmcError) as e:
+        ch.sweep(1)                                     # tape exhausted
+    assert e.value.code == capi.ETAPE
+    ch.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tail cutting and the reference-shaped driver
+# ------------------------------------------------------------------------------------------------------------
+def test_tailcut_matches_sequential_reference_semantics(mc, port, c1_graph):
+    cumul, neighs = c1_graph
+    n = 1000
+    for nCol, seed in [(137, 3), (60, 4), (45, 5)]:
+        ch = make_chain(mc, cumul, neighs, nCol, seed=seed)
+        c0 = port.init_colors(seed, n, nCol)
+        ch.init_colors(c0)
+        want, rounds, left = port.tailcut(cumul, neighs, nCol, c0)
+        ch.tailcut()
+        got = ch.get_colors()
+        assert np.array_equal(got, want)
+        st = ch.status()
+        assert st.conflictEdges == left == port.conflict_edges(cumul, neighs, got)
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(got, nCol))
+        ch.close()
+
+
+def test_reference_shaped_run_writes_logs(mc, port, c1_graph, pins, tmp_path):
+    cumul, neighs = c1_graph
+    g = mc.Graph(cumul, neighs, prob=0.1)
+    assert (g.getMaxNodeDeg(), g.getMinNodeDeg()) == (137, 73)
+    ref_runs = [r for r in pins["runs"] if r["ratio"] == 1.0]
+    stds = []
+    for seed in range(1, 7):
+        prm = mc.ColoringMCMCParams(nCol=mc.Graph.default_ncol(g.getMaxNodeDeg(), 1.0), seed=seed,
+                                    proposal=mc.PROPOSAL_UNIFORM, convergence=mc.CONVERGE_VERTICES)
+        col = mc.ColoringMCMC(g, None, prm, device=0)
+        col.setDirectoryPath(str(tmp_path / f"1000_0.1_1-MCMC_GPU-{seed}"))
+        colors = col.run(seed)
+        assert port.conflict_edges(cumul, neighs, colors) == 0            # proper
+        assert col.stats["used"] == ref_runs[0]["usedColors"] == 137      # colour count of the reference
+        assert not col.maxIterReached and col.rip - 1 <= 8
+        stds.append(col.stats["std"])
+        log = open(str(tmp_path / f"1000_0.1_1-MCMC_GPU-{seed}.log")).read()
+        for key in ("numCol: 137", "COLORAZIONE FINALE", "Number of used colors is 137 on 137 available",
+                    "StandardDeviation ", "BalancingIndex ", "Max iteration reached no"):
+            assert key in log
+        lines = open(str(tmp_path / f"1000_0.1_1-MCMC_GPU-{seed}-colors.txt")).read().splitlines()
+        assert len(lines) == 1000 and lines[3] == "3 %d" % colors[3]
+        col.chain.close()
+    ref_std = np.array([r["std"] for r in ref_runs])
+    # balance (class-size StD) within 25 % of the reference CPU chains' mean over seeds
+    assert abs(np.mean(stds) - ref_std.mean()) <= 0.25 * ref_std.mean(), (stds, ref_std)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 2 size (n = 1M, mean degree 32): oracle on a 3-sweep replay + numpy restatement of the counters
+# ------------------------------------------------------------------------------------------------------------
+def test_config2_size(mc, port):
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    n = 1_000_000
+    cumul, neighs = er_graph_numpy(n, 32, seed=42)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=UNIFORM, seed=1, convergence=0)
+    ch.init_colors(None)
+    c = port.init_colors(1, n, nCol)
+    assert np.array_equal(ch.get_colors(), c)
+    src = np.repeat(np.arange(n, dtype=np.uint32), np.diff(cumul.astype(np.int64)))
+    for s in range(1, 4):
+        st = ch.status()
+        samec = c[src] == c[neighs]
+        assert st.conflictEdges == int(samec.sum()) // 2
+        assert st.violatingVertices == int(np.unique(src[samec]).size)
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, EPS, c, port.tape(1, s, n), UNIFORM)
+        assert np.array_equal(ch.get_colors(), c), s
+    ch.sweep(100)
+    st = ch.status()
+    assert st.converged == 1 and st.conflictEdges == 0
+    final = ch.get_colors()
+    assert not np.any(final[src] == final[neighs])                      # proper colouring
+    assert ch.class_sizes().sum() == n and np.array_equal(ch.class_sizes(), np.bincount(final, minlength=nCol))
+    ch.close()
