@@ -54,26 +54,27 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.rows, self.index, self.proc = [], index, None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.3)                                    # let the first samples arrive before the timed region
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
         self.t.join(timeout=6)
 
     def summary(self):

@@ -68,7 +68,8 @@ namespace {
 
 template <int W, typename ColT>
 cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
-	sweep_kernel<W, ColT><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
+	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) sweep_kernel<W, ColT, true><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
+	else sweep_kernel<W, ColT, false><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
 	return cudaGetLastError();
 }
 
@@ -84,7 +85,12 @@ cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a) {
 
 template <int W, typename ColT>
 cudaError_t occupancy_t(int * blocks, size_t smem) {
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, sweep_kernel<W, ColT>, kThreads, smem);
+	int a = 0, b = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sweep_kernel<W, ColT, false>, kThreads, smem);
+	if (e != cudaSuccess) return e;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sweep_kernel<W, ColT, true>, kThreads, smem);
+	*blocks = a < b ? a : b;
+	return e;
 }
 
 cudaError_t sweep_occupancy(mcmcb200_handle * h, int * blocks) {

@@ -126,8 +126,49 @@ __device__ __forceinline__ void finalize_sweep_device(const SweepArgs & a) {
 
 __global__ void finalize_kernel(SweepArgs a) { finalize_sweep_device(a); }
 
-template <int W, typename ColT>
-__global__ void __launch_bounds__(kThreads)
+// ---------------------------------------------------------------------------------------------
+// Sequential CDF walks.  The reference selects the first colour whose float32 running sum exceeds the draw
+// (coloringMCMC_CPU.cpp:510-514; ">=" in coloringMCMC_balance.cu:123-136).  The sum is order dependent, so it is
+// reproduced addend by addend with __fadd_rn (never contracted); the loops below are kept as tight as possible
+// because they are the kernel's instruction hot spot (65 % of the warp instructions before this rewrite).
+// ---------------------------------------------------------------------------------------------
+// "stay" distribution (all colours eps, own colour 1-(nCol-1)eps) when the draw fell into an epsilon tail:
+// probability ~ nCol*eps per vertex, kept out of line.
+template <bool kDyn>
+__device__ __noinline__ uint32_t walk_stay(uint32_t nCol, uint32_t own, float eps, float stayW, float u) {
+	float cdf = 0.0f;
+	for (uint32_t k = 0; k < nCol; ++k) {
+		cdf = __fadd_rn(cdf, k == own ? stayW : eps);
+		if (kDyn ? (cdf >= u) : (cdf > u)) return k;
+	}
+	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
+}
+
+// conflicting vertex with free colours: occupied colours weigh eps, free ones freeW (UNIFORM) or dist[k]+r (DYNAMIC)
+template <int W, bool kDyn>
+__device__ __forceinline__ uint32_t walk_conflicting(const unsigned long long (&m)[W], uint32_t nCol, float eps,
+                                                     float freeW, float r, const float * s_dist, float u) {
+	float cdf = 0.0f;
+#pragma unroll
+	for (int h = 0; h < 2 * W; ++h) {
+		if ((uint32_t)(h * 32) < nCol) {
+			uint32_t bits = (h & 1) ? (uint32_t)(m[h >> 1] >> 32) : (uint32_t)m[h >> 1];
+			const uint32_t lim = min(32u, nCol - (uint32_t)(h * 32));
+			for (uint32_t b = 0; b < lim; ++b) {
+				float q;
+				if (kDyn) q = (bits & 1u) ? eps : __fadd_rn(s_dist[h * 32 + b], r);
+				else q = (bits & 1u) ? eps : freeW;
+				bits >>= 1;
+				cdf = __fadd_rn(cdf, q);
+				if (kDyn ? (cdf >= u) : (cdf > u)) return (uint32_t)(h * 32) + b;
+			}
+		}
+	}
+	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
+}
+
+template <int W, typename ColT, bool kDyn>
+__global__ void __launch_bounds__(kThreads, (W <= 2 ? 4 : 2))
 sweep_kernel(const SweepArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t nCol = a.nCol;
@@ -151,7 +192,7 @@ sweep_kernel(const SweepArgs a) {
 	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
-	const bool isDyn = a.proposal == 1u;
+	constexpr bool isDyn = kDyn;
 	const float eps = a.eps;
 	// "stay" weight 1 - (nCol-1)*eps, two roundings like the reference's x86 build (coloringMCMC_CPU.cpp:406,474)
 	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
@@ -361,58 +402,31 @@ sweep_kernel(const SweepArgs a) {
 							if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
 							else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
 							const bool stay = !viol || Zp == 0u;  // :472-478 / :402-411
-							bool doneSel = false;
 							if (stay) {
 								// fast path: everything before `own` weighs eps (table S), own weighs stayW
 								const float sOwn = s_S[myOwn];
 								const float tOwn = __fadd_rn(sOwn, stayW);
 								const bool notBefore = isDyn ? (sOwn < u) : (sOwn <= u);
 								const bool hit = isDyn ? (tOwn >= u) : (tOwn > u);
-								if (notBefore && hit) { newc = myOwn; doneSel = true; }
-							}
-							if (!doneSel) {
-								float freeW = stayW, r = 0.0f;
-								if (!stay) {
-									if (!isDyn) {                 // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
-										freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
-									} else {                      // reminder / Zp, coloringMCMC_balance.cu:104-109,124
-										float rem = 0.0f;
+								newc = (notBefore && hit) ? myOwn : walk_stay<isDyn>(nCol, myOwn, eps, stayW, u);
+							} else {
+								float freeW = 0.0f, r = 0.0f;
+								if (!isDyn) {                     // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
+									freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
+								} else {                          // reminder / Zp, coloringMCMC_balance.cu:104-109,124
+									float rem = 0.0f;
 #pragma unroll
-										for (int w = 0; w < W; ++w) {
-											unsigned long long bits = m[w];
-											while (bits) {
-												const int b = __ffsll((long long)bits) - 1;
-												bits &= bits - 1ull;
-												rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
-											}
-										}
-										r = __fdiv_rn(rem, __uint2float_rn(Zp));
-									}
-								}
-								// sequential CDF walk (coloringMCMC_CPU.cpp:510-514 / coloringMCMC_balance.cu:123-136)
-								float cdf = 0.0f;
-								uint32_t idx = nCol - 1u;         // overflow contract: clamp to nCol-1
-								bool found = false;
-#pragma unroll
-								for (int w = 0; w < W; ++w) {
-									if (!found && (uint32_t)(w * 64) < nCol) {
-										const unsigned long long word = m[w];
-										const uint32_t lim = min(64u, nCol - (uint32_t)(w * 64));
-										for (uint32_t b = 0; b < lim; ++b) {
-											const uint32_t k = (uint32_t)(w * 64) + b;
-											const bool isEps = stay ? (k != myOwn) : (((word >> b) & 1ull) != 0ull);
-											float q;
-											if (isEps) q = eps;
-											else if (stay) q = stayW;
-											else if (isDyn) q = __fadd_rn(s_dist[k], r);
-											else q = freeW;
-											cdf = __fadd_rn(cdf, q);
-											const bool stop = isDyn ? (cdf >= u) : (cdf > u);
-											if (stop) { idx = k; found = true; break; }
+									for (int w = 0; w < W; ++w) {
+										unsigned long long bits = m[w];
+										while (bits) {
+											const int b = __ffsll((long long)bits) - 1;
+											bits &= bits - 1ull;
+											rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
 										}
 									}
+									r = __fdiv_rn(rem, __uint2float_rn(Zp));
 								}
-								newc = idx;
+								newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
 							}
 							if (a.tabooIter) a.taboo[v0 + slot] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);  // :526
 						}

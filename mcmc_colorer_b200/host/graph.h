@@ -39,6 +39,12 @@ public:
 	Graph(Graph<nodeW, edgeW> * const fullGraph);                  // "device" alias, see header comment
 	Graph(node nn, const node_sz * cumulDegs, const node * neighs, float prob);   // adopt-by-copy of an existing CSR
 	~Graph();
+	// the O(E) sampler for any n (the (n, prob, seed) ctor selects it above kExactRandLimit)
+	static Graph<nodeW, edgeW> * makeFast(node nn, float prob, uint32_t seed) {
+		Graph<nodeW, edgeW> * g = new Graph<nodeW, edgeW>();
+		g->prob = prob; g->setupRndFast(nn, prob, seed);
+		return g;
+	}
 
 	GraphStruct<nodeW, edgeW> * getStruct() { return str; }
 	GraphStruct<nodeW, edgeW> * getStruct() const { return str; }
@@ -54,6 +60,7 @@ public:
 	float prob{0.0f};                                               // graph.h:129
 
 private:
+	Graph() {}
 	float density{0.0f};
 	GraphStruct<nodeW, edgeW> * str{nullptr};
 	node maxDeg{0}, minDeg{0};

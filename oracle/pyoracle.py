@@ -183,6 +183,8 @@ class Ref:
         L.ref_graph_from_csr.restype = vp
         L.ref_graph_from_csr.argtypes = [C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_float]
         L.ref_graph_info.argtypes = [vp] + [C.c_void_p] * 5
+        L.ref_graph_from_file.restype = vp
+        L.ref_graph_from_file.argtypes = [C.c_char_p]
         L.ref_graph_copy_csr.argtypes = [vp, _u32p, _u32p]
         L.ref_graph_free.argtypes = [vp]
         L.ref_mcmc_create.restype = vp
@@ -217,6 +219,9 @@ class Ref:
 
     def graph_from_csr(self, cumul, neighs, prob=0.0):
         return self.L.ref_graph_from_csr(len(cumul) - 1, len(neighs), cumul, neighs, prob)
+
+    def graph_from_file(self, path):
+        return self.L.ref_graph_from_file(path.encode())
 
     def graph_info(self, g):
         n, nnz, mx, mn = (C.c_uint32() for _ in range(4))

@@ -179,6 +179,16 @@ void * ref_graph_from_csr(uint32_t n, uint32_t nnz, const uint32_t * cumulDegs, 
 	return g;
 }
 
+// Graph(fileImporter*, bool) -> setupImporterNew (graphCPU.cpp:19-26,112-170) through utils/fileImporter.cpp
+void * ref_graph_from_file(const char * path) {
+	std::streambuf * old = std::cout.rdbuf(nullptr);
+	fileImporter * imp = new fileImporter(std::string(path), "");
+	Graph<float, float> * g = new Graph<float, float>(imp, false);
+	std::cout.rdbuf(old);
+	delete imp;
+	return g;
+}
+
 void ref_graph_info(void * gp, uint32_t * n, uint32_t * nnz, uint32_t * maxDeg, uint32_t * minDeg, float * meanDeg) {
 	Graph<float, float> * g = (Graph<float, float> *)gp;
 	*n = g->getStruct()->nNodes; *nnz = g->getStruct()->nEdges;
