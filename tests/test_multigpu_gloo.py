@@ -1,0 +1,140 @@
+"""CPU, world_size 2, gloo: the multi-GPU driver (mcmc_colorer_b200.multigpu.DistributedSweeper) over a test double
+of the per-rank engine that implements the engine interface with the CPU oracle.  Covers the vertex partition, the
+in-place all-gather layout of the colour slices, the all-reduce of the counters / class-size deltas, the stale-counter
+protocol and the GPU-count independence of the trajectory -- without a GPU."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleEngine:
+    """TEST DOUBLE (tests only): GpuEngine's interface on top of the oracle port, numpy/torch-CPU buffers."""
+
+    def __init__(self, port, cumul, neighs, vb, ve, chunk, world, nCol, seed, proposal):
+        import torch
+        self.P, self.cumul, self.neighs = port, cumul, neighs
+        self.n, self.vb, self.ve, self.nCol, self.seed, self.proposal = len(cumul) - 1, vb, ve, nCol, seed, proposal
+        self.elem_bytes = 1
+        self.bufs = [torch.zeros(chunk * world + 64, dtype=torch.uint8) for _ in range(2)]
+        self._counters = torch.zeros(2 + nCol, dtype=torch.int64)
+        self.t, self.counts_sweep, self.last = 0, None, (0, 0)
+        self.src = np.repeat(np.arange(self.n, dtype=np.uint32), np.diff(cumul.astype(np.int64)))
+
+    def _cur(self):
+        return self.bufs[self.t & 1][: self.n].numpy().astype(np.uint32)
+
+    def init_colors(self, colors=None):
+        import torch
+        c = self.P.init_colors(self.seed, self.n, self.nCol) if colors is None else colors
+        self.bufs[0][: self.n] = torch.from_numpy(c.astype(np.uint8))
+        self.hist = self.P.class_sizes(c, self.nCol).astype(np.int64)
+        self.t, self.counts_sweep = 0, None
+        self._counters.zero_()
+
+    def _local_counts(self, c):
+        lo, hi = self.cumul[self.vb], self.cumul[self.ve]
+        same = c[self.src[lo:hi]] == c[self.neighs[lo:hi]]
+        self._counters[0] += int(same.sum())                                   # directed conflicts of the owned rows
+        self._counters[1] += int(np.unique(self.src[lo:hi][same]).size)        # violating owned vertices
+
+    def local_sweep(self):
+        import torch
+        c = self._cur()
+        self._local_counts(c)
+        u = self.P.tape(self.seed, self.t + 1, self.n, self.proposal)
+        cs, _ = self.P.sweep(self.cumul, self.neighs, self.nCol, 1e-8, c, u, self.proposal,
+                             hist=self.hist.astype(np.uint32), vb=self.vb, ve=self.ve)
+        self.bufs[(self.t + 1) & 1][self.vb:self.ve] = torch.from_numpy(cs[self.vb:self.ve].astype(np.uint8))
+        old, new = c[self.vb:self.ve], cs[self.vb:self.ve]
+        d = np.bincount(new, minlength=self.nCol).astype(np.int64) - np.bincount(old, minlength=self.nCol).astype(np.int64)
+        self._counters[2:] += torch.from_numpy(d)
+        self.pending_count = False
+
+    def next_colors(self):
+        return self.bufs[(self.t + 1) & 1]
+
+    def counters(self):
+        return self._counters
+
+    def finalize(self, advanced):
+        self.last = (int(self._counters[0]) // 2, int(self._counters[1]))
+        self.counts_sweep = self.t
+        if advanced:
+            self.hist = self.hist + self._counters[2:].numpy()
+            self.t += 1
+        self._counters.zero_()
+
+    def status(self):
+        if self.counts_sweep != self.t:
+            self._local_counts(self._cur())                                    # local counting pass, like the C ABI in split mode
+            return types.SimpleNamespace(sweep=self.t, countsSweep=0xffffffff, conflictEdges=0, violatingVertices=0)
+        return types.SimpleNamespace(sweep=self.t, countsSweep=self.t, conflictEdges=self.last[0], violatingVertices=self.last[1])
+
+
+def _worker(rank, world, port_file, result_dir, proposal):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    from mcmc_colorer_b200.multigpu import DistributedSweeper, partition
+    from oracle.pyoracle import Port
+    dist.init_process_group("gloo", init_method=f"file://{port_file}", rank=rank, world_size=world)
+    P = Port()
+    n = 3001
+    cumul, neighs = er_graph_numpy(n, 12, seed=5)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    parts, chunk = partition(n, world, align=256)
+    vb, ve = parts[rank]
+    eng = OracleEngine(P, cumul, neighs, vb, ve, chunk, world, nCol, seed=11, proposal=proposal)
+    sw = DistributedSweeper(eng, rank, world, chunk)
+    eng.init_colors(None)
+    hist = []
+    for s in range(6):
+        st = sw.status()
+        hist.append((st.sweep, st.conflictEdges, st.violatingVertices))
+        sw.sweep(1)
+    final = eng.bufs[eng.t & 1][:n].numpy().astype(np.uint32)
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), final=final, hist=np.array(hist), class_sizes=eng.hist)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("proposal", [0, 1])
+def test_two_rank_driver_matches_single_process_oracle(port, tmp_path, proposal):
+    import torch.multiprocessing as mp
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    from mcmc_colorer_b200.multigpu import partition
+    world = 2
+    rdv = str(tmp_path / "rdv")
+    mp.spawn(_worker, args=(world, rdv, str(tmp_path), proposal), nprocs=world, join=True)
+    n = 3001
+    cumul, neighs = er_graph_numpy(n, 12, seed=5)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    c = port.init_colors(11, n, nCol)
+    want_hist = []
+    for s in range(6):
+        want_hist.append((s, port.conflict_edges(cumul, neighs, c), port.violation_count(cumul, neighs, c)))
+        c, _ = port.sweep(cumul, neighs, nCol, 1e-8, c, port.tape(11, s + 1, n, proposal), proposal)
+    for r in range(world):
+        z = np.load(str(tmp_path / f"rank{r}.npz"))
+        assert np.array_equal(z["final"], c), r                       # same trajectory as one process, on every rank
+        assert z["hist"].tolist() == [list(x) for x in want_hist]
+        assert np.array_equal(z["class_sizes"], port.class_sizes(c, nCol).astype(np.int64))
+    parts, chunk = partition(n, world)
+    assert parts[0][0] == 0 and parts[-1][1] == n and chunk % 256 == 0 and parts[0][1] == parts[1][0]
+
+
+def test_partition_properties():
+    from mcmc_colorer_b200.multigpu import partition
+    for n in (1, 255, 256, 257, 1000, 100_000_000):
+        for world in (1, 2, 4, 8):
+            parts, chunk = partition(n, world)
+            assert chunk % 256 == 0 and chunk * world >= n and chunk * world <= n + 256 * world
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert all(0 <= ve - vb <= chunk for vb, ve in parts)
