@@ -1,0 +1,55 @@
+"""torchrun --nproc-per-node N scripts/multigpu_check.py : N-GPU trajectories must equal the single-process oracle
+(and therefore the 1-GPU run) bit for bit -- counters, class sizes and colours."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from mcmc_colorer_b200 import ColoringMCMCParams
+from mcmc_colorer_b200.graphgen import er_graph_numpy
+from mcmc_colorer_b200.multigpu import DistributedSweeper, GpuEngine, partition
+from oracle.pyoracle import Port
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dev = f"cuda:{lr}"
+dist.init_process_group("nccl", device_id=torch.device(dev))
+P = Port()
+ok = True
+for n, deg, proposal in [(50_001, 12, 0), (50_001, 12, 1), (300_000, 20, 0)]:
+    cumul, neighs = er_graph_numpy(n, deg, seed=5)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    parts, chunk = partition(n, world)
+    vb, ve = parts[rank]
+    e0, e1 = int(cumul[vb]), int(cumul[ve])
+    rp = torch.from_numpy((cumul[vb:ve + 1].astype(np.int64) - e0).astype(np.int32)).to(dev)
+    nb = torch.zeros(e1 - e0 + 16, dtype=torch.int32, device=dev)
+    nb[: e1 - e0] = torch.from_numpy(neighs[e0:e1].astype(np.int32)).to(dev)
+    prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=proposal, seed=11)
+    eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr)
+    sw = DistributedSweeper(eng, rank, world, chunk)
+    eng.init_colors(None)
+    c = P.init_colors(11, n, nCol)
+    for s in range(5):
+        st = sw.status()
+        want = (P.conflict_edges(cumul, neighs, c), P.violation_count(cumul, neighs, c))
+        if (st.conflictEdges, st.violatingVertices) != want or st.sweep != s:
+            ok = False; print(f"rank {rank}: counters differ at sweep {s}: {(st.conflictEdges, st.violatingVertices)} vs {want}")
+        sw.sweep(1)
+        c, _ = P.sweep(cumul, neighs, nCol, 1e-8, c, P.tape(11, s + 1, n, proposal), proposal)
+        got = eng.colors_host()
+        if not np.array_equal(got, c):
+            ok = False; print(f"rank {rank}: colours differ at sweep {s + 1}: {np.flatnonzero(got != c)[:8]}")
+    if not np.array_equal(eng.chain.class_sizes().astype(np.uint32), P.class_sizes(c, nCol)):
+        ok = False; print(f"rank {rank}: class sizes differ")
+    eng.chain.close()
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+if rank == 0:
+    print("MULTIGPU_CHECK", "OK" if flag.item() == 0 else "FAILED", "world", world)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 0 else 1)
