@@ -67,6 +67,8 @@ typedef struct mcmcb200_params {
 } mcmcb200_params;
 
 #define MCMCB200_FLAG_NO_FUSED_FINALIZE 1u  /* caller reduces the sweep counters across ranks itself (multi-GPU) */
+#define MCMCB200_FLAG_FORCE_DIRECT      4u  /* always use the single-pass direct-gather sweep kernel */
+#define MCMCB200_FLAG_FORCE_BLOCKED     8u  /* always use the source-blocked two-pass sweep (EUNSUPPORTED if a row exceeds a tile) */
 #define MCMCB200_FLAG_NO_EARLY_STOP     2u  /* sweeps keep advancing after C_t became proper (tape replay, benchmarking);
                                                mcmcb200_status still reports `converged` for the current colouring */
 

@@ -1,0 +1,153 @@
+// Host side of the source-blocked sweep: builds the static layout once per graph (all on the device, CUB radix sort
+// + scans) and launches the two passes.
+#pragma once
+#include <cstdlib>
+#include <vector>
+
+#include "blocked_sweep.cuh"
+
+namespace mcmcb200 {
+
+inline void free_blocked_layout(BlockedLayout & L) {
+	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.items);
+	L = BlockedLayout{};
+}
+
+#define BLK_CU(call) do { err = (call); if (err != cudaSuccess) goto done; } while (0)
+
+// Returns cudaSuccess with L.valid == false when the layout does not apply (hub rows larger than a tile, > 2^31 edges...).
+inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_rowptr, const uint32_t * d_neighs, uint32_t nLocal,
+                                        uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes,
+                                        cudaStream_t stream, uint64_t * launches) {
+	cudaError_t err = cudaSuccess;
+	L = BlockedLayout{};
+	if (nnzLocal == 0 || nnzLocal >= (1ull << 31) || nLocal == 0) return cudaSuccess;
+	const uint32_t nnz = (uint32_t)nnzLocal;
+	const uint32_t P = (nGlobal + kChunkV - 1) / kChunkV;
+	const uint32_t stageCap = (stageCapBytes / (uint32_t)colBytes) & ~15u;
+	if (stageCap < 1024 || stageCap > 65536) return cudaSuccess;
+
+	uint32_t * d_tmp = nullptr;          // [2]: scratch scalars
+	uint32_t * d_tileE = nullptr;
+	uint16_t * d_keys[2] = {nullptr, nullptr};
+	uint32_t * d_vals[2] = {nullptr, nullptr};
+	void * d_cub = nullptr; size_t cubBytes = 0;
+	uint32_t * d_cnt = nullptr, * d_us = nullptr, * d_plen = nullptr, * d_gs = nullptr, * d_plenT = nullptr, * d_scanT = nullptr, * d_bs = nullptr;
+	uint32_t TV = 0, numTiles = 0, h2[2] = {0, 0};
+	size_t cells = 0;
+	std::vector<uint32_t> bs, items;
+
+	BLK_CU(cudaMalloc(&d_tmp, 2 * sizeof(uint32_t)));
+	// ---- tile size: the largest multiple of 256 vertices whose worst tile (edges + run padding) fits the stage ----
+	for (uint32_t j = std::min<uint32_t>(32u, (nLocal + 255u) / 256u); j >= 1; --j) {
+		const uint32_t tv = 256u * j, nt = (nLocal + tv - 1) / tv;
+		BLK_CU(cudaMemsetAsync(d_tmp, 0, sizeof(uint32_t), stream));
+		blk_max_tile_edges_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, tv, nt, d_tmp); (*launches)++;
+		BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		BLK_CU(cudaStreamSynchronize(stream));
+		const uint64_t worst = (uint64_t)h2[0] + 3ull * std::min<uint64_t>(P, h2[0]);
+		if (worst <= stageCap) { TV = tv; numTiles = nt; break; }
+	}
+	if (TV == 0) goto done;                                     // a row (or 256 of them) exceeds the stage: direct kernel only
+	cells = (size_t)P * numTiles;
+	if (cells >= (1ull << 31)) goto done;
+
+	// ---- bin the directed edges by source chunk (stable radix sort of (chunk, edge id)) ----
+	BLK_CU(cudaMalloc(&d_tileE, sizeof(uint32_t) * ((size_t)numTiles + 1)));
+	blk_tile_edge_starts_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, TV, numTiles, d_tileE); (*launches)++;
+	for (int i = 0; i < 2; ++i) {
+		BLK_CU(cudaMalloc(&d_keys[i], sizeof(uint16_t) * (size_t)nnz));
+		BLK_CU(cudaMalloc(&d_vals[i], sizeof(uint32_t) * (size_t)nnz));
+	}
+	blk_edge_keys_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_neighs, nnz, d_keys[0], d_vals[0]); (*launches)++;
+	{
+		cub::DoubleBuffer<uint16_t> kb(d_keys[0], d_keys[1]);
+		cub::DoubleBuffer<uint32_t> vb(d_vals[0], d_vals[1]);
+		int endBit = 1;
+		while ((1u << endBit) < P) endBit++;
+		BLK_CU(cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, kb, vb, (int)nnz, 0, endBit, stream));
+		BLK_CU(cudaMalloc(&d_cub, cubBytes));
+		BLK_CU(cub::DeviceRadixSort::SortPairs(d_cub, cubBytes, kb, vb, (int)nnz, 0, endBit, stream)); (*launches) += 4;
+		if (kb.Current() != d_keys[0]) { std::swap(d_keys[0], d_keys[1]); }
+		if (vb.Current() != d_vals[0]) { std::swap(d_vals[0], d_vals[1]); }
+		cudaFree(d_cub); d_cub = nullptr;
+	}
+	cudaFree(d_keys[1]); d_keys[1] = nullptr; cudaFree(d_vals[1]); d_vals[1] = nullptr;
+
+	// ---- run lengths per (bucket, tile), padded to 4; three exclusive scans ----
+	BLK_CU(cudaMalloc(&d_cnt, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_us, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_plen, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_gs, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_plenT, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_scanT, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * cells, stream));
+	blk_run_count_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_tileE, numTiles, d_cnt); (*launches)++;
+	blk_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_cnt, P, numTiles, d_plen, d_plenT); (*launches)++;
+	{
+		size_t need = 0;
+		BLK_CU(cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt, d_us, (int)cells, stream));
+		BLK_CU(cudaMalloc(&d_cub, need));
+		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_cnt, d_us, (int)cells, stream));
+		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_plen, d_gs, (int)cells, stream));
+		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_plenT, d_scanT, (int)cells, stream)); (*launches) += 6;
+	}
+	// total padded entries = gs[last] + plen[last]; must fit 32-bit offsets
+	{
+		uint32_t lastG = 0, lastP = 0;
+		BLK_CU(cudaMemcpyAsync(&lastG, d_gs + cells - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		BLK_CU(cudaMemcpyAsync(&lastP, d_plen + cells - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		BLK_CU(cudaStreamSynchronize(stream));
+		const uint64_t total = (uint64_t)lastG + lastP;
+		if (total < nnz || total >= 0xfffffff0ull || total > (uint64_t)nnz + 3ull * cells) goto done;   // wrapped: too many runs
+		L.totalPadded = (uint32_t)total;
+	}
+	// ---- static tables and entry arrays ----
+	BLK_CU(cudaMalloc(&L.runStart, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&L.stageOff, sizeof(uint32_t) * ((size_t)numTiles * (P + 1))));
+	BLK_CU(cudaMemsetAsync(d_tmp, 0, 2 * sizeof(uint32_t), stream));
+	blk_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_gs, d_scanT, d_plenT, P, numTiles, L.runStart, L.stageOff, d_tmp); (*launches)++;
+	BLK_CU(cudaMalloc(&L.srcLocal, sizeof(uint16_t) * ((size_t)L.totalPadded + 16)));
+	BLK_CU(cudaMemsetAsync(L.srcLocal, 0, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));
+	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
+	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
+	blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
+	                                                                L.stageOff, L.srcLocal, L.gidx); (*launches)++;
+	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
+	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
+	// ---- pass-A work items: (bucket, begin, end), at most kItemEntries entries each ----
+	BLK_CU(cudaMalloc(&d_bs, sizeof(uint32_t) * ((size_t)P + 1)));
+	blk_bucket_starts_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.totalPadded, d_bs); (*launches)++;
+	bs.resize((size_t)P + 1);
+	BLK_CU(cudaMemcpyAsync(bs.data(), d_bs, sizeof(uint32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, stream));
+	BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	BLK_CU(cudaStreamSynchronize(stream));
+	if (h2[0] > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
+	for (uint32_t b = 0; b < P; ++b)
+		for (uint32_t beg = bs[b]; beg < bs[b + 1]; beg += kItemEntries) {
+			items.push_back(b); items.push_back(beg); items.push_back(std::min(bs[b + 1], beg + kItemEntries));
+		}
+	L.numItems = (uint32_t)(items.size() / 3);
+	BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * std::max<size_t>(items.size(), 3)));
+	BLK_CU(cudaMemcpyAsync(L.items, items.data(), sizeof(uint32_t) * items.size(), cudaMemcpyHostToDevice, stream));
+	BLK_CU(cudaStreamSynchronize(stream));
+	L.P = P; L.TV = TV; L.numTiles = numTiles; L.stageCap = stageCap;
+	L.valid = true;
+done:
+	cudaFree(d_tmp); cudaFree(d_tileE); cudaFree(d_keys[0]); cudaFree(d_keys[1]); cudaFree(d_vals[0]); cudaFree(d_vals[1]); cudaFree(d_cub);
+	cudaFree(d_cnt); cudaFree(d_us); cudaFree(d_plen); cudaFree(d_gs); cudaFree(d_plenT); cudaFree(d_scanT); cudaFree(d_bs);
+	if (err != cudaSuccess || !L.valid) { cudaError_t keep = err; free_blocked_layout(L); err = keep; }
+	if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); err = cudaSuccess; }   // not enough room for the layout: direct kernel
+	return err;
+}
+#undef BLK_CU
+
+inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
+	BlockedArgs b{};
+	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
+	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.runStart = L.runStart; b.stageOff = L.stageOff;
+	b.items = L.items; b.numItems = L.numItems;
+	return b;
+}
+
+} // namespace mcmcb200

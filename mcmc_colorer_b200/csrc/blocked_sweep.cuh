@@ -1,0 +1,411 @@
+// Source-blocked two-pass sweep ("v2").  Same result as sweep_kernel, different data movement.
+//
+// Why: the direct kernel issues one random 1-byte gather per directed edge into the L2-resident colour array; ncu
+// shows it pinned on the L1->L2 request port (one 32-byte sector request per cycle per SM, profiles/r01a_*).  Here
+// every random access is served from SHARED memory and every byte of DRAM traffic is a streaming read or write:
+//
+//   static, once per graph (build_blocked_layout):
+//     the directed edges (v <- u) are binned by SOURCE chunk b = u / 65536 (stable radix sort, so inside a bucket
+//     they stay in CSR order, i.e. grouped by destination tile T and vertex); each (bucket, tile) run is padded to
+//     4 entries.  srcLocal[pos] = u % 65536 (u16, bucket-major) and gidx[e] (u16, CSR order) = where edge e's colour
+//     lands in its tile's stage buffer.
+//   pass A  blocked_gather_kernel: per bucket, load the 64 Ki colours of the chunk into shared memory (coalesced),
+//     stream srcLocal (2 B/edge), gather from shared memory, write ecol (1 B/edge) sequentially.
+//   pass B  blocked_sweep_kernel: per destination tile, copy the tile's P short runs of ecol into a stage buffer in
+//     shared memory, permute them into CSR order through gidx (2 B/edge, shared-memory gather), then run exactly the
+//     phases 2-3 of the direct kernel (masks, proposal, draw, colour write, counters, device-side finalize).
+//
+// DRAM bytes per directed edge: 2 + 1 (pass A) + 2 + 1*a (pass B; a = sector amplification of the short runs), versus
+// the 8 of the reference layout -- the static preprocessing shrinks the index stream from u32 to 2 x u16.
+#pragma once
+#include <cub/cub.cuh>
+
+#include "sweep_kernel.cuh"
+
+namespace mcmcb200 {
+
+constexpr uint32_t kChunkBits = 16;
+constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
+constexpr int      kThreadsA  = 256;
+constexpr int      kThreadsB  = 512;
+constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
+constexpr uint32_t kRunLanes  = 8;                   // lanes cooperating on one (bucket, tile) run in pass B
+
+struct BlockedLayout {
+	bool      valid = false;
+	uint32_t  P = 0;             // source chunks
+	uint32_t  TV = 0;            // vertices per destination tile (multiple of 256)
+	uint32_t  numTiles = 0;
+	uint32_t  stageCap = 0;      // entries a tile stages at most
+	uint32_t  totalPadded = 0;   // entries in srcLocal / ecol
+	uint16_t * srcLocal = nullptr;   // [totalPadded], bucket-major
+	void *     ecol = nullptr;       // ColT[totalPadded]
+	uint16_t * gidx = nullptr;       // [nnzLocal (+8)], CSR order
+	uint32_t * runStart = nullptr;   // [numTiles][P]    start of run (b,T) in srcLocal/ecol
+	uint32_t * stageOff = nullptr;   // [numTiles][P+1]  start of run (b,T) inside the tile's stage buffer
+	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
+	uint32_t  numItems = 0;
+	size_t    smemA = 0, smemB = 0;
+	int       gridA = 0, gridB = 0;
+};
+
+struct BlockedArgs {
+	uint32_t P, TV, numTiles, stageCap;
+	const uint16_t * srcLocal;
+	void * ecol;
+	const uint16_t * gidx;
+	const uint32_t * runStart;
+	const uint32_t * stageOff;
+	const uint32_t * items;
+	uint32_t numItems;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// layout construction kernels
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void blk_max_tile_edges_kernel(const uint32_t * rowptr, uint32_t nLocal, uint32_t TV, uint32_t numTiles, uint32_t * out) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= numTiles) return;
+	const uint32_t v0 = k * TV, v1 = min(nLocal, v0 + TV);
+	atomicMax(out, rowptr[v1] - rowptr[v0]);
+}
+
+__global__ void blk_tile_edge_starts_kernel(const uint32_t * rowptr, uint32_t nLocal, uint32_t TV, uint32_t numTiles, uint32_t * tileE) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > numTiles) return;
+	tileE[k] = rowptr[min(nLocal, k * TV)];
+}
+
+__global__ void blk_edge_keys_kernel(const uint32_t * neighs, uint32_t nnz, uint16_t * keys, uint32_t * vals) {
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nnz) return;
+	keys[e] = (uint16_t)(neighs[e] >> kChunkBits);
+	vals[e] = e;
+}
+
+// tile of a CSR edge position: tileE is ascending, tileE[T] <= e < tileE[T+1] (empty tiles are skipped by upper_bound)
+__device__ __forceinline__ uint32_t blk_tile_of_edge(const uint32_t * tileE, uint32_t numTiles, uint32_t e) {
+	uint32_t lo = 0, hi = numTiles;          // first index with tileE[idx] > e, minus one
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (tileE[mid + 1] > e) hi = mid; else lo = mid + 1;
+	}
+	return lo;
+}
+
+__global__ void blk_run_count_kernel(const uint16_t * keys, const uint32_t * vals, uint32_t nnz, const uint32_t * tileE,
+                                     uint32_t numTiles, uint32_t * cnt /* [P][numTiles] */) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nnz) return;
+	const uint32_t T = blk_tile_of_edge(tileE, numTiles, vals[i]);
+	atomicAdd(&cnt[(size_t)keys[i] * numTiles + T], 1u);
+}
+
+// plen[b][T] = cnt padded to 4; plenT[T][b] = the same, transposed
+__global__ void blk_pad_kernel(const uint32_t * cnt, uint32_t P, uint32_t numTiles, uint32_t * plen, uint32_t * plenT) {
+	const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (size_t)P * numTiles) return;
+	const uint32_t b = (uint32_t)(idx / numTiles), T = (uint32_t)(idx % numTiles);
+	const uint32_t p = (cnt[idx] + 3u) & ~3u;
+	plen[idx] = p;
+	plenT[(size_t)T * P + b] = p;
+}
+
+// runStart[T][b] = gs[b][T];  stageOff[T][b] = scanT[T][b] - scanT[T][0], stageOff[T][P] = tile total
+__global__ void blk_tables_kernel(const uint32_t * gs, const uint32_t * scanT, const uint32_t * plenT, uint32_t P, uint32_t numTiles,
+                                  uint32_t * runStart, uint32_t * stageOff, uint32_t * maxStage) {
+	const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (size_t)P * numTiles) return;
+	const uint32_t T = (uint32_t)(idx / P), b = (uint32_t)(idx % P);
+	runStart[idx] = gs[(size_t)b * numTiles + T];
+	const uint32_t off = scanT[idx] - scanT[(size_t)T * P];
+	stageOff[(size_t)T * (P + 1) + b] = off;
+	if (b == P - 1) {
+		const uint32_t tot = off + plenT[idx];
+		stageOff[(size_t)T * (P + 1) + P] = tot;
+		atomicMax(maxStage, tot);
+	}
+}
+
+__global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * vals, uint32_t nnz, const uint32_t * neighs,
+                                        const uint32_t * tileE, uint32_t numTiles, uint32_t P, const uint32_t * us /* [P][numTiles] first sorted index */,
+                                        const uint32_t * gs /* [P][numTiles] */, const uint32_t * stageOff, uint16_t * srcLocal, uint16_t * gidx) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nnz) return;
+	const uint32_t e = vals[i], b = keys[i];
+	const uint32_t T = blk_tile_of_edge(tileE, numTiles, e);
+	const size_t idx = (size_t)b * numTiles + T;
+	const uint32_t r = i - us[idx];
+	srcLocal[gs[idx] + r] = (uint16_t)(neighs[e] & (kChunkV - 1u));
+	gidx[e] = (uint16_t)(stageOff[(size_t)T * (P + 1) + b] + r);
+}
+
+__global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32_t numTiles, uint32_t total, uint32_t * bs) {
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b < P) bs[b] = gs[(size_t)b * numTiles];
+	if (b == P) bs[P] = total;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pass A: ecol[pos] = cur[bucket * 65536 + srcLocal[pos]]  -- the gather runs out of shared memory
+// ------------------------------------------------------------------------------------------------------------------
+template <typename ColT>
+__global__ void __launch_bounds__(kThreadsA)
+blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	ColT * chunk = reinterpret_cast<ColT *>(smem_raw);
+	const DevState * st = a.st;
+	if (!a.countOnly && st->convergedAt >= 0) return;
+	const uint32_t t = st->sweep;
+	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
+	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
+	ColT * __restrict__ ecol = static_cast<ColT *>(bl.ecol);
+	const int tid = threadIdx.x;
+	// contiguous share of the work items, so that consecutive items of one bucket reuse the chunk already in shared memory
+	const uint32_t per = (bl.numItems + gridDim.x - 1) / gridDim.x;
+	const uint32_t it0 = blockIdx.x * per, it1 = min(bl.numItems, it0 + per);
+	uint32_t have = 0xffffffffu;
+	for (uint32_t it = it0; it < it1; ++it) {
+		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
+		if (b != have) {
+			__syncthreads();
+			// the colour buffers are padded by 64 Ki entries, so a whole chunk is always readable
+			const uint4 * src = reinterpret_cast<const uint4 *>(cur + (size_t)b * kChunkV);
+			uint4 * dst = reinterpret_cast<uint4 *>(chunk);
+			constexpr uint32_t nVec = kChunkV * sizeof(ColT) / 16;
+			for (uint32_t i = tid; i < nVec; i += kThreadsA) dst[i] = __ldg(src + i);
+			have = b;
+			__syncthreads();
+		}
+		// runs are padded to 4 entries, so an item may start 4 (mod 8): scalar head up to the next multiple of 8,
+		// then 8 entries per thread per step: one 128-bit load of local ids, 8 shared-memory gathers, one packed store
+		const uint32_t body = min(end, (beg + 7u) & ~7u);
+		if (beg + tid < body) ecol[beg + tid] = chunk[bl.srcLocal[beg + tid]];
+		for (uint32_t i = body + 8u * tid; i < end; i += 8u * kThreadsA) {
+			if (i + 8u <= end) {
+				const uint4 ids = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
+				const uint32_t c0 = chunk[ids.x & 0xffffu], c1 = chunk[ids.x >> 16], c2 = chunk[ids.y & 0xffffu], c3 = chunk[ids.y >> 16];
+				const uint32_t c4 = chunk[ids.z & 0xffffu], c5 = chunk[ids.z >> 16], c6 = chunk[ids.w & 0xffffu], c7 = chunk[ids.w >> 16];
+				if (sizeof(ColT) == 1) {
+					uint2 pk;
+					pk.x = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+					pk.y = c4 | (c5 << 8) | (c6 << 16) | (c7 << 24);
+					__stcs(reinterpret_cast<uint2 *>(ecol + i), pk);
+				} else {
+					uint4 pk;
+					pk.x = c0 | (c1 << 16); pk.y = c2 | (c3 << 16); pk.z = c4 | (c5 << 16); pk.w = c6 | (c7 << 16);
+					__stcs(reinterpret_cast<uint4 *>(ecol + i), pk);
+				}
+			} else {
+				for (uint32_t j = i; j < end; ++j) ecol[j] = chunk[bl.srcLocal[j]];
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes) {
+	size_t b = 0;
+	b += sizeof(uint32_t) * (size_t)(TV + 4);              // s_rp
+	b += sizeof(uint32_t) * (size_t)((P + 1 + 3) & ~3u);   // s_so
+	b += sizeof(uint32_t) * (size_t)((P + 3) & ~3u);       // s_rs
+	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
+	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
+	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
+	b += sizeof(uint32_t) * 8;                             // s_ctl
+	b += sizeof(uint32_t) * 64;                            // s_red
+	b += sizeof(uint16_t) * (size_t)((TV + 7) & ~7u);      // s_heavy
+	b = (b + 15) & ~(size_t)15;
+	b += (size_t)colBytes * (stageCap + 16);               // stage
+	b += (size_t)colBytes * (stageCap + 16);               // s_col
+	return (b + 15) & ~(size_t)15;
+}
+
+template <int W, typename ColT, bool kDyn>
+__global__ void __launch_bounds__(kThreadsB)
+blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const uint32_t nCol = a.nCol, P = bl.P, TV = bl.TV;
+	uint32_t * s_rp   = reinterpret_cast<uint32_t *>(smem_raw);
+	uint32_t * s_so   = s_rp + (TV + 4);
+	uint32_t * s_rs   = s_so + ((P + 1 + 3) & ~3u);
+	float *    s_S    = reinterpret_cast<float *>(s_rs + ((P + 3) & ~3u));
+	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
+	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
+	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
+	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 32 x u64
+	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 64);
+	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + ((TV + 7) & ~7u)) - smem_raw);
+	off = (off + 15) & ~(size_t)15;
+	ColT * stage = reinterpret_cast<ColT *>(smem_raw + off);
+	ColT * s_col = stage + (bl.stageCap + 16);
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int nWarps = kThreadsB / 32;
+	DevState * st = a.st;
+	if (!a.countOnly && st->convergedAt >= 0) return;
+	const uint32_t t = st->sweep;
+	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
+	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
+	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
+	const ColT * __restrict__ ecol = static_cast<const ColT *>(bl.ecol);
+	constexpr bool isDyn = kDyn;
+	const float eps = a.eps;
+	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
+
+	for (uint32_t k = tid; k < nCol; k += kThreadsB) s_hist[k] = 0;
+	if (tid == 0) {
+		float s = 0.0f; s_S[0] = 0.0f;
+		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
+	}
+	if (isDyn && !a.countOnly) {
+		const unsigned long long * hc = a.hist[t & 1];
+		const float nF = __uint2float_rn(a.nGlobal), dF = __uint2float_rn(nCol - 1u);
+		for (uint32_t k = tid; k < nCol; k += kThreadsB)
+			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(__uint2float_rn((uint32_t)hc[k]), nF)), dF);
+	}
+	unsigned long long accDirected = 0ull, accViol = 0ull;
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_ctl[0] = atomicAdd(&st->tileCounter, 1u);
+		__syncthreads();
+		const uint32_t T = s_ctl[0];
+		if (T >= bl.numTiles) break;
+		const uint32_t v0 = T * TV;
+		const uint32_t nv = min(TV, a.nLocal - v0);
+		for (uint32_t i = tid; i <= nv; i += kThreadsB) s_rp[i] = a.rowptr[v0 + i];
+		for (uint32_t b = tid; b <= P; b += kThreadsB) s_so[b] = bl.stageOff[(size_t)T * (P + 1) + b];
+		for (uint32_t b = tid; b < P; b += kThreadsB) s_rs[b] = bl.runStart[(size_t)T * P + b];
+		__syncthreads();
+		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules) ----
+		{
+			constexpr uint32_t groups = kThreadsB / kRunLanes;
+			const uint32_t grp = tid / kRunLanes, gl = tid % kRunLanes;
+			for (uint32_t b = grp; b < P; b += groups) {
+				const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
+				for (uint32_t w = 4u * gl; w < len; w += 4u * kRunLanes) {
+					if (sizeof(ColT) == 1)
+						*reinterpret_cast<uint32_t *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint32_t *>(ecol + g + w));
+					else
+						*reinterpret_cast<uint2 *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint2 *>(ecol + g + w));
+				}
+			}
+		}
+		__syncthreads();
+		// ---- phase 1': CSR order through the static permutation: s_col[e - ea] = stage[gidx[e]] ----
+		const uint32_t e0 = s_rp[0], e1 = s_rp[nv];
+		const uint32_t ea = e0 & ~7u;
+		{
+			const uint32_t nOct = (e1 - ea + 7u) >> 3;
+			for (uint32_t o = tid; o < nOct; o += kThreadsB) {
+				const uint4 gi = __ldcs(reinterpret_cast<const uint4 *>(bl.gidx + ea + 8u * o));
+				const uint32_t lim = e1 - (ea + 8u * o);       // valid entries in this octet from the top; entries below e0 are other tiles' (harmless, but their indices may exceed this tile's stage)
+				uint32_t idx[8] = {gi.x & 0xffffu, gi.x >> 16, gi.y & 0xffffu, gi.y >> 16, gi.z & 0xffffu, gi.z >> 16, gi.w & 0xffffu, gi.w >> 16};
+				uint32_t c[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					const bool ok = (uint32_t)j < lim && (ea + 8u * o + j) >= e0;
+					c[j] = ok ? (uint32_t)stage[idx[j]] : 0u;
+				}
+				if (sizeof(ColT) == 1) {
+					uint2 pk;
+					pk.x = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+					pk.y = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+					*reinterpret_cast<uint2 *>(s_col + 8u * o) = pk;
+				} else {
+					uint4 pk;
+					pk.x = c[0] | (c[1] << 16); pk.y = c[2] | (c[3] << 16); pk.z = c[4] | (c[5] << 16); pk.w = c[6] | (c[7] << 16);
+					*reinterpret_cast<uint4 *>(s_col + 8u * o) = pk;
+				}
+			}
+		}
+		if (tid == 0) s_ctl[1] = 0u;
+		__syncthreads();
+		// ---- phases 2-3: thread per vertex (light), warp per vertex (heavy) ----
+		for (uint32_t g = 0; g < nv; g += kThreadsB) {
+			const uint32_t slot = g + tid;
+			if (slot < nv) {
+				const uint32_t myBeg = s_rp[slot], deg = s_rp[slot + 1] - myBeg;
+				if (deg <= (uint32_t)kLightMaxDeg) {
+					const uint32_t gv = a.vBegin + v0 + slot;
+					const uint32_t own = (uint32_t)cur[gv];
+					unsigned long long m[W];
+#pragma unroll
+					for (int w = 0; w < W; ++w) m[w] = 0ull;
+					uint32_t same = 0;
+					const ColT * p = s_col + (myBeg - ea);
+					for (uint32_t i = 0; i < deg; ++i) {
+						const uint32_t c = p[i];
+						same += (c == own);
+						if (W == 1) m[0] |= 1ull << c;
+						else {
+#pragma unroll
+							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						}
+					}
+					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol);
+				} else {
+					s_heavy[atomicAdd(&s_ctl[1], 1u)] = (uint16_t)slot;
+				}
+			}
+		}
+		__syncthreads();
+		const uint32_t nHeavy = s_ctl[1];
+		for (uint32_t h = warp; h < nHeavy; h += nWarps) {
+			const uint32_t slot = s_heavy[h];
+			const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
+			const uint32_t gv = a.vBegin + v0 + slot;
+			const uint32_t own = (uint32_t)cur[gv];
+			const ColT * p = s_col + (hb - ea);
+			unsigned long long m[W];
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] = 0ull;
+			uint32_t same = 0;
+			for (uint32_t i = lane; i < hd; i += 32) {
+				const uint32_t c = p[i];
+				same += (c == own);
+#pragma unroll
+				for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+			}
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
+			same = __reduce_add_sync(0xffffffffu, same);
+			if (lane == 0)
+				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol);
+		}
+	}
+
+	// ---- epilogue (same protocol as sweep_kernel) ----
+	accDirected = warp_reduce_add64(accDirected);
+	accViol = warp_reduce_add64(accViol);
+	__syncthreads();
+	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }
+	__syncthreads();
+	if (tid == 0) {
+		unsigned long long d = 0, vv = 0;
+		for (int w = 0; w < nWarps; ++w) { d += s_red[w]; vv += s_red[16 + w]; }
+		if (d) atomicAdd(a.scratch + 0, d);
+		if (vv) atomicAdd(a.scratch + 1, vv);
+	}
+	if (!a.countOnly) {
+		for (uint32_t k = tid; k < nCol; k += kThreadsB) {
+			const int dlt = s_hist[k];
+			if (dlt) atomicAdd(a.scratch + 2 + k, (unsigned long long)(long long)dlt);
+		}
+	}
+	if (a.fuseFinalize) {
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) s_ctl[2] = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+		__syncthreads();
+		if (s_ctl[2]) {
+			__threadfence();
+			finalize_sweep_device(a);
+		}
+	}
+}
+
+} // namespace mcmcb200

@@ -2,6 +2,7 @@
 #include "../../include/mcmcb200.h"
 #include "sweep_kernel.cuh"
 #include "tailcut_kernel.cuh"
+#include "blocked_build.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -62,24 +63,65 @@ struct mcmcb200_handle {
 	uint64_t launches = 0;
 	uint64_t z = 0;
 	int smCount = 0;
+	BlockedLayout bl;                    // source-blocked two-pass layout (valid => the sweeps use it)
 };
 
 namespace {
 
 template <int W, typename ColT>
 cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
+	if (h->bl.valid) {
+		// source-blocked path: pass A (gather through shared memory) + pass B (tile sweep); two launches per sweep
+		const BlockedArgs b = make_blocked_args(h->bl);
+		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, h->stream>>>(a, b);
+		h->launches++;
+		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, kThreadsB, h->bl.smemB, h->stream>>>(a, b);
+		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, kThreadsB, h->bl.smemB, h->stream>>>(a, b);
+		return cudaGetLastError();
+	}
 	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) sweep_kernel<W, ColT, true><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
 	else sweep_kernel<W, ColT, false><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
 	return cudaGetLastError();
 }
 
+// shared-memory opt-in and grid sizes of the two blocked kernels for this handle's template instance
+template <int W, typename ColT>
+cudaError_t configure_blocked_t(mcmcb200_handle * h) {
+	BlockedLayout & L = h->bl;
+	L.smemA = (size_t)kChunkV * sizeof(ColT);
+	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.P, L.TV, L.stageCap, (int)sizeof(ColT));
+	cudaError_t e = cudaFuncSetAttribute(blocked_gather_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemA);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
+	if (e != cudaSuccess) return e;
+	int oa = 0, ob0 = 0, ob1 = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, blocked_gather_kernel<ColT>, kThreadsA, L.smemA);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob0, blocked_sweep_kernel<W, ColT, false>, kThreadsB, L.smemB);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob1, blocked_sweep_kernel<W, ColT, true>, kThreadsB, L.smemB);
+	if (e != cudaSuccess) return e;
+	const int ob = ob0 < ob1 ? ob0 : ob1;
+	if (oa < 1 || ob < 1) { L.valid = false; return cudaSuccess; }
+	L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(oa * h->smCount)));
+	L.gridB = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numTiles, (uint32_t)(ob * h->smCount)));
+	return cudaSuccess;
+}
+
 cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a) {
-	h->launches++;
+	h->launches++;   // (the blocked path counts its first pass itself)
 	switch (h->W) {
 	case 1: return launch_sweep_t<1, uint8_t>(h, a);
 	case 2: return launch_sweep_t<2, uint8_t>(h, a);
 	case 4: return launch_sweep_t<4, uint8_t>(h, a);
 	default: return launch_sweep_t<8, uint16_t>(h, a);
+	}
+}
+
+cudaError_t configure_blocked(mcmcb200_handle * h) {
+	switch (h->W) {
+	case 1: return configure_blocked_t<1, uint8_t>(h);
+	case 2: return configure_blocked_t<2, uint8_t>(h);
+	case 4: return configure_blocked_t<4, uint8_t>(h);
+	default: return configure_blocked_t<8, uint16_t>(h);
 	}
 }
 
@@ -275,6 +317,21 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 	}
 	rc = alloc_chain_state(h);
 	if (rc) return fail(rc);
+	{
+		// kernel choice: the source-blocked two-pass sweep pays off once the random colour gathers dominate (large sparse
+		// graphs); small graphs keep the single-pass direct kernel.  MCMCB200_FLAG_FORCE_{DIRECT,BLOCKED} override.
+		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
+		const bool want = forceBlocked || (!forceDirect && nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18));
+		if (want) {
+			uint32_t capBytes = 32768;
+			if (const char * env = getenv("MCMCB200_STAGE_CAP_BYTES")) capBytes = (uint32_t)strtoul(env, nullptr, 10);
+			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes,
+			                                     h->stream, &h->launches);
+			if (e == cudaSuccess && h->bl.valid) e = configure_blocked(h);
+			if (e != cudaSuccess) return fail(cuda_fail(e, "build_blocked_layout", __LINE__));
+			if (forceBlocked && !h->bl.valid) return fail(MCMCB200_EUNSUPPORTED);
+		}
+	}
 	rc = reset_state(h);
 	if (rc) return fail(rc);
 	*out = h;
@@ -339,6 +396,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_colors[0]); cudaFree(h->d_colors[1]); cudaFree(h->d_colorsTmp); cudaFree(h->d_taboo);
 	cudaFree(h->d_tape); cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
+	free_blocked_layout(h->bl);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);

@@ -167,6 +167,79 @@ __device__ __forceinline__ uint32_t walk_conflicting(const unsigned long long (&
 	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
 }
 
+// ---------------------------------------------------------------------------------------------
+// PHASE 3 for one vertex (shared by the direct-gather kernel and the source-blocked kernel): conflict flag, free
+// colour count, taboo gate, draw, proposal, colour write, class-size deltas.
+//   v = global vertex id, lv = local (owned) index, m = occupancy mask, same = #neighbours with v's colour.
+// ---------------------------------------------------------------------------------------------
+template <int W, typename ColT, bool kDyn>
+__device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, ColT * __restrict__ nxt, uint32_t v, uint32_t lv,
+                                              uint32_t myOwn, const unsigned long long (&m)[W], uint32_t same,
+                                              const float * s_S, const float * s_dist, int * s_hist, float stayW,
+                                              unsigned long long & accDirected, unsigned long long & accViol) {
+	constexpr bool isDyn = kDyn;
+	const uint32_t nCol = a.nCol;
+	const float eps = a.eps;
+	const bool viol = same > 0u;                              // occ[C[v]]  (violation_count, coloringMCMC_CPU.cpp:342-348)
+	accDirected += same;
+	accViol += viol ? 1ull : 0ull;
+	if (a.dbgMasks) {
+#pragma unroll
+		for (int w = 0; w < W; ++w) a.dbgMasks[(size_t)lv * W + w] = m[w];
+		a.dbgSame[lv] = same;
+	}
+	if (a.countOnly) return;
+	uint32_t newc = myOwn;
+	bool tabooed = false;
+	if (a.tabooIter) {                                        // TABOO gate, coloringMCMC_CPU.cpp:496-501
+		const uint32_t tb = a.taboo[lv];
+		if (tb > 0u) { a.taboo[lv] = (uint16_t)(tb - 1u); tabooed = true; }
+	}
+	if (!tabooed) {
+		uint32_t Zn = 0;
+#pragma unroll
+		for (int w = 0; w < W; ++w) Zn += __popcll(m[w]);
+		const uint32_t Zp = nCol - Zn;                        // free colours (count_free_colors :382)
+		if (isDyn && Zp == 0u) {
+			newc = myOwn;                                     // coloringMCMC_balance.cu:111-115: no draw, taboo untouched
+		} else {
+			float u;
+			if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
+			else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
+			const bool stay = !viol || Zp == 0u;              // :472-478 / :402-411
+			if (stay) {
+				// fast path: everything before `own` weighs eps (table S), own weighs stayW
+				const float sOwn = s_S[myOwn];
+				const float tOwn = __fadd_rn(sOwn, stayW);
+				const bool notBefore = isDyn ? (sOwn < u) : (sOwn <= u);
+				const bool hit = isDyn ? (tOwn >= u) : (tOwn > u);
+				newc = (notBefore && hit) ? myOwn : walk_stay<isDyn>(nCol, myOwn, eps, stayW, u);
+			} else {
+				float freeW = 0.0f, r = 0.0f;
+				if (!isDyn) {                                 // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
+					freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
+				} else {                                      // reminder / Zp, coloringMCMC_balance.cu:104-109,124
+					float rem = 0.0f;
+#pragma unroll
+					for (int w = 0; w < W; ++w) {
+						unsigned long long bits = m[w];
+						while (bits) {
+							const int b = __ffsll((long long)bits) - 1;
+							bits &= bits - 1ull;
+							rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
+						}
+					}
+					r = __fdiv_rn(rem, __uint2float_rn(Zp));
+				}
+				newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
+			}
+			if (a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);  // :526
+		}
+	}
+	nxt[v] = (ColT)newc;
+	if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
+}
+
 template <int W, typename ColT, bool kDyn>
 __global__ void __launch_bounds__(kThreads, (W <= 2 ? 4 : 2))
 sweep_kernel(const SweepArgs a) {
@@ -370,71 +443,9 @@ sweep_kernel(const SweepArgs a) {
 			}
 
 			// ---------------- PHASE 3: thread-per-vertex proposal, draw, colour write ----------------
-			if (mine) {
-				const uint32_t slot = tid;
-				const uint32_t v = a.vBegin + v0 + slot;
-				const uint32_t myOwn = own;
-				const bool viol = same > 0u;                      // occ[C[v]]  (violation_count, coloringMCMC_CPU.cpp:342-348)
-				accDirected += same;
-				accViol += viol ? 1ull : 0ull;
-				if (a.dbgMasks) {
-#pragma unroll
-					for (int w = 0; w < W; ++w) a.dbgMasks[(size_t)(v0 + slot) * W + w] = m[w];
-					a.dbgSame[v0 + slot] = same;
-				}
-				if (!a.countOnly) {
-					uint32_t newc = myOwn;
-					bool tabooed = false;
-					uint32_t tb = 0;
-					if (a.tabooIter) {                            // TABOO gate, coloringMCMC_CPU.cpp:496-501
-						tb = a.taboo[v0 + slot];
-						if (tb > 0u) { a.taboo[v0 + slot] = (uint16_t)(tb - 1u); tabooed = true; }
-					}
-					if (!tabooed) {
-						uint32_t Zn = 0;
-#pragma unroll
-						for (int w = 0; w < W; ++w) Zn += __popcll(m[w]);
-						const uint32_t Zp = nCol - Zn;            // free colours (count_free_colors :382)
-						if (isDyn && Zp == 0u) {
-							newc = myOwn;                         // coloringMCMC_balance.cu:111-115: no draw, taboo untouched
-						} else {
-							float u;
-							if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
-							else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
-							const bool stay = !viol || Zp == 0u;  // :472-478 / :402-411
-							if (stay) {
-								// fast path: everything before `own` weighs eps (table S), own weighs stayW
-								const float sOwn = s_S[myOwn];
-								const float tOwn = __fadd_rn(sOwn, stayW);
-								const bool notBefore = isDyn ? (sOwn < u) : (sOwn <= u);
-								const bool hit = isDyn ? (tOwn >= u) : (tOwn > u);
-								newc = (notBefore && hit) ? myOwn : walk_stay<isDyn>(nCol, myOwn, eps, stayW, u);
-							} else {
-								float freeW = 0.0f, r = 0.0f;
-								if (!isDyn) {                     // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
-									freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
-								} else {                          // reminder / Zp, coloringMCMC_balance.cu:104-109,124
-									float rem = 0.0f;
-#pragma unroll
-									for (int w = 0; w < W; ++w) {
-										unsigned long long bits = m[w];
-										while (bits) {
-											const int b = __ffsll((long long)bits) - 1;
-											bits &= bits - 1ull;
-											rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
-										}
-									}
-									r = __fdiv_rn(rem, __uint2float_rn(Zp));
-								}
-								newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
-							}
-							if (a.tabooIter) a.taboo[v0 + slot] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);  // :526
-						}
-					}
-					nxt[v] = (ColT)newc;
-					if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
-				}
-			}
+			if (mine)
+				commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + v0 + tid, v0 + tid, own, m, same, s_S, s_dist, s_hist, stayW,
+				                             accDirected, accViol);
 		} // sub-tiles
 	} // tiles
 

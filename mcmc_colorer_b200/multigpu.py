@@ -9,8 +9,8 @@ The reference is single-GPU; this is new work defined by the north s
   * draws are Philox keyed by the GLOBAL vertex id, so trajectories are bit-identical for 1, 2, 4 and 8 GPUs.
 
 The driver below is engine-agnostic: `engine` is anything with the small interface of GpuEngine (the B200 engine over
-libmcmcb200).  The CPU tests drive the same driver over gloo with a test double that implements the interface with the
-oracle, which covers the partition arithmetic, the exchange layout and the convergence protocol without a GPU.
+libmcmcb200).  The CPU tests drive the same driver over gloo with a test double of that interface (defined in
+tests/, backed by the CPU checker), which covers the partition arithmetic, the exchange layout and the convergence protocol without a GPU.
 """
 import os
 import time

@@ -26,12 +26,23 @@ def mc():
     return m
 
 
+KERNELS = ["direct", "blocked"]   # single-pass direct-gather kernel / source-blocked two-pass kernel
+
+
 def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence=0, tailcut=False, max_rip=250,
-               replay=False):
+               replay=False, kernel=None):
     prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=convergence, tabooIteration=taboo,
                                 seed=seed, tailcut=tailcut, maxRip=max_rip)
     # replay=True: keep sweeping past convergence, like the oracle's tape harness does
-    return mc.Chain(cumul, neighs, prm, device=0, flags=mc.FLAG_NO_EARLY_STOP if replay else 0)
+    flags = mc.FLAG_NO_EARLY_STOP if replay else 0
+    flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED}[kernel]
+    try:
+        return mc.Chain(cumul, neighs, prm, device=0, flags=flags)
+    except mc.McmcError as e:
+        from mcmc_colorer_b200 import capi
+        if kernel == "blocked" and e.code == capi.EUNSUPPORTED:
+            pytest.skip("a 256-vertex tile of this graph does not fit the blocked kernel's stage (by design: direct kernel)")
+        raise
 
 
 @pytest.fixture(scope="module")
@@ -53,11 +64,12 @@ def unpack_masks(masks64, nCol):
 # ------------------------------------------------------------------------------------------------------------
 # parity gate 1: conflict counts and neighbour-colour occupancy, bit-exact for a given colouring
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("nCol", [137, 68, 45, 300, 64, 65, 128, 129, 256, 257, 512])
-def test_counts_and_occupancy_c1(mc, port, c1_graph, nCol):
+def test_counts_and_occupancy_c1(mc, port, c1_graph, nCol, kernel):
     cumul, neighs = c1_graph
     n = 1000
-    ch = make_chain(mc, cumul, neighs, nCol)
+    ch = make_chain(mc, cumul, neighs, nCol, kernel=kernel)
     for cseed in (1, 2):
         c = port.init_colors(cseed, n, nCol)
         ch.init_colors(c)
@@ -83,12 +95,13 @@ def test_counts_and_occupancy_c1(mc, port, c1_graph, nCol):
     ch.close()
 
 
-def test_golden_small_fixture_counts(mc, golden_dir):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_small_fixture_counts(mc, golden_dir, kernel):
     z = np.load(os.path.join(golden_dir, "small_traj.npz"))
     cumul, neighs = z["cumul"], z["neighs"]
     for tag in ("a", "b", "c", "ovf"):
         nCol = int(z[f"{tag}_nCol"])
-        ch = make_chain(mc, cumul, neighs, nCol)
+        ch = make_chain(mc, cumul, neighs, nCol, kernel=kernel)
         ch.init_colors(z[f"{tag}_c0"])
         assert ch.status().violatingVertices == int(z[f"{tag}_viol0"])
         masks, same = ch.debug_all_occupancy()
@@ -100,12 +113,13 @@ def test_golden_small_fixture_counts(mc, golden_dir):
 # ------------------------------------------------------------------------------------------------------------
 # parity gate 2: replay of a fixed draw tape gives bit-exact colour trajectories
 # ------------------------------------------------------------------------------------------------------------
-def test_golden_small_fixture_trajectories(mc, golden_dir):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_small_fixture_trajectories(mc, golden_dir, kernel):
     z = np.load(os.path.join(golden_dir, "small_traj.npz"))
     cumul, neighs = z["cumul"], z["neighs"]
     for tag in ("a", "b", "c", "ovf"):
         nCol, ti = int(z[f"{tag}_nCol"]), int(z[f"{tag}_taboo_iter"])
-        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True)
+        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True, kernel=kernel)
         ch.init_colors(z[f"{tag}_c0"])
         ch.set_tape(z[f"{tag}_tapes"])
         for s in range(10):
@@ -121,12 +135,13 @@ def test_golden_small_fixture_trajectories(mc, golden_dir):
         ch.close()
 
 
-def test_c1_golden_tape_trajectories(mc, port, pins, c1_graph):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c1_golden_tape_trajectories(mc, port, pins, c1_graph, kernel):
     cumul, neighs = c1_graph
     n = 1000
     for tr in pins["tape_trajectories"]:
         nCol, ti = tr["nCol"], tr["tabooIteration"]
-        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True)
+        ch = make_chain(mc, cumul, neighs, nCol, taboo=ti, replay=True, kernel=kernel)
         c0 = port.init_colors(tr["color_seed"], n, nCol)
         assert sha(c0) == tr["start_sha256"]
         ch.init_colors(c0)
@@ -138,13 +153,14 @@ def test_c1_golden_tape_trajectories(mc, port, pins, c1_graph):
         ch.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
 @pytest.mark.parametrize("nCol,taboo", [(137, 0), (100, 2), (60, 0), (40, 3), (300, 0)])
-def test_random_tapes_vs_port(mc, port, c1_graph, proposal, nCol, taboo):
+def test_random_tapes_vs_port(mc, port, c1_graph, proposal, nCol, taboo, kernel):
     cumul, neighs = c1_graph
     n = 1000
     rng = np.random.default_rng(nCol * 10 + taboo + proposal)
-    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, taboo=taboo, replay=True)
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, taboo=taboo, replay=True, kernel=kernel)
     c = rng.integers(0, nCol, n).astype(np.uint32)
     tapes = rng.random((12, n), dtype=np.float32)
     if proposal == DYNAMIC:
@@ -166,12 +182,13 @@ def test_random_tapes_vs_port(mc, port, c1_graph, proposal, nCol, taboo):
 # ------------------------------------------------------------------------------------------------------------
 # Philox: the device draws equal the oracle's, so free-running chains are bit-identical end to end
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("proposal,conv", [(UNIFORM, 0), (DYNAMIC, 1)])
-def test_free_running_chain_equals_port(mc, port, c1_graph, proposal, conv):
+def test_free_running_chain_equals_port(mc, port, c1_graph, proposal, conv, kernel):
     cumul, neighs = c1_graph
     n = 1000
     for nCol, seed in [(137, 1234), (68, 5), (45, 77)]:
-        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=seed, convergence=conv)
+        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=seed, convergence=conv, kernel=kernel)
         ch.init_colors(None)
         c0 = port.init_colors(seed, n, nCol)
         assert np.array_equal(ch.get_colors(), c0)
@@ -185,13 +202,15 @@ def test_free_running_chain_equals_port(mc, port, c1_graph, proposal, conv):
         ch.close()
 
 
-def test_philox_draws_medium_graph(mc, port):
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("palette", ["maxdeg", 300])
+def test_philox_draws_medium_graph(mc, port, kernel, palette):
     from mcmc_colorer_b200.graphgen import er_graph_numpy
-    n = 200_000
+    n = 200_001                                          # 4 source chunks, ragged last tile
     cumul, neighs = er_graph_numpy(n, 16, seed=3)
-    nCol = int(np.diff(cumul.astype(np.int64)).max())
+    nCol = int(np.diff(cumul.astype(np.int64)).max()) if palette == "maxdeg" else palette   # 300: u16 colours, 8 mask words
     for proposal in (UNIFORM, DYNAMIC):
-        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=9, convergence=proposal)
+        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=9, convergence=proposal, kernel=kernel)
         ch.init_colors(None)
         c = port.init_colors(9, n, nCol)
         assert np.array_equal(ch.get_colors(), c)
@@ -224,6 +243,29 @@ def skewed_graph(n, hubs, seed):
     lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
     from mcmc_colorer_b200.graphgen import _csr_from_undirected_numpy
     return _csr_from_undirected_numpy(lo, hi, n)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
+def test_skewed_degrees_moderate(mc, port, proposal, kernel):
+    """heavy (warp-per-vertex) rows and empty rows on both kernels; hubs beyond a tile are direct-kernel only (below)"""
+    n = 40_003
+    cumul, neighs = skewed_graph(n, hubs=[(5, 6_000), (300, 2_500), (301, 700), (20_000, 100), (39_000, 66)], seed=8)
+    nCol = 150
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=3, kernel=kernel)
+    ch.init_colors(None)
+    c = port.init_colors(3, n, nCol)
+    masks, same = ch.debug_all_occupancy()
+    occ = unpack_masks(masks, nCol)
+    for v in [0, 5, 6, 300, 301, 302, 20_000, 39_000, n - 1] + list(range(7, n, 1999)):
+        assert np.array_equal(occ[v], port.occupancy(v, cumul, neighs, c, nCol)[0]), v
+    for s in range(1, 4):
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, EPS, c, port.tape(3, s, n, proposal), proposal)
+        assert np.array_equal(ch.get_colors(), c), s
+    st = ch.status()
+    assert st.conflictEdges == port.conflict_edges(cumul, neighs, c)
+    ch.close()
 
 
 @pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
@@ -359,12 +401,13 @@ def test_reference_shaped_run_writes_logs(mc, port, c1_graph, pins, tmp_path):
 # ------------------------------------------------------------------------------------------------------------
 # BASELINE config 2 size (n = 1M, mean degree 32): oracle on a 3-sweep replay + numpy restatement of the counters
 # ------------------------------------------------------------------------------------------------------------
-def test_config2_size(mc, port):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config2_size(mc, port, kernel):
     from mcmc_colorer_b200.graphgen import er_graph_numpy
     n = 1_000_000
     cumul, neighs = er_graph_numpy(n, 32, seed=42)
     nCol = int(np.diff(cumul.astype(np.int64)).max())
-    ch = make_chain(mc, cumul, neighs, nCol, proposal=UNIFORM, seed=1, convergence=0)
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=UNIFORM, seed=1, convergence=0, kernel=kernel)
     ch.init_colors(None)
     c = port.init_colors(1, n, nCol)
     assert np.array_equal(ch.get_colors(), c)
