@@ -210,7 +210,8 @@ def test_philox_draws_medium_graph(mc, port, kernel, palette):
     cumul, neighs = er_graph_numpy(n, 16, seed=3)
     nCol = int(np.diff(cumul.astype(np.int64)).max()) if palette == "maxdeg" else palette   # 300: u16 colours, 8 mask words
     for proposal in (UNIFORM, DYNAMIC):
-        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=9, convergence=proposal, kernel=kernel)
+        # replay: keep sweeping after the chain became proper (a 300-colour palette converges in 2 sweeps), like the port loop below
+        ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=9, convergence=proposal, kernel=kernel, replay=True)
         ch.init_colors(None)
         c = port.init_colors(9, n, nCol)
         assert np.array_equal(ch.get_colors(), c)
