@@ -181,23 +181,35 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 		// then 8 entries per thread per step: one 128-bit load of local ids, 8 shared-memory gathers, one packed store
 		const uint32_t body = min(end, (beg + 7u) & ~7u);
 		if (beg + tid < body) ecol[beg + tid] = chunk[bl.srcLocal[beg + tid]];
-		for (uint32_t i = body + 8u * tid; i < end; i += 8u * kThreadsA) {
-			if (i + 8u <= end) {
-				const uint4 ids = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
-				const uint32_t c0 = chunk[ids.x & 0xffffu], c1 = chunk[ids.x >> 16], c2 = chunk[ids.y & 0xffffu], c3 = chunk[ids.y >> 16];
-				const uint32_t c4 = chunk[ids.z & 0xffffu], c5 = chunk[ids.z >> 16], c6 = chunk[ids.w & 0xffffu], c7 = chunk[ids.w >> 16];
-				if (sizeof(ColT) == 1) {
-					uint2 pk;
-					pk.x = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-					pk.y = c4 | (c5 << 8) | (c6 << 16) | (c7 << 24);
-					__stcs(reinterpret_cast<uint2 *>(ecol + i), pk);
-				} else {
-					uint4 pk;
-					pk.x = c0 | (c1 << 16); pk.y = c2 | (c3 << 16); pk.z = c4 | (c5 << 16); pk.w = c6 | (c7 << 16);
-					__stcs(reinterpret_cast<uint4 *>(ecol + i), pk);
+		// four 128-bit id loads in flight per thread (the pass is pure streaming: bytes in flight = bandwidth)
+		constexpr uint32_t kU = 4;
+		for (uint32_t i0 = body + 8u * tid; i0 < end; i0 += 8u * kThreadsA * kU) {
+			uint4 ids[kU];
+#pragma unroll
+			for (uint32_t k = 0; k < kU; ++k) {
+				const uint32_t i = i0 + k * 8u * kThreadsA;
+				if (i + 8u <= end) ids[k] = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
+			}
+#pragma unroll
+			for (uint32_t k = 0; k < kU; ++k) {
+				const uint32_t i = i0 + k * 8u * kThreadsA;
+				if (i + 8u <= end) {
+					const uint4 d = ids[k];
+					const uint32_t c0 = chunk[d.x & 0xffffu], c1 = chunk[d.x >> 16], c2 = chunk[d.y & 0xffffu], c3 = chunk[d.y >> 16];
+					const uint32_t c4 = chunk[d.z & 0xffffu], c5 = chunk[d.z >> 16], c6 = chunk[d.w & 0xffffu], c7 = chunk[d.w >> 16];
+					if (sizeof(ColT) == 1) {
+						uint2 pk;
+						pk.x = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+						pk.y = c4 | (c5 << 8) | (c6 << 16) | (c7 << 24);
+						__stcs(reinterpret_cast<uint2 *>(ecol + i), pk);
+					} else {
+						uint4 pk;
+						pk.x = c0 | (c1 << 16); pk.y = c2 | (c3 << 16); pk.z = c4 | (c5 << 16); pk.w = c6 | (c7 << 16);
+						__stcs(reinterpret_cast<uint4 *>(ecol + i), pk);
+					}
+				} else if (i < end) {
+					for (uint32_t j = i; j < end; ++j) ecol[j] = chunk[bl.srcLocal[j]];
 				}
-			} else {
-				for (uint32_t j = i; j < end; ++j) ecol[j] = chunk[bl.srcLocal[j]];
 			}
 		}
 	}
@@ -206,7 +218,9 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 // ------------------------------------------------------------------------------------------------------------------
 // pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes) {
+constexpr uint32_t kQueueCap = kThreadsB;   // deferred CDF walks per group of kThreadsB vertices
+
+__host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	size_t b = 0;
 	b += sizeof(uint32_t) * (size_t)(TV + 4);              // s_rp
 	b += sizeof(uint32_t) * (size_t)((P + 1 + 3) & ~3u);   // s_so
@@ -218,13 +232,13 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint32_t) * 64;                            // s_red
 	b += sizeof(uint16_t) * (size_t)((TV + 7) & ~7u);      // s_heavy
 	b = (b + 15) & ~(size_t)15;
+	if (W <= 2) b += (size_t)kQueueCap * (8 * W + 16);      // walk queue (mask, lv/own, u/w)
 	b += (size_t)colBytes * (stageCap + 16);               // stage
-	b += (size_t)colBytes * (stageCap + 16);               // s_col
 	return (b + 15) & ~(size_t)15;
 }
 
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsB)
+__global__ void __launch_bounds__(kThreadsB, (W <= 2 ? 2 : 1))
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t nCol = a.nCol, P = bl.P, TV = bl.TV;
@@ -239,8 +253,16 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 64);
 	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + ((TV + 7) & ~7u)) - smem_raw);
 	off = (off + 15) & ~(size_t)15;
+	WalkQueue<W> wq{};
+	constexpr bool useQueue = W <= 2;
+	if (useQueue) {
+		wq.count = s_ctl + 3; wq.cap = kQueueCap;
+		wq.mask = reinterpret_cast<unsigned long long *>(smem_raw + off);
+		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)kQueueCap * W);
+		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kQueueCap);
+		off += (size_t)kQueueCap * (8 * W + 16);
+	}
 	ColT * stage = reinterpret_cast<ColT *>(smem_raw + off);
-	ColT * s_col = stage + (bl.stageCap + 16);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nWarps = kThreadsB / 32;
@@ -295,36 +317,11 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			}
 		}
 		__syncthreads();
-		// ---- phase 1': CSR order through the static permutation: s_col[e - ea] = stage[gidx[e]] ----
-		const uint32_t e0 = s_rp[0], e1 = s_rp[nv];
-		const uint32_t ea = e0 & ~7u;
-		{
-			const uint32_t nOct = (e1 - ea + 7u) >> 3;
-			for (uint32_t o = tid; o < nOct; o += kThreadsB) {
-				const uint4 gi = __ldcs(reinterpret_cast<const uint4 *>(bl.gidx + ea + 8u * o));
-				const uint32_t lim = e1 - (ea + 8u * o);       // valid entries in this octet from the top; entries below e0 are other tiles' (harmless, but their indices may exceed this tile's stage)
-				uint32_t idx[8] = {gi.x & 0xffffu, gi.x >> 16, gi.y & 0xffffu, gi.y >> 16, gi.z & 0xffffu, gi.z >> 16, gi.w & 0xffffu, gi.w >> 16};
-				uint32_t c[8];
-#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					const bool ok = (uint32_t)j < lim && (ea + 8u * o + j) >= e0;
-					c[j] = ok ? (uint32_t)stage[idx[j]] : 0u;
-				}
-				if (sizeof(ColT) == 1) {
-					uint2 pk;
-					pk.x = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-					pk.y = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
-					*reinterpret_cast<uint2 *>(s_col + 8u * o) = pk;
-				} else {
-					uint4 pk;
-					pk.x = c[0] | (c[1] << 16); pk.y = c[2] | (c[3] << 16); pk.z = c[4] | (c[5] << 16); pk.w = c[6] | (c[7] << 16);
-					*reinterpret_cast<uint4 *>(s_col + 8u * o) = pk;
-				}
-			}
-		}
-		if (tid == 0) s_ctl[1] = 0u;
+		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static permutation gidx
+		//      (CSR order, u16: where edge e's colour sits in this tile's stage).  Thread per vertex; the 2-byte
+		//      indices of a row are fetched 4 at a time once the row pointer is 8-byte aligned. ----
+		if (tid == 0) { s_ctl[1] = 0u; s_ctl[3] = 0u; }
 		__syncthreads();
-		// ---- phases 2-3: thread per vertex (light), warp per vertex (heavy) ----
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
 			const uint32_t slot = g + tid;
 			if (slot < nv) {
@@ -336,36 +333,51 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 #pragma unroll
 					for (int w = 0; w < W; ++w) m[w] = 0ull;
 					uint32_t same = 0;
-					const ColT * p = s_col + (myBeg - ea);
-					for (uint32_t i = 0; i < deg; ++i) {
-						const uint32_t c = p[i];
+					auto add = [&](uint32_t idx) {
+						const uint32_t c = stage[idx];
 						same += (c == own);
 						if (W == 1) m[0] |= 1ull << c;
 						else {
 #pragma unroll
 							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
 						}
+					};
+					const uint16_t * gp = bl.gidx + myBeg;
+					uint32_t i = 0;
+					for (; i < deg && ((myBeg + i) & 3u); ++i) add(__ldg(gp + i));            // head, up to 3 entries
+					for (; i + 4u <= deg; i += 4u) {                                          // body, 8-byte loads
+						const uint2 q = __ldg(reinterpret_cast<const uint2 *>(gp + i));
+						add(q.x & 0xffffu); add(q.x >> 16); add(q.y & 0xffffu); add(q.y >> 16);
 					}
-					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol);
+					for (; i < deg; ++i) add(__ldg(gp + i));                                  // tail
+					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
+					                             useQueue ? &wq : nullptr);
 				} else {
 					s_heavy[atomicAdd(&s_ctl[1], 1u)] = (uint16_t)slot;
 				}
 			}
+			if (useQueue) {                          // walk the parked conflicting vertices with dense lanes
+				__syncthreads();
+				const uint32_t qn = s_ctl[3];
+				drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn, s_dist, s_hist, tid, kThreadsB);
+				__syncthreads();
+				if (tid == 0) s_ctl[3] = 0u;
+				__syncthreads();
+			}
 		}
 		__syncthreads();
 		const uint32_t nHeavy = s_ctl[1];
-		for (uint32_t h = warp; h < nHeavy; h += nWarps) {
+		for (uint32_t h = warp; h < nHeavy; h += nWarps) {       // warp per heavy vertex
 			const uint32_t slot = s_heavy[h];
 			const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
 			const uint32_t gv = a.vBegin + v0 + slot;
 			const uint32_t own = (uint32_t)cur[gv];
-			const ColT * p = s_col + (hb - ea);
 			unsigned long long m[W];
 #pragma unroll
 			for (int w = 0; w < W; ++w) m[w] = 0ull;
 			uint32_t same = 0;
 			for (uint32_t i = lane; i < hd; i += 32) {
-				const uint32_t c = p[i];
+				const uint32_t c = stage[__ldg(bl.gidx + hb + i)];
 				same += (c == own);
 #pragma unroll
 				for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;

@@ -89,7 +89,7 @@ template <int W, typename ColT>
 cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	BlockedLayout & L = h->bl;
 	L.smemA = (size_t)kChunkV * sizeof(ColT);
-	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.P, L.TV, L.stageCap, (int)sizeof(ColT));
+	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.P, L.TV, L.stageCap, (int)sizeof(ColT), W);
 	cudaError_t e = cudaFuncSetAttribute(blocked_gather_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemA);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
@@ -323,7 +323,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
 		const bool want = forceBlocked || (!forceDirect && nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18));
 		if (want) {
-			uint32_t capBytes = 32768;
+			uint32_t capBytes = 65536;   // stage bytes per tile (u8: 64 Ki entries, the u16 index limit)
 			if (const char * env = getenv("MCMCB200_STAGE_CAP_BYTES")) capBytes = (uint32_t)strtoul(env, nullptr, 10);
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes,
 			                                     h->stream, &h->launches);

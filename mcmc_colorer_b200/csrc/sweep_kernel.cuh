@@ -144,17 +144,43 @@ __device__ __noinline__ uint32_t walk_stay(uint32_t nCol, uint32_t own, float ep
 	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
 }
 
-// conflicting vertex with free colours: occupied colours weigh eps, free ones freeW (UNIFORM) or dist[k]+r (DYNAMIC)
+// conflicting vertex with free colours: occupied colours weigh eps, free ones freeW (UNIFORM) or dist[k]+r (DYNAMIC).
+// The running sum is non-decreasing (all addends >= 0; the DYNAMIC corner r < 0 takes the one-step loop), so the
+// stop test is made once per 4 colours and the first crossing inside the block is located afterwards: ~4.5 instead of
+// 10 instructions per colour, with exactly the reference's sequence of float32 partial sums.
 template <int W, bool kDyn>
 __device__ __forceinline__ uint32_t walk_conflicting(const unsigned long long (&m)[W], uint32_t nCol, float eps,
                                                      float freeW, float r, const float * s_dist, float u) {
 	float cdf = 0.0f;
+	const bool blocks = !kDyn || r >= 0.0f;
 #pragma unroll
 	for (int h = 0; h < 2 * W; ++h) {
 		if ((uint32_t)(h * 32) < nCol) {
 			uint32_t bits = (h & 1) ? (uint32_t)(m[h >> 1] >> 32) : (uint32_t)m[h >> 1];
 			const uint32_t lim = min(32u, nCol - (uint32_t)(h * 32));
-			for (uint32_t b = 0; b < lim; ++b) {
+			uint32_t b = 0;
+			if (blocks) {
+				for (; b + 4u <= lim; b += 4u) {
+					float q0, q1, q2, q3;
+					if (kDyn) {
+						const float * d = s_dist + h * 32 + b;
+						q0 = (bits & 1u) ? eps : __fadd_rn(d[0], r); q1 = (bits & 2u) ? eps : __fadd_rn(d[1], r);
+						q2 = (bits & 4u) ? eps : __fadd_rn(d[2], r); q3 = (bits & 8u) ? eps : __fadd_rn(d[3], r);
+					} else {
+						q0 = (bits & 1u) ? eps : freeW; q1 = (bits & 2u) ? eps : freeW;
+						q2 = (bits & 4u) ? eps : freeW; q3 = (bits & 8u) ? eps : freeW;
+					}
+					const float c1 = __fadd_rn(cdf, q0), c2 = __fadd_rn(c1, q1), c3 = __fadd_rn(c2, q2), c4 = __fadd_rn(c3, q3);
+					if (kDyn ? (c4 >= u) : (c4 > u)) {
+						const uint32_t first = (kDyn ? (c1 >= u) : (c1 > u)) ? 0u : (kDyn ? (c2 >= u) : (c2 > u)) ? 1u
+						                     : (kDyn ? (c3 >= u) : (c3 > u)) ? 2u : 3u;
+						return (uint32_t)(h * 32) + b + first;
+					}
+					cdf = c4;
+					bits >>= 4;
+				}
+			}
+			for (; b < lim; ++b) {
 				float q;
 				if (kDyn) q = (bits & 1u) ? eps : __fadd_rn(s_dist[h * 32 + b], r);
 				else q = (bits & 1u) ? eps : freeW;
@@ -167,6 +193,28 @@ __device__ __forceinline__ uint32_t walk_conflicting(const unsigned long long (&
 	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
 }
 
+// Deferred CDF walks: conflicting vertices are parked in shared memory and walked later by densely packed lanes
+// (in the first sweeps ~1/3 of the vertices conflict, later almost none: without the queue nearly every warp would
+// run the full walk for a handful of active lanes).
+template <int W>
+struct WalkQueue {
+	uint32_t * count;               // shared counter
+	uint32_t cap;
+	unsigned long long * mask;      // [cap][W]
+	uint32_t * lvOwn;               // [cap][2]: local vertex index, own colour
+	float * uw;                     // [cap][2]: draw, freeW (UNIFORM) or r (DYNAMIC)
+	static __host__ __device__ constexpr size_t bytes_per_entry() { return 8 * W + 16; }
+};
+
+// colour write + taboo + class-size deltas of a vertex whose new colour is known
+template <typename ColT>
+__device__ __forceinline__ void finish_vertex(const SweepArgs & a, ColT * __restrict__ nxt, uint32_t lv, uint32_t myOwn, uint32_t newc,
+                                              int * s_hist, bool touchTaboo) {
+	if (touchTaboo && a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);   // coloringMCMC_CPU.cpp:526
+	nxt[a.vBegin + lv] = (ColT)newc;
+	if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PHASE 3 for one vertex (shared by the direct-gather kernel and the source-blocked kernel): conflict flag, free
 // colour count, taboo gate, draw, proposal, colour write, class-size deltas.
@@ -176,7 +224,8 @@ template <int W, typename ColT, bool kDyn>
 __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, ColT * __restrict__ nxt, uint32_t v, uint32_t lv,
                                               uint32_t myOwn, const unsigned long long (&m)[W], uint32_t same,
                                               const float * s_S, const float * s_dist, int * s_hist, float stayW,
-                                              unsigned long long & accDirected, unsigned long long & accViol) {
+                                              unsigned long long & accDirected, unsigned long long & accViol,
+                                              const WalkQueue<W> * queue = nullptr) {
 	constexpr bool isDyn = kDyn;
 	const uint32_t nCol = a.nCol;
 	const float eps = a.eps;
@@ -231,13 +280,38 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 					}
 					r = __fdiv_rn(rem, __uint2float_rn(Zp));
 				}
+				if (queue != nullptr) {
+					const uint32_t qi = atomicAdd(queue->count, 1u);
+					if (qi < queue->cap) {                    // park the walk; drained by dense lanes (drain_walk_queue)
+#pragma unroll
+						for (int w = 0; w < W; ++w) queue->mask[(size_t)qi * W + w] = m[w];
+						queue->lvOwn[2 * qi] = lv; queue->lvOwn[2 * qi + 1] = myOwn;
+						queue->uw[2 * qi] = u; queue->uw[2 * qi + 1] = isDyn ? r : freeW;
+						return;
+					}
+				}
 				newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
 			}
-			if (a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);  // :526
+			finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, true);
+			return;
 		}
 	}
-	nxt[v] = (ColT)newc;
-	if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
+	finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, false);
+}
+
+template <int W, typename ColT, bool kDyn>
+__device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __restrict__ nxt, const WalkQueue<W> & q, uint32_t count,
+                                                 const float * s_dist, int * s_hist, int tid, int nThreads) {
+	count = min(count, q.cap);
+	for (uint32_t i = tid; i < count; i += nThreads) {
+		unsigned long long m[W];
+#pragma unroll
+		for (int w = 0; w < W; ++w) m[w] = q.mask[(size_t)i * W + w];
+		const uint32_t lv = q.lvOwn[2 * i], own = q.lvOwn[2 * i + 1];
+		const float u = q.uw[2 * i], x = q.uw[2 * i + 1];
+		const uint32_t newc = walk_conflicting<W, kDyn>(m, a.nCol, a.eps, x, x, s_dist, u);
+		finish_vertex<ColT>(a, nxt, lv, own, newc, s_hist, true);
+	}
 }
 
 template <int W, typename ColT, bool kDyn>
