@@ -27,7 +27,10 @@ namespace mcmcb200 {
 constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
 constexpr int      kThreadsA  = 256;
-constexpr int      kThreadsB  = 512;
+#ifndef MCMCB200_THREADS_B
+#define MCMCB200_THREADS_B 512
+#endif
+constexpr int      kThreadsB  = MCMCB200_THREADS_B;
 constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
 constexpr uint32_t kRunLanes  = 8;                   // lanes cooperating on one (bucket, tile) run in pass B
 
@@ -247,7 +250,7 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 }
 
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsB, (W <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(kThreadsB, (W <= 2 ? (1024 / kThreadsB) : 1))
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t nCol = a.nCol, P = bl.P, TV = bl.TV;
@@ -444,7 +447,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	accDirected = warp_reduce_add64(accDirected);
 	accViol = warp_reduce_add64(accViol);
 	__syncthreads();
-	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }
+	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }   // nWarps <= 16
 	__syncthreads();
 	if (tid == 0) {
 		unsigned long long d = 0, vv = 0;
