@@ -9,7 +9,7 @@
 namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
-	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.perm); cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.tileBase); cudaFree(L.items);
+	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.items);
 	L = BlockedLayout{};
 }
 
@@ -25,7 +25,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	const uint32_t nnz = (uint32_t)nnzLocal;
 	const uint32_t P = (nGlobal + kChunkV - 1) / kChunkV;
 	const uint32_t stageCap = (stageCapBytes / (uint32_t)colBytes) & ~15u;
-	if (stageCap < 1024 || stageCap > 65520) return cudaSuccess;   // positions are u16 and 0xffff marks padding
+	if (stageCap < 1024 || stageCap > 65536) return cudaSuccess;
 
 	uint32_t * d_tmp = nullptr;          // [2]: scratch scalars
 	uint32_t * d_tileE = nullptr;
@@ -109,12 +109,10 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	blk_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_gs, d_scanT, d_plenT, P, numTiles, L.runStart, L.stageOff, d_tmp); (*launches)++;
 	BLK_CU(cudaMalloc(&L.srcLocal, sizeof(uint16_t) * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.srcLocal, 0, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));
-	BLK_CU(cudaMalloc(&L.perm, sizeof(uint16_t) * ((size_t)L.totalPadded + 16)));
-	BLK_CU(cudaMemsetAsync(L.perm, 0xff, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));   // padding entries: 0xffff -> dump slot
-	BLK_CU(cudaMalloc(&L.tileBase, sizeof(uint32_t) * ((size_t)numTiles + 1)));
-	blk_tile_base_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_scanT, P, numTiles, L.totalPadded, L.tileBase); (*launches)++;
+	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
+	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
 	blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
-	                                                                d_scanT, L.srcLocal, L.perm); (*launches)++;
+	                                                                L.stageOff, L.srcLocal, L.gidx); (*launches)++;
 	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
 	// ---- pass-A work items: (bucket, begin, end), at most kItemEntries entries each ----
@@ -147,7 +145,7 @@ done:
 inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	BlockedArgs b{};
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
-	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.perm = L.perm; b.tileBase = L.tileBase; b.runStart = L.runStart; b.stageOff = L.stageOff;
+	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.runStart = L.runStart; b.stageOff = L.stageOff;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;
 }

@@ -43,10 +43,9 @@ struct BlockedLayout {
 	uint32_t  totalPadded = 0;   // entries in srcLocal / ecol
 	uint16_t * srcLocal = nullptr;   // [totalPadded], bucket-major
 	void *     ecol = nullptr;       // ColT[totalPadded]
-	uint16_t * perm = nullptr;       // [totalPadded], tile-major stage order: CSR position (within the tile) of each staged entry
+	uint16_t * gidx = nullptr;       // [nnzLocal (+8)], CSR order
 	uint32_t * runStart = nullptr;   // [numTiles][P]    start of run (b,T) in srcLocal/ecol
-	uint32_t * stageOff = nullptr;   // [numTiles][P+1]  start of run (b,T) inside the tile's block of perm
-	uint32_t * tileBase = nullptr;   // [numTiles+1]     start of tile T's block in perm
+	uint32_t * stageOff = nullptr;   // [numTiles][P+1]  start of run (b,T) inside the tile's stage buffer
 	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
 	uint32_t  numItems = 0;
 	size_t    smemA = 0, smemB = 0;
@@ -57,8 +56,7 @@ struct BlockedArgs {
 	uint32_t P, TV, numTiles, stageCap;
 	const uint16_t * srcLocal;
 	void * ecol;
-	const uint16_t * perm;
-	const uint32_t * tileBase;   // [numTiles+1] start of tile T in perm
+	const uint16_t * gidx;
 	const uint32_t * runStart;
 	const uint32_t * stageOff;
 	const uint32_t * items;
@@ -134,8 +132,7 @@ __global__ void blk_tables_kernel(const uint32_t * gs, const uint32_t * scanT, c
 
 __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * vals, uint32_t nnz, const uint32_t * neighs,
                                         const uint32_t * tileE, uint32_t numTiles, uint32_t P, const uint32_t * us /* [P][numTiles] first sorted index */,
-                                        const uint32_t * gs /* [P][numTiles] */, const uint32_t * scanT /* [numTiles][P] */,
-                                        uint16_t * srcLocal, uint16_t * perm) {
+                                        const uint32_t * gs /* [P][numTiles] */, const uint32_t * stageOff, uint16_t * srcLocal, uint16_t * gidx) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nnz) return;
 	const uint32_t e = vals[i], b = keys[i];
@@ -143,13 +140,7 @@ __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * 
 	const size_t idx = (size_t)b * numTiles + T;
 	const uint32_t r = i - us[idx];
 	srcLocal[gs[idx] + r] = (uint16_t)(neighs[e] & (kChunkV - 1u));
-	perm[scanT[(size_t)T * P + b] + r] = (uint16_t)(e - tileE[T]);     // CSR position of this entry inside its tile
-}
-
-__global__ void blk_tile_base_kernel(const uint32_t * scanT, uint32_t P, uint32_t numTiles, uint32_t total, uint32_t * tileBase) {
-	const uint32_t T = blockIdx.x * blockDim.x + threadIdx.x;
-	if (T < numTiles) tileBase[T] = scanT[(size_t)T * P];
-	if (T == numTiles) tileBase[T] = total;
+	gidx[e] = (uint16_t)(stageOff[(size_t)T * (P + 1) + b] + r);
 }
 
 __global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32_t numTiles, uint32_t total, uint32_t * bs) {
@@ -245,7 +236,7 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint16_t) * (size_t)((TV + 7) & ~7u);      // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)kQueueCap * (8 * W + 16);      // walk queue (mask, lv/own, u/w)
-	b += (size_t)colBytes * (stageCap + 32);               // s_col: the tile's neighbour colours in CSR order (+ dump slots)
+	b += (size_t)colBytes * (stageCap + 16);               // stage
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -274,7 +265,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kQueueCap);
 		off += (size_t)kQueueCap * (8 * W + 16);
 	}
-	ColT * s_col = reinterpret_cast<ColT *>(smem_raw + off);
+	ColT * stage = reinterpret_cast<ColT *>(smem_raw + off);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nWarps = kThreadsB / 32;
@@ -314,66 +305,26 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		for (uint32_t b = tid; b <= P; b += kThreadsB) s_so[b] = bl.stageOff[(size_t)T * (P + 1) + b];
 		for (uint32_t b = tid; b < P; b += kThreadsB) s_rs[b] = bl.runStart[(size_t)T * P + b];
 		__syncthreads();
-		// ---- phase 0/1: the tile's P short runs of gathered colours (bucket-major in ecol) are scattered straight into
-		//      CSR order in shared memory through the static permutation (tile-major, so its read is one contiguous
-		//      stream).  kRunLanes lanes per run, 4 entries per lane, kRunUnroll runs in flight per lane group. ----
-		const uint32_t e0 = s_rp[0];
-		const uint32_t dump = bl.stageCap;                       // padding entries carry 0xffff and land in the dump slots
+		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules) ----
 		{
 			constexpr uint32_t groups = kThreadsB / kRunLanes;
-			constexpr uint32_t kRunUnroll = 4;
 			const uint32_t grp = tid / kRunLanes, gl = tid % kRunLanes;
-			const uint16_t * __restrict__ pm = bl.perm + bl.tileBase[T];
-			for (uint32_t b0 = grp; b0 < P; b0 += groups * kRunUnroll) {
-				uint32_t colw[kRunUnroll]; uint2 pw[kRunUnroll]; bool have[kRunUnroll];
-#pragma unroll
-				for (uint32_t k = 0; k < kRunUnroll; ++k) {
-					const uint32_t b = b0 + k * groups;
-					have[k] = false;
-					if (b < P) {
-						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0;
-						const uint32_t w = 4u * gl;
-						if (w < len) {
-							have[k] = true;
-							if (sizeof(ColT) == 1) colw[k] = __ldcs(reinterpret_cast<const uint32_t *>(ecol + s_rs[b] + w));
-							pw[k] = __ldcs(reinterpret_cast<const uint2 *>(pm + o0 + w));
-						}
-					}
-				}
-#pragma unroll
-				for (uint32_t k = 0; k < kRunUnroll; ++k) {
-					if (have[k]) {
-						const uint32_t b = b0 + k * groups;
-						const uint32_t i0 = min(pw[k].x & 0xffffu, dump), i1 = min(pw[k].x >> 16, dump);
-						const uint32_t i2 = min(pw[k].y & 0xffffu, dump), i3 = min(pw[k].y >> 16, dump);
-						if (sizeof(ColT) == 1) {
-							s_col[i0] = (ColT)(colw[k] & 0xffu); s_col[i1] = (ColT)((colw[k] >> 8) & 0xffu);
-							s_col[i2] = (ColT)((colw[k] >> 16) & 0xffu); s_col[i3] = (ColT)(colw[k] >> 24);
-						} else {
-							const uint2 cw = __ldcs(reinterpret_cast<const uint2 *>(ecol + s_rs[b] + 4u * gl));
-							s_col[i0] = (ColT)(cw.x & 0xffffu); s_col[i1] = (ColT)(cw.x >> 16);
-							s_col[i2] = (ColT)(cw.y & 0xffffu); s_col[i3] = (ColT)(cw.y >> 16);
-						}
-					}
-				}
-				// runs longer than 4*kRunLanes entries: remaining granules (rare for sparse tiles)
-#pragma unroll
-				for (uint32_t k = 0; k < kRunUnroll; ++k) {
-					const uint32_t b = b0 + k * groups;
-					if (b < P) {
-						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
-						for (uint32_t w = 4u * (gl + kRunLanes); w < len; w += 4u * kRunLanes) {
-							const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(pm + o0 + w));
-							const uint32_t i0 = min(q.x & 0xffffu, dump), i1 = min(q.x >> 16, dump), i2 = min(q.y & 0xffffu, dump), i3 = min(q.y >> 16, dump);
-							s_col[i0] = ecol[g + w]; s_col[i1] = ecol[g + w + 1]; s_col[i2] = ecol[g + w + 2]; s_col[i3] = ecol[g + w + 3];
-						}
-					}
+			for (uint32_t b = grp; b < P; b += groups) {
+				const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
+				for (uint32_t w = 4u * gl; w < len; w += 4u * kRunLanes) {
+					if (sizeof(ColT) == 1)
+						*reinterpret_cast<uint32_t *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint32_t *>(ecol + g + w));
+					else
+						*reinterpret_cast<uint2 *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint2 *>(ecol + g + w));
 				}
 			}
 		}
+		__syncthreads();
+		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static permutation gidx
+		//      (CSR order, u16: where edge e's colour sits in this tile's stage).  Thread per vertex; the 2-byte
+		//      indices of a row are fetched 4 at a time once the row pointer is 8-byte aligned. ----
 		if (tid == 0) { s_ctl[1] = 0u; s_ctl[3] = 0u; }
 		__syncthreads();
-		// ---- phase 2: occupancy masks, thread per vertex, from the CSR-ordered colours in shared memory ----
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
 			const uint32_t slot = g + tid;
 			if (slot < nv) {
@@ -385,7 +336,8 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 #pragma unroll
 					for (int w = 0; w < W; ++w) m[w] = 0ull;
 					uint32_t same = 0;
-					auto add = [&](uint32_t c) {
+					auto add = [&](uint32_t idx) {
+						const uint32_t c = stage[idx];
 						same += (c == own);
 						if (W == 1) m[0] |= 1ull << c;
 						else {
@@ -393,16 +345,14 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
 						}
 					};
-					uint32_t pos = myBeg - e0;
-					const uint32_t end = pos + deg;
-					if (sizeof(ColT) == 1) {
-						for (; pos < end && (pos & 3u); ++pos) add(s_col[pos]);                    // head bytes
-						for (; pos + 4u <= end; pos += 4u) {                                        // aligned words
-							const uint32_t w4 = *reinterpret_cast<const uint32_t *>(s_col + pos);
-							add(w4 & 0xffu); add((w4 >> 8) & 0xffu); add((w4 >> 16) & 0xffu); add(w4 >> 24);
-						}
+					const uint16_t * gp = bl.gidx + myBeg;
+					uint32_t i = 0;
+					for (; i < deg && ((myBeg + i) & 3u); ++i) add(__ldg(gp + i));            // head, up to 3 entries
+					for (; i + 4u <= deg; i += 4u) {                                          // body, 8-byte loads
+						const uint2 q = __ldg(reinterpret_cast<const uint2 *>(gp + i));
+						add(q.x & 0xffffu); add(q.x >> 16); add(q.y & 0xffffu); add(q.y >> 16);
 					}
-					for (; pos < end; ++pos) add(s_col[pos]);                                      // tail (and the u16 path)
+					for (; i < deg; ++i) add(__ldg(gp + i));                                  // tail
 					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 					                             useQueue ? &wq : nullptr);
 				} else {
@@ -430,7 +380,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			for (int w = 0; w < W; ++w) m[w] = 0ull;
 			uint32_t same = 0;
 			for (uint32_t i = lane; i < hd; i += 32) {
-				const uint32_t c = s_col[hb - e0 + i];
+				const uint32_t c = stage[__ldg(bl.gidx + hb + i)];
 				same += (c == own);
 #pragma unroll
 				for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
@@ -447,7 +397,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	accDirected = warp_reduce_add64(accDirected);
 	accViol = warp_reduce_add64(accViol);
 	__syncthreads();
-	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }   // nWarps <= 16
+	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }
 	__syncthreads();
 	if (tid == 0) {
 		unsigned long long d = 0, vv = 0;
