@@ -145,6 +145,10 @@ done:
 inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	BlockedArgs b{};
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
+	{   // lanes per run from the mean padded run length (in 4-entry granules)
+		const double granules = (double)L.totalPadded / 4.0 / ((double)L.P * L.numTiles);
+		b.runLanes = granules > 12.0 ? 32u : granules > 5.0 ? 16u : 8u;
+	}
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.runStart = L.runStart; b.stageOff = L.stageOff;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;

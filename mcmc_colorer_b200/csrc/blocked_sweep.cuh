@@ -19,6 +19,7 @@
 // the 8 of the reference layout -- the static preprocessing shrinks the index stream from u32 to 2 x u16.
 #pragma once
 #include <cub/cub.cuh>
+#include <type_traits>
 
 #include "sweep_kernel.cuh"
 
@@ -32,7 +33,6 @@ constexpr int      kThreadsA  = 256;
 #endif
 constexpr int      kThreadsB  = MCMCB200_THREADS_B;
 constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
-constexpr uint32_t kRunLanes  = 8;                   // lanes cooperating on one (bucket, tile) run in pass B
 
 struct BlockedLayout {
 	bool      valid = false;
@@ -54,6 +54,7 @@ struct BlockedLayout {
 
 struct BlockedArgs {
 	uint32_t P, TV, numTiles, stageCap;
+	uint32_t runLanes;           // lanes cooperating on one (bucket, tile) run in pass B: 8, 16 or 32 (by mean run length)
 	const uint16_t * srcLocal;
 	void * ecol;
 	const uint16_t * gidx;
@@ -221,7 +222,7 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 // ------------------------------------------------------------------------------------------------------------------
 // pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kQueueCap = kThreadsB;   // deferred CDF walks per group of kThreadsB vertices
+constexpr uint32_t kWarpQueueCap = 64;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier)
 
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	size_t b = 0;
@@ -232,10 +233,10 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
 	b += sizeof(uint32_t) * 8;                             // s_ctl
-	b += sizeof(uint32_t) * 64;                            // s_red
+	b += sizeof(uint32_t) * 96;                            // s_red (32 x u64) + per-warp queue counters (32 x u32)
 	b += sizeof(uint16_t) * (size_t)((TV + 7) & ~7u);      // s_heavy
 	b = (b + 15) & ~(size_t)15;
-	if (W <= 2) b += (size_t)kQueueCap * (8 * W + 16);      // walk queue (mask, lv/own, u/w)
+	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
 	b += (size_t)colBytes * (stageCap + 16);               // stage
 	return (b + 15) & ~(size_t)15;
 }
@@ -253,17 +254,21 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
 	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
 	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 32 x u64
-	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 64);
+	uint32_t * s_qcnt = s_ctl + 8 + 64;                                               // 32 x u32
+	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 96);
 	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + ((TV + 7) & ~7u)) - smem_raw);
 	off = (off + 15) & ~(size_t)15;
 	WalkQueue<W> wq{};
 	constexpr bool useQueue = W <= 2;
-	if (useQueue) {
-		wq.count = s_ctl + 3; wq.cap = kQueueCap;
-		wq.mask = reinterpret_cast<unsigned long long *>(smem_raw + off);
-		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)kQueueCap * W);
-		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kQueueCap);
-		off += (size_t)kQueueCap * (8 * W + 16);
+	if (useQueue) {                                           // this warp's private queue
+		constexpr size_t perWarp = (size_t)kWarpQueueCap * (8 * W + 16);
+		unsigned char * qb = smem_raw + off + (size_t)(threadIdx.x >> 5) * perWarp;
+		wq.count = s_qcnt + (threadIdx.x >> 5);
+		wq.cap = kWarpQueueCap;
+		wq.mask = reinterpret_cast<unsigned long long *>(qb);
+		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)kWarpQueueCap * W);
+		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kWarpQueueCap);
+		off += (size_t)(kThreadsB / 32) * perWarp;
 	}
 	ColT * stage = reinterpret_cast<ColT *>(smem_raw + off);
 
@@ -305,17 +310,36 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		for (uint32_t b = tid; b <= P; b += kThreadsB) s_so[b] = bl.stageOff[(size_t)T * (P + 1) + b];
 		for (uint32_t b = tid; b < P; b += kThreadsB) s_rs[b] = bl.runStart[(size_t)T * P + b];
 		__syncthreads();
-		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules) ----
+		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules).
+		//      runLanes lanes per run, 4 runs in flight per lane group (loads first, then the stores). ----
 		{
-			constexpr uint32_t groups = kThreadsB / kRunLanes;
-			const uint32_t grp = tid / kRunLanes, gl = tid % kRunLanes;
-			for (uint32_t b = grp; b < P; b += groups) {
-				const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
-				for (uint32_t w = 4u * gl; w < len; w += 4u * kRunLanes) {
-					if (sizeof(ColT) == 1)
-						*reinterpret_cast<uint32_t *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint32_t *>(ecol + g + w));
-					else
-						*reinterpret_cast<uint2 *>(stage + o0 + w) = __ldcs(reinterpret_cast<const uint2 *>(ecol + g + w));
+			const uint32_t RL = bl.runLanes;
+			const uint32_t groups = kThreadsB / RL;
+			const uint32_t grp = tid / RL, gl = tid % RL;
+			typedef typename std::conditional<sizeof(ColT) == 1, uint32_t, uint2>::type Gran;   // 4 colours
+			constexpr uint32_t kRU = 4;
+			for (uint32_t b0 = grp; b0 < P; b0 += groups * kRU) {
+				Gran v[kRU]; uint32_t dst[kRU]; bool have[kRU];
+#pragma unroll
+				for (uint32_t k = 0; k < kRU; ++k) {
+					const uint32_t b = b0 + k * groups;
+					have[k] = false;
+					if (b < P) {
+						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, w = 4u * gl;
+						if (w < len) { have[k] = true; dst[k] = o0 + w; v[k] = __ldcs(reinterpret_cast<const Gran *>(ecol + s_rs[b] + w)); }
+					}
+				}
+#pragma unroll
+				for (uint32_t k = 0; k < kRU; ++k)
+					if (have[k]) *reinterpret_cast<Gran *>(stage + dst[k]) = v[k];
+#pragma unroll
+				for (uint32_t k = 0; k < kRU; ++k) {                   // runs longer than 4*RL entries
+					const uint32_t b = b0 + k * groups;
+					if (b < P) {
+						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
+						for (uint32_t w = 4u * (gl + RL); w < len; w += 4u * RL)
+							*reinterpret_cast<Gran *>(stage + o0 + w) = __ldcs(reinterpret_cast<const Gran *>(ecol + g + w));
+					}
 				}
 			}
 		}
@@ -323,7 +347,8 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static permutation gidx
 		//      (CSR order, u16: where edge e's colour sits in this tile's stage).  Thread per vertex; the 2-byte
 		//      indices of a row are fetched 4 at a time once the row pointer is 8-byte aligned. ----
-		if (tid == 0) { s_ctl[1] = 0u; s_ctl[3] = 0u; }
+		if (tid == 0) s_ctl[1] = 0u;
+		if (useQueue && lane == 0) *wq.count = 0u;
 		__syncthreads();
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
 			const uint32_t slot = g + tid;
@@ -345,28 +370,49 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
 						}
 					};
-					const uint16_t * gp = bl.gidx + myBeg;
-					uint32_t i = 0;
-					for (; i < deg && ((myBeg + i) & 3u); ++i) add(__ldg(gp + i));            // head, up to 3 entries
-					for (; i + 4u <= deg; i += 4u) {                                          // body, 8-byte loads
-						const uint2 q = __ldg(reinterpret_cast<const uint2 *>(gp + i));
-						add(q.x & 0xffffu); add(q.x >> 16); add(q.y & 0xffffu); add(q.y >> 16);
+					// the row's u16 stage indices, fetched as aligned 8-byte words, kPf words in flight; entries of the
+					// first/last word that belong to the neighbouring rows are masked by the unsigned range test
+					const uint32_t a0 = myBeg & ~3u, skip = myBeg - a0;
+					const uint32_t nq = (skip + deg + 3u) >> 2;
+					const uint2 * gq = reinterpret_cast<const uint2 *>(bl.gidx + a0);
+					constexpr uint32_t kPf = 6;
+					for (uint32_t wb = 0; wb < nq; wb += kPf) {
+						uint2 q[kPf];
+#pragma unroll
+						for (uint32_t j = 0; j < kPf; ++j) if (wb + j < nq) q[j] = __ldg(gq + wb + j);
+#pragma unroll
+						for (uint32_t j = 0; j < kPf; ++j) {
+							if (wb + j < nq) {
+								const uint32_t p0 = 4u * (wb + j) - skip;           // position in the row of the word's first entry (wraps below 0)
+								if (p0 < deg) add(q[j].x & 0xffffu);
+								if (p0 + 1u < deg) add(q[j].x >> 16);
+								if (p0 + 2u < deg) add(q[j].y & 0xffffu);
+								if (p0 + 3u < deg) add(q[j].y >> 16);
+							}
+						}
 					}
-					for (; i < deg; ++i) add(__ldg(gp + i));                                  // tail
 					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 					                             useQueue ? &wq : nullptr);
 				} else {
 					s_heavy[atomicAdd(&s_ctl[1], 1u)] = (uint16_t)slot;
 				}
 			}
-			if (useQueue) {                          // walk the parked conflicting vertices with dense lanes
-				__syncthreads();
-				const uint32_t qn = s_ctl[3];
-				drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn, s_dist, s_hist, tid, kThreadsB);
-				__syncthreads();
-				if (tid == 0) s_ctl[3] = 0u;
-				__syncthreads();
+			if (useQueue) {                          // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
+				__syncwarp();
+				const uint32_t qn = min(*wq.count, wq.cap);
+				if (qn >= 32u) {
+					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn - 32u, 32u, s_dist, s_hist, lane);
+					__syncwarp();
+					if (lane == 0) *wq.count = qn - 32u;
+				}
+				__syncwarp();
 			}
+		}
+		if (useQueue) {                              // remainder of this warp's queue
+			__syncwarp();
+			const uint32_t qn = min(*wq.count, wq.cap);
+			drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, s_dist, s_hist, lane);
+			__syncwarp();
 		}
 		__syncthreads();
 		const uint32_t nHeavy = s_ctl[1];

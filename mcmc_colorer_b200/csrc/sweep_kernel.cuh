@@ -299,11 +299,12 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 	finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, false);
 }
 
+// entries [first, first+count) of a queue, one per lane (called by the owning warp; count <= 32)
 template <int W, typename ColT, bool kDyn>
-__device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __restrict__ nxt, const WalkQueue<W> & q, uint32_t count,
-                                                 const float * s_dist, int * s_hist, int tid, int nThreads) {
-	count = min(count, q.cap);
-	for (uint32_t i = tid; i < count; i += nThreads) {
+__device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __restrict__ nxt, const WalkQueue<W> & q, uint32_t first,
+                                                 uint32_t count, const float * s_dist, int * s_hist, int lane) {
+	if ((uint32_t)lane < count) {
+		const uint32_t i = first + lane;
 		unsigned long long m[W];
 #pragma unroll
 		for (int w = 0; w < W; ++w) m[w] = q.mask[(size_t)i * W + w];
