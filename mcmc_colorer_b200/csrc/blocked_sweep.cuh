@@ -313,11 +313,19 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules).
 		//      runLanes lanes per run, 4 runs in flight per lane group (loads first, then the stores). ----
 		{
+#ifdef MCMCB200_RL
+			const uint32_t RL = MCMCB200_RL;
+#else
 			const uint32_t RL = bl.runLanes;
+#endif
 			const uint32_t groups = kThreadsB / RL;
 			const uint32_t grp = tid / RL, gl = tid % RL;
 			typedef typename std::conditional<sizeof(ColT) == 1, uint32_t, uint2>::type Gran;   // 4 colours
+#ifdef MCMCB200_RU
+			constexpr uint32_t kRU = MCMCB200_RU;
+#else
 			constexpr uint32_t kRU = 4;
+#endif
 			for (uint32_t b0 = grp; b0 < P; b0 += groups * kRU) {
 				Gran v[kRU]; uint32_t dst[kRU]; bool have[kRU];
 #pragma unroll
@@ -375,7 +383,11 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 					const uint32_t a0 = myBeg & ~3u, skip = myBeg - a0;
 					const uint32_t nq = (skip + deg + 3u) >> 2;
 					const uint2 * gq = reinterpret_cast<const uint2 *>(bl.gidx + a0);
+#ifdef MCMCB200_PF
+					constexpr uint32_t kPf = MCMCB200_PF;
+#else
 					constexpr uint32_t kPf = 6;
+#endif
 					for (uint32_t wb = 0; wb < nq; wb += kPf) {
 						uint2 q[kPf];
 #pragma unroll
