@@ -222,7 +222,8 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 // ------------------------------------------------------------------------------------------------------------------
 // pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kWarpQueueCap = 64;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier)
+constexpr uint32_t kWarpQueueCap = 48;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier; overflow walks inline)
+constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per tile (overflow is handled by the owning thread)
 
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	size_t b = 0;
@@ -234,7 +235,7 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
 	b += sizeof(uint32_t) * 8;                             // s_ctl
 	b += sizeof(uint32_t) * 96;                            // s_red (32 x u64) + per-warp queue counters (32 x u32)
-	b += sizeof(uint16_t) * (size_t)((TV + 7) & ~7u);      // s_heavy
+	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
 	b += (size_t)colBytes * (stageCap + 16);               // stage
@@ -256,7 +257,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 32 x u64
 	uint32_t * s_qcnt = s_ctl + 8 + 64;                                               // 32 x u32
 	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 96);
-	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + ((TV + 7) & ~7u)) - smem_raw);
+	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + kHeavyCap) - smem_raw);
 	off = (off + 15) & ~(size_t)15;
 	WalkQueue<W> wq{};
 	constexpr bool useQueue = W <= 2;
@@ -324,7 +325,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 #ifdef MCMCB200_RU
 			constexpr uint32_t kRU = MCMCB200_RU;
 #else
-			constexpr uint32_t kRU = 4;
+			constexpr uint32_t kRU = 2;
 #endif
 			for (uint32_t b0 = grp; b0 < P; b0 += groups * kRU) {
 				Gran v[kRU]; uint32_t dst[kRU]; bool have[kRU];
@@ -362,7 +363,12 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			const uint32_t slot = g + tid;
 			if (slot < nv) {
 				const uint32_t myBeg = s_rp[slot], deg = s_rp[slot + 1] - myBeg;
-				if (deg <= (uint32_t)kLightMaxDeg) {
+				bool light = deg <= (uint32_t)kLightMaxDeg;
+				if (!light) {                                          // warp-per-vertex list; if it is full the thread does the row itself
+					const uint32_t hi = atomicAdd(&s_ctl[1], 1u);
+					if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)slot; else light = true;
+				}
+				if (light) {
 					const uint32_t gv = a.vBegin + v0 + slot;
 					const uint32_t own = (uint32_t)cur[gv];
 					unsigned long long m[W];
@@ -386,7 +392,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 #ifdef MCMCB200_PF
 					constexpr uint32_t kPf = MCMCB200_PF;
 #else
-					constexpr uint32_t kPf = 6;
+					constexpr uint32_t kPf = 4;
 #endif
 					for (uint32_t wb = 0; wb < nq; wb += kPf) {
 						uint2 q[kPf];
@@ -405,8 +411,6 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 					}
 					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 					                             useQueue ? &wq : nullptr);
-				} else {
-					s_heavy[atomicAdd(&s_ctl[1], 1u)] = (uint16_t)slot;
 				}
 			}
 			if (useQueue) {                          // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
@@ -427,7 +431,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			__syncwarp();
 		}
 		__syncthreads();
-		const uint32_t nHeavy = s_ctl[1];
+		const uint32_t nHeavy = min(s_ctl[1], kHeavyCap);
 		for (uint32_t h = warp; h < nHeavy; h += nWarps) {       // warp per heavy vertex
 			const uint32_t slot = s_heavy[h];
 			const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
