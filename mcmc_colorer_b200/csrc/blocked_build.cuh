@@ -9,7 +9,8 @@
 namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
-	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.items);
+	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.sliceOff);
+	cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.items);
 	L = BlockedLayout{};
 }
 
@@ -35,6 +36,10 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	uint32_t * d_cnt = nullptr, * d_us = nullptr, * d_plen = nullptr, * d_gs = nullptr, * d_plenT = nullptr, * d_scanT = nullptr, * d_bs = nullptr;
 	uint32_t TV = 0, numTiles = 0, h2[2] = {0, 0};
 	size_t cells = 0;
+	unsigned long long * d_k64[2] = {nullptr, nullptr};
+	uint32_t * d_v32[2] = {nullptr, nullptr};
+	uint32_t * d_words = nullptr;
+	uint32_t numSlices = 0, sellTotal = 0;
 	std::vector<uint32_t> bs, items;
 
 	BLK_CU(cudaMalloc(&d_tmp, 2 * sizeof(uint32_t)));
@@ -115,6 +120,47 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	                                                                L.stageOff, L.srcLocal, L.gidx); (*launches)++;
 	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
+	// ---- SELL-32-sigma copy of gidx for the light rows: per tile, vertices by descending degree; 32-slot slices interleaved ----
+	// (the sort buffers of the edge binning are released first)
+	cudaFree(d_keys[0]); d_keys[0] = nullptr; cudaFree(d_vals[0]); d_vals[0] = nullptr;
+	cudaFree(d_cnt); d_cnt = nullptr; cudaFree(d_us); d_us = nullptr; cudaFree(d_plen); d_plen = nullptr; cudaFree(d_plenT); d_plenT = nullptr;
+	for (int i = 0; i < 2; ++i) {
+		BLK_CU(cudaMalloc(&d_k64[i], sizeof(unsigned long long) * (size_t)nLocal));
+		BLK_CU(cudaMalloc(&d_v32[i], sizeof(uint32_t) * (size_t)nLocal));
+	}
+	blk_sell_keys_kernel<<<(nLocal + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, TV, d_k64[0], d_v32[0]); (*launches)++;
+	{
+		cub::DoubleBuffer<unsigned long long> kb(d_k64[0], d_k64[1]);
+		cub::DoubleBuffer<uint32_t> vb(d_v32[0], d_v32[1]);
+		int endBit = 33;
+		while (endBit < 64 && (1ull << (endBit - 32)) < (unsigned long long)numTiles) endBit++;
+		size_t need = 0;
+		cudaFree(d_cub); d_cub = nullptr;
+		BLK_CU(cub::DeviceRadixSort::SortPairs(nullptr, need, kb, vb, (int)nLocal, 0, endBit, stream));
+		BLK_CU(cudaMalloc(&d_cub, need));
+		BLK_CU(cub::DeviceRadixSort::SortPairs(d_cub, need, kb, vb, (int)nLocal, 0, endBit, stream)); (*launches) += 6;
+		if (vb.Current() != d_v32[0]) std::swap(d_v32[0], d_v32[1]);
+	}
+	numSlices = (uint32_t)(((size_t)numTiles * TV) / 32);
+	BLK_CU(cudaMalloc(&L.order, sizeof(uint16_t) * (size_t)numTiles * TV));
+	blk_sell_order_kernel<<<(unsigned)(((size_t)numTiles * TV + 255) / 256), 256, 0, stream>>>(d_v32[0], nLocal, TV, numTiles, L.order); (*launches)++;
+	BLK_CU(cudaMalloc(&d_words, sizeof(uint32_t) * ((size_t)numSlices + 1)));
+	BLK_CU(cudaMemsetAsync(d_words, 0, sizeof(uint32_t) * ((size_t)numSlices + 1), stream));
+	blk_sell_width_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, TV, numSlices, d_words); (*launches)++;
+	BLK_CU(cudaMalloc(&L.sliceOff, sizeof(uint32_t) * ((size_t)numSlices + 1)));
+	{
+		size_t need = 0;
+		cudaFree(d_cub); d_cub = nullptr;
+		BLK_CU(cub::DeviceScan::ExclusiveSum(nullptr, need, d_words, L.sliceOff, (int)numSlices + 1, stream));
+		BLK_CU(cudaMalloc(&d_cub, need));
+		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_words, L.sliceOff, (int)numSlices + 1, stream)); (*launches) += 2;
+	}
+	BLK_CU(cudaMemcpyAsync(&sellTotal, L.sliceOff + numSlices, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	BLK_CU(cudaStreamSynchronize(stream));
+	if ((uint64_t)sellTotal > (uint64_t)nnz + 32ull * numSlices + 64ull * nLocal) goto done;              // 32-bit scan wrapped
+	BLK_CU(cudaMalloc(&L.gidxS, sizeof(uint2) * ((size_t)sellTotal + 64)));
+	BLK_CU(cudaMemsetAsync(L.gidxS, 0, sizeof(uint2) * ((size_t)sellTotal + 64), stream));
+	blk_sell_fill_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, L.gidx, TV, numSlices, L.sliceOff, L.gidxS); (*launches)++;
 	// ---- pass-A work items: (bucket, begin, end), at most kItemEntries entries each ----
 	BLK_CU(cudaMalloc(&d_bs, sizeof(uint32_t) * ((size_t)P + 1)));
 	blk_bucket_starts_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.totalPadded, d_bs); (*launches)++;
@@ -136,6 +182,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 done:
 	cudaFree(d_tmp); cudaFree(d_tileE); cudaFree(d_keys[0]); cudaFree(d_keys[1]); cudaFree(d_vals[0]); cudaFree(d_vals[1]); cudaFree(d_cub);
 	cudaFree(d_cnt); cudaFree(d_us); cudaFree(d_plen); cudaFree(d_gs); cudaFree(d_plenT); cudaFree(d_scanT); cudaFree(d_bs);
+	cudaFree(d_k64[0]); cudaFree(d_k64[1]); cudaFree(d_v32[0]); cudaFree(d_v32[1]); cudaFree(d_words);
 	if (err != cudaSuccess || !L.valid) { cudaError_t keep = err; free_blocked_layout(L); err = keep; }
 	if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); err = cudaSuccess; }   // not enough room for the layout: direct kernel
 	return err;
@@ -149,7 +196,8 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 		const double granules = (double)L.totalPadded / 4.0 / ((double)L.P * L.numTiles);
 		b.runLanes = granules > 12.0 ? 32u : granules > 5.0 ? 16u : 8u;
 	}
-	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.runStart = L.runStart; b.stageOff = L.stageOff;
+	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.order = L.order; b.sliceOff = L.sliceOff;
+	b.runStart = L.runStart; b.stageOff = L.stageOff;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;
 }

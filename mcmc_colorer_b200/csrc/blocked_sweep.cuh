@@ -43,7 +43,10 @@ struct BlockedLayout {
 	uint32_t  totalPadded = 0;   // entries in srcLocal / ecol
 	uint16_t * srcLocal = nullptr;   // [totalPadded], bucket-major
 	void *     ecol = nullptr;       // ColT[totalPadded]
-	uint16_t * gidx = nullptr;       // [nnzLocal (+8)], CSR order
+	uint16_t * gidx = nullptr;       // [nnzLocal (+16)], CSR order (heavy rows and layout construction)
+	uint2 *    gidxS = nullptr;      // SELL-32-sigma copy of gidx for the light rows: slice-interleaved 4-entry words
+	uint16_t * order = nullptr;      // [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
+	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
 	uint32_t * runStart = nullptr;   // [numTiles][P]    start of run (b,T) in srcLocal/ecol
 	uint32_t * stageOff = nullptr;   // [numTiles][P+1]  start of run (b,T) inside the tile's stage buffer
 	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
@@ -58,6 +61,9 @@ struct BlockedArgs {
 	const uint16_t * srcLocal;
 	void * ecol;
 	const uint16_t * gidx;
+	const uint2 * gidxS;
+	const uint16_t * order;
+	const uint32_t * sliceOff;
 	const uint32_t * runStart;
 	const uint32_t * stageOff;
 	const uint32_t * items;
@@ -148,6 +154,57 @@ __global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b < P) bs[b] = gs[(size_t)b * numTiles];
 	if (b == P) bs[P] = total;
+}
+
+// SELL-32-sigma (sigma = one tile) construction -------------------------------------------------------------------
+// key = (tile << 32) | (0xffffffff - degree): one stable radix sort orders every tile's vertices by descending degree
+__global__ void blk_sell_keys_kernel(const uint32_t * rowptr, uint32_t nLocal, uint32_t TV, unsigned long long * keys, uint32_t * vals) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= nLocal) return;
+	const uint32_t deg = rowptr[v + 1] - rowptr[v];
+	keys[v] = ((unsigned long long)(v / TV) << 32) | (unsigned long long)(0xffffffffu - deg);
+	vals[v] = v;
+}
+
+// order[T*TV + s] = local index of the s-th vertex of tile T (sorted); slots past the tile's vertex count get 0xffff
+__global__ void blk_sell_order_kernel(const uint32_t * sortedV, uint32_t nLocal, uint32_t TV, uint32_t numTiles, uint16_t * order) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)numTiles * TV) return;
+	const uint32_t T = (uint32_t)(i / TV), s = (uint32_t)(i % TV);
+	const uint32_t v0 = T * TV, nv = min(TV, nLocal - v0);
+	order[i] = (s < nv) ? (uint16_t)(sortedV[v0 + s] - v0) : (uint16_t)0xffffu;
+}
+
+// words[slice] = 32 * ceil(max light degree in the slice / 4)   (uint2 words the slice occupies in gidxS)
+__global__ void blk_sell_width_kernel(const uint32_t * rowptr, const uint16_t * order, uint32_t TV, uint32_t numSlices, uint32_t * words) {
+	const uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (sl >= numSlices) return;
+	const size_t slot = (size_t)sl * 32 + lane;
+	const uint32_t T = (uint32_t)(slot / TV);
+	const uint32_t o = order[slot];
+	uint32_t deg = 0;
+	if (o != 0xffffu) { const uint32_t v = T * TV + o; deg = rowptr[v + 1] - rowptr[v]; if (deg > (uint32_t)kLightMaxDeg) deg = 0; }
+	deg = __reduce_max_sync(0xffffffffu, deg);
+	if (lane == 0) words[sl] = 32u * ((deg + 3u) >> 2);
+}
+
+__global__ void blk_sell_fill_kernel(const uint32_t * rowptr, const uint16_t * order, const uint16_t * gidx, uint32_t TV, uint32_t numSlices,
+                                     const uint32_t * sliceOff, uint2 * gidxS) {
+	const uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (sl >= numSlices) return;
+	const size_t slot = (size_t)sl * 32 + lane;
+	const uint32_t T = (uint32_t)(slot / TV);
+	const uint32_t o = order[slot];
+	if (o == 0xffffu) return;
+	const uint32_t v = T * TV + o, beg = rowptr[v], deg = rowptr[v + 1] - beg;
+	if (deg > (uint32_t)kLightMaxDeg) return;
+	const uint32_t base = sliceOff[sl];
+	for (uint32_t j = 0; 4u * j < deg; ++j) {
+		uint32_t e[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) e[k] = (4u * j + k < deg) ? (uint32_t)gidx[beg + 4u * j + k] : 0u;
+		gidxS[(size_t)base + (size_t)j * 32 + lane] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -359,57 +416,76 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		if (tid == 0) s_ctl[1] = 0u;
 		if (useQueue && lane == 0) *wq.count = 0u;
 		__syncthreads();
+		const uint32_t slicesPerTile = TV >> 5;
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
-			const uint32_t slot = g + tid;
-			if (slot < nv) {
-				const uint32_t myBeg = s_rp[slot], deg = s_rp[slot + 1] - myBeg;
+			const uint32_t slot = g + tid;                        // slots are degree-sorted: a warp's 32 rows have (almost) equal length
+			const uint32_t sl = T * slicesPerTile + (slot >> 5);  // warp-uniform
+			uint32_t lv = 0xffffu;
+			if (slot < nv) lv = bl.order[(size_t)T * TV + slot];
+			if (lv != 0xffffu) {
+				const uint32_t myBeg = s_rp[lv], deg = s_rp[lv + 1] - myBeg;
 				bool light = deg <= (uint32_t)kLightMaxDeg;
 				if (!light) {                                          // warp-per-vertex list; if it is full the thread does the row itself
 					const uint32_t hi = atomicAdd(&s_ctl[1], 1u);
-					if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)slot; else light = true;
+					if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)lv; else light = true;
 				}
 				if (light) {
-					const uint32_t gv = a.vBegin + v0 + slot;
+					const uint32_t gv = a.vBegin + v0 + lv;
 					const uint32_t own = (uint32_t)cur[gv];
 					unsigned long long m[W];
 #pragma unroll
 					for (int w = 0; w < W; ++w) m[w] = 0ull;
-					uint32_t same = 0;
 					auto add = [&](uint32_t idx) {
 						const uint32_t c = stage[idx];
-						same += (c == own);
 						if (W == 1) m[0] |= 1ull << c;
 						else {
 #pragma unroll
 							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
 						}
 					};
-					// the row's u16 stage indices, fetched as aligned 8-byte words, kPf words in flight; entries of the
-					// first/last word that belong to the neighbouring rows are masked by the unsigned range test
-					const uint32_t a0 = myBeg & ~3u, skip = myBeg - a0;
-					const uint32_t nq = (skip + deg + 3u) >> 2;
-					const uint2 * gq = reinterpret_cast<const uint2 *>(bl.gidx + a0);
-#ifdef MCMCB200_PF
-					constexpr uint32_t kPf = MCMCB200_PF;
-#else
-					constexpr uint32_t kPf = 4;
-#endif
-					for (uint32_t wb = 0; wb < nq; wb += kPf) {
-						uint2 q[kPf];
+					uint32_t same = 0;
+					if (deg <= (uint32_t)kLightMaxDeg) {
+						// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
+						const uint32_t so0 = bl.sliceOff[sl], nW = (deg + 3u) >> 2;
+						const uint2 * gq = bl.gidxS + so0 + lane;
+						for (uint32_t j = 0; j < nW; j += 2) {
+							const uint2 q0 = __ldcs(gq + (size_t)j * 32);
+							uint2 q1 = make_uint2(0u, 0u);
+							if (j + 1u < nW) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
+							const uint32_t p0 = 4u * j;
+							add(q0.x & 0xffffu);
+							if (p0 + 1u < deg) add(q0.x >> 16);
+							if (p0 + 2u < deg) add(q0.y & 0xffffu);
+							if (p0 + 3u < deg) add(q0.y >> 16);
+							if (p0 + 4u < deg) add(q1.x & 0xffffu);
+							if (p0 + 5u < deg) add(q1.x >> 16);
+							if (p0 + 6u < deg) add(q1.y & 0xffffu);
+							if (p0 + 7u < deg) add(q1.y >> 16);
+						}
+						// the number of same-coloured neighbours (conflict metric) only matters for conflicting vertices: recount those
+						bool viol;
+						if (W == 1) viol = (m[0] >> own) & 1ull;
+						else { viol = false;
 #pragma unroll
-						for (uint32_t j = 0; j < kPf; ++j) if (wb + j < nq) q[j] = __ldg(gq + wb + j);
-#pragma unroll
-						for (uint32_t j = 0; j < kPf; ++j) {
-							if (wb + j < nq) {
-								const uint32_t p0 = 4u * (wb + j) - skip;           // position in the row of the word's first entry (wraps below 0)
-								if (p0 < deg) add(q[j].x & 0xffffu);
-								if (p0 + 1u < deg) add(q[j].x >> 16);
-								if (p0 + 2u < deg) add(q[j].y & 0xffffu);
-								if (p0 + 3u < deg) add(q[j].y >> 16);
+							for (int w = 0; w < W; ++w) viol = viol || (((int)(own >> 6) == w) && ((m[w] >> (own & 63u)) & 1ull)); }
+						if (viol) {
+							for (uint32_t j = 0; j < nW; ++j) {
+								const uint2 q = __ldg(gq + (size_t)j * 32);
+								const uint32_t p0 = 4u * j;
+								same += (stage[q.x & 0xffffu] == own);
+								if (p0 + 1u < deg) same += (stage[q.x >> 16] == own);
+								if (p0 + 2u < deg) same += (stage[q.y & 0xffffu] == own);
+								if (p0 + 3u < deg) same += (stage[q.y >> 16] == own);
 							}
 						}
+					} else {                                           // overflow of the heavy list: plain CSR-order indices
+						for (uint32_t i = 0; i < deg; ++i) {
+							const uint32_t idx = __ldg(bl.gidx + myBeg + i);
+							same += (stage[idx] == own);
+							add(idx);
+						}
 					}
-					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
+					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 					                             useQueue ? &wq : nullptr);
 				}
 			}
