@@ -10,7 +10,7 @@ namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
 	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.sliceOff);
-	cudaFree(L.runStart); cudaFree(L.stageOff); cudaFree(L.items);
+	cudaFree(L.granSrc); cudaFree(L.tileGran); cudaFree(L.items);
 	L = BlockedLayout{};
 }
 
@@ -38,7 +38,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	size_t cells = 0;
 	unsigned long long * d_k64[2] = {nullptr, nullptr};
 	uint32_t * d_v32[2] = {nullptr, nullptr};
-	uint32_t * d_words = nullptr;
+	uint32_t * d_words = nullptr, * d_runStart = nullptr, * d_stageOff = nullptr;
 	uint32_t numSlices = 0, sellTotal = 0;
 	std::vector<uint32_t> bs, items;
 
@@ -108,16 +108,20 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 		L.totalPadded = (uint32_t)total;
 	}
 	// ---- static tables and entry arrays ----
-	BLK_CU(cudaMalloc(&L.runStart, sizeof(uint32_t) * cells));
-	BLK_CU(cudaMalloc(&L.stageOff, sizeof(uint32_t) * ((size_t)numTiles * (P + 1))));
+	BLK_CU(cudaMalloc(&d_runStart, sizeof(uint32_t) * cells));
+	BLK_CU(cudaMalloc(&d_stageOff, sizeof(uint32_t) * ((size_t)numTiles * (P + 1))));
 	BLK_CU(cudaMemsetAsync(d_tmp, 0, 2 * sizeof(uint32_t), stream));
-	blk_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_gs, d_scanT, d_plenT, P, numTiles, L.runStart, L.stageOff, d_tmp); (*launches)++;
+	blk_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_gs, d_scanT, d_plenT, P, numTiles, d_runStart, d_stageOff, d_tmp); (*launches)++;
+	BLK_CU(cudaMalloc(&L.granSrc, sizeof(uint32_t) * ((size_t)(L.totalPadded >> 2) + 16)));
+	BLK_CU(cudaMalloc(&L.tileGran, sizeof(uint32_t) * ((size_t)numTiles + 1)));
+	blk_gran_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_runStart, d_scanT, d_plenT, cells, L.granSrc); (*launches)++;
+	blk_tile_gran_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_scanT, P, numTiles, L.totalPadded, L.tileGran); (*launches)++;
 	BLK_CU(cudaMalloc(&L.srcLocal, sizeof(uint16_t) * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.srcLocal, 0, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));
 	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
 	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
 	blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
-	                                                                L.stageOff, L.srcLocal, L.gidx); (*launches)++;
+	                                                                d_stageOff, L.srcLocal, L.gidx); (*launches)++;
 	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
 	// ---- SELL-32-sigma copy of gidx for the light rows: per tile, vertices by descending degree; 32-slot slices interleaved ----
@@ -182,7 +186,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 done:
 	cudaFree(d_tmp); cudaFree(d_tileE); cudaFree(d_keys[0]); cudaFree(d_keys[1]); cudaFree(d_vals[0]); cudaFree(d_vals[1]); cudaFree(d_cub);
 	cudaFree(d_cnt); cudaFree(d_us); cudaFree(d_plen); cudaFree(d_gs); cudaFree(d_plenT); cudaFree(d_scanT); cudaFree(d_bs);
-	cudaFree(d_k64[0]); cudaFree(d_k64[1]); cudaFree(d_v32[0]); cudaFree(d_v32[1]); cudaFree(d_words);
+	cudaFree(d_k64[0]); cudaFree(d_k64[1]); cudaFree(d_v32[0]); cudaFree(d_v32[1]); cudaFree(d_words); cudaFree(d_runStart); cudaFree(d_stageOff);
 	if (err != cudaSuccess || !L.valid) { cudaError_t keep = err; free_blocked_layout(L); err = keep; }
 	if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); err = cudaSuccess; }   // not enough room for the layout: direct kernel
 	return err;
@@ -197,7 +201,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 		b.runLanes = granules > 12.0 ? 32u : granules > 5.0 ? 16u : 8u;
 	}
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.order = L.order; b.sliceOff = L.sliceOff;
-	b.runStart = L.runStart; b.stageOff = L.stageOff;
+	b.granSrc = L.granSrc; b.tileGran = L.tileGran;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;
 }

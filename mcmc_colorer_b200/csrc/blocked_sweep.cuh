@@ -47,8 +47,8 @@ struct BlockedLayout {
 	uint2 *    gidxS = nullptr;      // SELL-32-sigma copy of gidx for the light rows: slice-interleaved 4-entry words
 	uint16_t * order = nullptr;      // [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
 	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
-	uint32_t * runStart = nullptr;   // [numTiles][P]    start of run (b,T) in srcLocal/ecol
-	uint32_t * stageOff = nullptr;   // [numTiles][P+1]  start of run (b,T) inside the tile's stage buffer
+	uint32_t * granSrc = nullptr;    // [totalPadded/4]  tile-major: where in ecol the i-th 4-entry granule of the tile's stage comes from
+	uint32_t * tileGran = nullptr;   // [numTiles+1]     first granule of each tile in granSrc
 	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
 	uint32_t  numItems = 0;
 	size_t    smemA = 0, smemB = 0;
@@ -64,8 +64,8 @@ struct BlockedArgs {
 	const uint2 * gidxS;
 	const uint16_t * order;
 	const uint32_t * sliceOff;
-	const uint32_t * runStart;
-	const uint32_t * stageOff;
+	const uint32_t * granSrc;
+	const uint32_t * tileGran;
 	const uint32_t * items;
 	uint32_t numItems;
 };
@@ -154,6 +154,22 @@ __global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b < P) bs[b] = gs[(size_t)b * numTiles];
 	if (b == P) bs[P] = total;
+}
+
+// granSrc: one descriptor per 4-entry granule of every tile's stage buffer (tile-major, contiguous per tile), so that
+// pass B stages a tile with a flat, fully parallel copy loop instead of walking P run descriptors.
+__global__ void blk_gran_kernel(const uint32_t * runStart /* [T][b] */, const uint32_t * scanT /* [T][b] */, const uint32_t * plenT /* [T][b] */,
+                                size_t cells, uint32_t * granSrc) {
+	const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= cells) return;
+	const uint32_t g0 = scanT[idx] >> 2, ng = plenT[idx] >> 2, src = runStart[idx];
+	for (uint32_t g = 0; g < ng; ++g) granSrc[g0 + g] = src + 4u * g;
+}
+
+__global__ void blk_tile_gran_kernel(const uint32_t * scanT, uint32_t P, uint32_t numTiles, uint32_t totalPadded, uint32_t * tileGran) {
+	const uint32_t T = blockIdx.x * blockDim.x + threadIdx.x;
+	if (T < numTiles) tileGran[T] = scanT[(size_t)T * P] >> 2;
+	if (T == numTiles) tileGran[T] = totalPadded >> 2;
 }
 
 // SELL-32-sigma (sigma = one tile) construction -------------------------------------------------------------------
@@ -285,8 +301,6 @@ constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per til
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	size_t b = 0;
 	b += sizeof(uint32_t) * (size_t)(TV + 4);              // s_rp
-	b += sizeof(uint32_t) * (size_t)((P + 1 + 3) & ~3u);   // s_so
-	b += sizeof(uint32_t) * (size_t)((P + 3) & ~3u);       // s_rs
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
@@ -303,11 +317,9 @@ template <int W, typename ColT, bool kDyn>
 __global__ void __launch_bounds__(kThreadsB, (W <= 2 ? (1024 / kThreadsB) : 1))
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const uint32_t nCol = a.nCol, P = bl.P, TV = bl.TV;
+	const uint32_t nCol = a.nCol, TV = bl.TV;
 	uint32_t * s_rp   = reinterpret_cast<uint32_t *>(smem_raw);
-	uint32_t * s_so   = s_rp + (TV + 4);
-	uint32_t * s_rs   = s_so + ((P + 1 + 3) & ~3u);
-	float *    s_S    = reinterpret_cast<float *>(s_rs + ((P + 3) & ~3u));
+	float *    s_S    = reinterpret_cast<float *>(s_rp + (TV + 4));
 	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
 	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
 	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
@@ -365,48 +377,24 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		const uint32_t v0 = T * TV;
 		const uint32_t nv = min(TV, a.nLocal - v0);
 		for (uint32_t i = tid; i <= nv; i += kThreadsB) s_rp[i] = a.rowptr[v0 + i];
-		for (uint32_t b = tid; b <= P; b += kThreadsB) s_so[b] = bl.stageOff[(size_t)T * (P + 1) + b];
-		for (uint32_t b = tid; b < P; b += kThreadsB) s_rs[b] = bl.runStart[(size_t)T * P + b];
 		__syncthreads();
-		// ---- phase 0: copy the tile's P runs of gathered colours into the stage buffer (4-entry granules).
-		//      runLanes lanes per run, 4 runs in flight per lane group (loads first, then the stores). ----
+		// ---- phase 0: stage the tile's gathered colours.  They sit in ecol as P short runs (one per source chunk); the
+		//      static granule list says where each 4-entry granule comes from, so the copy is a flat loop, 4 deep. ----
 		{
-#ifdef MCMCB200_RL
-			const uint32_t RL = MCMCB200_RL;
-#else
-			const uint32_t RL = bl.runLanes;
-#endif
-			const uint32_t groups = kThreadsB / RL;
-			const uint32_t grp = tid / RL, gl = tid % RL;
 			typedef typename std::conditional<sizeof(ColT) == 1, uint32_t, uint2>::type Gran;   // 4 colours
-#ifdef MCMCB200_RU
-			constexpr uint32_t kRU = MCMCB200_RU;
-#else
-			constexpr uint32_t kRU = 2;
-#endif
-			for (uint32_t b0 = grp; b0 < P; b0 += groups * kRU) {
-				Gran v[kRU]; uint32_t dst[kRU]; bool have[kRU];
+			const uint32_t gb = bl.tileGran[T], ng = bl.tileGran[T + 1] - gb;
+			const uint32_t * __restrict__ gs = bl.granSrc + gb;
+			Gran * st4 = reinterpret_cast<Gran *>(stage);
+			const Gran * __restrict__ ec4 = reinterpret_cast<const Gran *>(ecol);
+			constexpr uint32_t kU = 4;
+			for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
+				uint32_t src[kU]; Gran v[kU];
 #pragma unroll
-				for (uint32_t k = 0; k < kRU; ++k) {
-					const uint32_t b = b0 + k * groups;
-					have[k] = false;
-					if (b < P) {
-						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, w = 4u * gl;
-						if (w < len) { have[k] = true; dst[k] = o0 + w; v[k] = __ldcs(reinterpret_cast<const Gran *>(ecol + s_rs[b] + w)); }
-					}
-				}
+				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
 #pragma unroll
-				for (uint32_t k = 0; k < kRU; ++k)
-					if (have[k]) *reinterpret_cast<Gran *>(stage + dst[k]) = v[k];
+				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; if (i < ng) v[k] = __ldcs(ec4 + (src[k] >> 2)); }
 #pragma unroll
-				for (uint32_t k = 0; k < kRU; ++k) {                   // runs longer than 4*RL entries
-					const uint32_t b = b0 + k * groups;
-					if (b < P) {
-						const uint32_t o0 = s_so[b], len = s_so[b + 1] - o0, g = s_rs[b];
-						for (uint32_t w = 4u * (gl + RL); w < len; w += 4u * RL)
-							*reinterpret_cast<Gran *>(stage + o0 + w) = __ldcs(reinterpret_cast<const Gran *>(ecol + g + w));
-					}
-				}
+				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; if (i < ng) st4[i] = v[k]; }
 			}
 		}
 		__syncthreads();
@@ -444,6 +432,12 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 						}
 					};
 					uint32_t same = 0;
+					auto addc = [&](uint32_t idx) { const uint32_t c = stage[idx]; same += (c == own);
+						if (W == 1) m[0] |= 1ull << c;
+						else {
+#pragma unroll
+							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						} };
 					if (deg <= (uint32_t)kLightMaxDeg) {
 						// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
 						const uint32_t so0 = bl.sliceOff[sl], nW = (deg + 3u) >> 2;
@@ -453,37 +447,17 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 							uint2 q1 = make_uint2(0u, 0u);
 							if (j + 1u < nW) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
 							const uint32_t p0 = 4u * j;
-							add(q0.x & 0xffffu);
-							if (p0 + 1u < deg) add(q0.x >> 16);
-							if (p0 + 2u < deg) add(q0.y & 0xffffu);
-							if (p0 + 3u < deg) add(q0.y >> 16);
-							if (p0 + 4u < deg) add(q1.x & 0xffffu);
-							if (p0 + 5u < deg) add(q1.x >> 16);
-							if (p0 + 6u < deg) add(q1.y & 0xffffu);
-							if (p0 + 7u < deg) add(q1.y >> 16);
-						}
-						// the number of same-coloured neighbours (conflict metric) only matters for conflicting vertices: recount those
-						bool viol;
-						if (W == 1) viol = (m[0] >> own) & 1ull;
-						else { viol = false;
-#pragma unroll
-							for (int w = 0; w < W; ++w) viol = viol || (((int)(own >> 6) == w) && ((m[w] >> (own & 63u)) & 1ull)); }
-						if (viol) {
-							for (uint32_t j = 0; j < nW; ++j) {
-								const uint2 q = __ldg(gq + (size_t)j * 32);
-								const uint32_t p0 = 4u * j;
-								same += (stage[q.x & 0xffffu] == own);
-								if (p0 + 1u < deg) same += (stage[q.x >> 16] == own);
-								if (p0 + 2u < deg) same += (stage[q.y & 0xffffu] == own);
-								if (p0 + 3u < deg) same += (stage[q.y >> 16] == own);
-							}
+							addc(q0.x & 0xffffu);
+							if (p0 + 1u < deg) addc(q0.x >> 16);
+							if (p0 + 2u < deg) addc(q0.y & 0xffffu);
+							if (p0 + 3u < deg) addc(q0.y >> 16);
+							if (p0 + 4u < deg) addc(q1.x & 0xffffu);
+							if (p0 + 5u < deg) addc(q1.x >> 16);
+							if (p0 + 6u < deg) addc(q1.y & 0xffffu);
+							if (p0 + 7u < deg) addc(q1.y >> 16);
 						}
 					} else {                                           // overflow of the heavy list: plain CSR-order indices
-						for (uint32_t i = 0; i < deg; ++i) {
-							const uint32_t idx = __ldg(bl.gidx + myBeg + i);
-							same += (stage[idx] == own);
-							add(idx);
-						}
+						for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
 					}
 					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 					                             useQueue ? &wq : nullptr);

@@ -323,7 +323,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
 		const bool want = forceBlocked || (!forceDirect && nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18));
 		if (want) {
-			uint32_t capBytes = 61440;   // colour bytes a tile stages in shared memory (sized for 2 CTAs/SM at P ~ 1500 chunks)
+			uint32_t capBytes = 65504;   // colour bytes a tile stages in shared memory (u8: just under the u16 index limit; 2 CTAs/SM)
 			if (const char * env = getenv("MCMCB200_STAGE_CAP_BYTES")) capBytes = (uint32_t)strtoul(env, nullptr, 10);
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes,
 			                                     h->stream, &h->launches);
