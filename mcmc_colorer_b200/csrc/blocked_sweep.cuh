@@ -29,7 +29,7 @@ constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
 constexpr int      kThreadsA  = 256;
 #ifndef MCMCB200_THREADS_B
-#define MCMCB200_THREADS_B 512
+#define MCMCB200_THREADS_B 1024
 #endif
 constexpr int      kThreadsB  = MCMCB200_THREADS_B;
 constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
@@ -299,33 +299,45 @@ constexpr uint32_t kWarpQueueCap = 48;     // deferred CDF walks parked per warp
 constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per tile (overflow is handled by the owning thread)
 
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
+	(void)P;
 	size_t b = 0;
-	b += sizeof(uint32_t) * (size_t)(TV + 4);              // s_rp
+	b += 2 * sizeof(uint32_t) * (size_t)(TV + 4);          // s_rp, double buffered
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
 	b += sizeof(uint32_t) * 8;                             // s_ctl
-	b += sizeof(uint32_t) * 96;                            // s_red (32 x u64) + per-warp queue counters (32 x u32)
+	b += sizeof(uint32_t) * 128;                           // s_red (64 x u64)
+	b += sizeof(uint32_t) * 32;                            // per-warp queue counters
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += (size_t)colBytes * (stageCap + 16);               // stage
+	b += 2 * (size_t)colBytes * (stageCap + 16);           // stage, double buffered
 	return (b + 15) & ~(size_t)15;
 }
 
+__device__ __forceinline__ void cp_async_4(void * smem, const void * gmem) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_8(void * smem, const void * gmem) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsB, (W <= 2 ? (1024 / kThreadsB) : 1))
+__global__ void __launch_bounds__(kThreadsB, 1)
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t nCol = a.nCol, TV = bl.TV;
-	uint32_t * s_rp   = reinterpret_cast<uint32_t *>(smem_raw);
-	float *    s_S    = reinterpret_cast<float *>(s_rp + (TV + 4));
+	uint32_t * s_rp2  = reinterpret_cast<uint32_t *>(smem_raw);                       // [2][TV+4]
+	float *    s_S    = reinterpret_cast<float *>(s_rp2 + 2 * (TV + 4));
 	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
 	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
 	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
-	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 32 x u64
-	uint32_t * s_qcnt = s_ctl + 8 + 64;                                               // 32 x u32
-	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 96);
+	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 64 x u64
+	uint32_t * s_qcnt = s_ctl + 8 + 128;                                              // 32 x u32
+	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 160);
 	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + kHeavyCap) - smem_raw);
 	off = (off + 15) & ~(size_t)15;
 	WalkQueue<W> wq{};
@@ -340,7 +352,8 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kWarpQueueCap);
 		off += (size_t)(kThreadsB / 32) * perWarp;
 	}
-	ColT * stage = reinterpret_cast<ColT *>(smem_raw + off);
+	ColT * stage2 = reinterpret_cast<ColT *>(smem_raw + off);                         // [2][stageCap+16]
+	const uint32_t stageStride = bl.stageCap + 16;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nWarps = kThreadsB / 32;
@@ -368,42 +381,49 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	}
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) s_ctl[0] = atomicAdd(&st->tileCounter, 1u);
-		__syncthreads();
-		const uint32_t T = s_ctl[0];
-		if (T >= bl.numTiles) break;
-		const uint32_t v0 = T * TV;
-		const uint32_t nv = min(TV, a.nLocal - v0);
-		for (uint32_t i = tid; i <= nv; i += kThreadsB) s_rp[i] = a.rowptr[v0 + i];
-		__syncthreads();
-		// ---- phase 0: stage the tile's gathered colours.  They sit in ecol as P short runs (one per source chunk); the
-		//      static granule list says where each 4-entry granule comes from, so the copy is a flat loop, 4 deep. ----
-		{
-			typedef typename std::conditional<sizeof(ColT) == 1, uint32_t, uint2>::type Gran;   // 4 colours
-			const uint32_t gb = bl.tileGran[T], ng = bl.tileGran[T + 1] - gb;
-			const uint32_t * __restrict__ gs = bl.granSrc + gb;
-			Gran * st4 = reinterpret_cast<Gran *>(stage);
-			const Gran * __restrict__ ec4 = reinterpret_cast<const Gran *>(ecol);
-			constexpr uint32_t kU = 4;
-			for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
-				uint32_t src[kU]; Gran v[kU];
+	// Software pipeline over the tiles of this CTA (static round robin: tile = blockIdx + k * gridDim).  The row pointers
+	// and the gathered colours of tile k+1 are fetched with cp.async (LDGSTS: no registers, no warp stalls) into the
+	// other half of the double buffers while tile k is being processed.  The colours sit in ecol as P short runs (one
+	// per source chunk); the static granule list says where each 4-entry granule of the stage comes from.
+	auto prefetch = [&](uint32_t T, uint32_t buf) {
+		const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
+		uint32_t * rp = s_rp2 + buf * (TV + 4);
+		for (uint32_t i = tid; i <= nv; i += kThreadsB) cp_async_4(rp + i, a.rowptr + v0 + i);
+		const uint32_t gb = bl.tileGran[T], ng = bl.tileGran[T + 1] - gb;
+		const uint32_t * __restrict__ gs = bl.granSrc + gb;
+		ColT * stg = stage2 + (size_t)buf * stageStride;
+		constexpr uint32_t kU = 8;
+		for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
+			uint32_t src[kU];
 #pragma unroll
-				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
+			for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
 #pragma unroll
-				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; if (i < ng) v[k] = __ldcs(ec4 + (src[k] >> 2)); }
-#pragma unroll
-				for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; if (i < ng) st4[i] = v[k]; }
+			for (uint32_t k = 0; k < kU; ++k) {
+				const uint32_t i = i0 + k * kThreadsB;
+				if (i < ng) {
+					if (sizeof(ColT) == 1) cp_async_4(stg + 4u * i, ecol + src[k]);
+					else cp_async_8(stg + 4u * i, ecol + src[k]);
+				}
 			}
 		}
-		__syncthreads();
+	};
+	if (tid == 0) s_ctl[1] = 0u;
+	uint32_t T = blockIdx.x;
+	if (T < bl.numTiles) prefetch(T, 0u);
+	for (uint32_t it = 0; T < bl.numTiles; T += gridDim.x, ++it) {
+		const uint32_t buf = it & 1u;
+		cp_async_commit_wait_all();
+		__syncthreads();                                          // tile `it` is staged; everybody is done with tile it-1
+		if (T + gridDim.x < bl.numTiles) prefetch(T + gridDim.x, buf ^ 1u);
+		const uint32_t v0 = T * TV;
+		const uint32_t nv = min(TV, a.nLocal - v0);
+		const uint32_t * s_rp = s_rp2 + buf * (TV + 4);
+		const ColT * stage = stage2 + (size_t)buf * stageStride;
 		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static permutation gidx
 		//      (CSR order, u16: where edge e's colour sits in this tile's stage).  Thread per vertex; the 2-byte
 		//      indices of a row are fetched 4 at a time once the row pointer is 8-byte aligned. ----
-		if (tid == 0) s_ctl[1] = 0u;
 		if (useQueue && lane == 0) *wq.count = 0u;
-		__syncthreads();
+		__syncwarp();
 		const uint32_t slicesPerTile = TV >> 5;
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
 			const uint32_t slot = g + tid;                        // slots are degree-sorted: a warp's 32 rows have (almost) equal length
@@ -503,17 +523,20 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			if (lane == 0)
 				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol);
 		}
+		__syncthreads();                                          // everybody has read the heavy list
+		if (tid == 0) s_ctl[1] = 0u;
 	}
+	cp_async_commit_wait_all();
 
 	// ---- epilogue (same protocol as sweep_kernel) ----
 	accDirected = warp_reduce_add64(accDirected);
 	accViol = warp_reduce_add64(accViol);
 	__syncthreads();
-	if (lane == 0) { s_red[warp] = accDirected; s_red[16 + warp] = accViol; }
+	if (lane == 0) { s_red[warp] = accDirected; s_red[32 + warp] = accViol; }
 	__syncthreads();
 	if (tid == 0) {
 		unsigned long long d = 0, vv = 0;
-		for (int w = 0; w < nWarps; ++w) { d += s_red[w]; vv += s_red[16 + w]; }
+		for (int w = 0; w < nWarps; ++w) { d += s_red[w]; vv += s_red[32 + w]; }
 		if (d) atomicAdd(a.scratch + 0, d);
 		if (vv) atomicAdd(a.scratch + 1, vv);
 	}
