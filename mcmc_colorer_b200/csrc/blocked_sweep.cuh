@@ -31,6 +31,11 @@ constexpr int      kThreadsA  = 256;
 #ifndef MCMCB200_THREADS_B
 #define MCMCB200_THREADS_B 1024
 #endif
+#ifndef MCMCB200_PIPELINE
+#define MCMCB200_PIPELINE 1
+#endif
+constexpr bool kPipe = MCMCB200_PIPELINE != 0;   // 1: one CTA/SM, tiles double buffered; 0: two CTAs/SM, single buffer
+constexpr uint32_t kBufs = kPipe ? 2u : 1u;
 constexpr int      kThreadsB  = MCMCB200_THREADS_B;
 constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
 
@@ -301,7 +306,7 @@ constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per til
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	(void)P;
 	size_t b = 0;
-	b += 2 * sizeof(uint32_t) * (size_t)(TV + 4);          // s_rp, double buffered
+	b += kBufs * sizeof(uint32_t) * (size_t)(TV + 4);      // s_rp (double buffered when pipelined)
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
@@ -311,7 +316,7 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += 2 * (size_t)colBytes * (stageCap + 16);           // stage, double buffered
+	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage (double buffered when pipelined)
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -326,12 +331,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsB, 1)
+__global__ void __launch_bounds__(kThreadsB, (kPipe || W > 2) ? 1 : (1024 / kThreadsB))
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t nCol = a.nCol, TV = bl.TV;
 	uint32_t * s_rp2  = reinterpret_cast<uint32_t *>(smem_raw);                       // [2][TV+4]
-	float *    s_S    = reinterpret_cast<float *>(s_rp2 + 2 * (TV + 4));
+	float *    s_S    = reinterpret_cast<float *>(s_rp2 + kBufs * (TV + 4));
 	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
 	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
 	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
@@ -409,12 +414,13 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	};
 	if (tid == 0) s_ctl[1] = 0u;
 	uint32_t T = blockIdx.x;
-	if (T < bl.numTiles) prefetch(T, 0u);
+	if (kPipe && T < bl.numTiles) prefetch(T, 0u);
 	for (uint32_t it = 0; T < bl.numTiles; T += gridDim.x, ++it) {
-		const uint32_t buf = it & 1u;
+		const uint32_t buf = kPipe ? (it & 1u) : 0u;
+		if (!kPipe) prefetch(T, 0u);
 		cp_async_commit_wait_all();
 		__syncthreads();                                          // tile `it` is staged; everybody is done with tile it-1
-		if (T + gridDim.x < bl.numTiles) prefetch(T + gridDim.x, buf ^ 1u);
+		if (kPipe && T + gridDim.x < bl.numTiles) prefetch(T + gridDim.x, buf ^ 1u);
 		const uint32_t v0 = T * TV;
 		const uint32_t nv = min(TV, a.nLocal - v0);
 		const uint32_t * s_rp = s_rp2 + buf * (TV + 4);
