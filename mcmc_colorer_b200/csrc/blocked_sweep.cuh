@@ -29,10 +29,10 @@ constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
 constexpr int      kThreadsA  = 256;
 #ifndef MCMCB200_THREADS_B
-#define MCMCB200_THREADS_B 1024
+#define MCMCB200_THREADS_B 512
 #endif
 #ifndef MCMCB200_PIPELINE
-#define MCMCB200_PIPELINE 1
+#define MCMCB200_PIPELINE 0      /* measured on B200: 2 CTAs/SM x 512 threads beat the double-buffered 1 x 1024 variant (profiles/) */
 #endif
 constexpr bool kPipe = MCMCB200_PIPELINE != 0;   // 1: one CTA/SM, tiles double buffered; 0: two CTAs/SM, single buffer
 constexpr uint32_t kBufs = kPipe ? 2u : 1u;
@@ -468,7 +468,24 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 						// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
 						const uint32_t so0 = bl.sliceOff[sl], nW = (deg + 3u) >> 2;
 						const uint2 * gq = bl.gidxS + so0 + lane;
-						for (uint32_t j = 0; j < nW; j += 2) {
+#ifndef MCMCB200_MASK_PF
+#define MCMCB200_MASK_PF 6
+#endif
+						constexpr uint32_t kMP = MCMCB200_MASK_PF;       // words fetched up front (covers degree <= 4*kMP in one round trip)
+						uint2 q[kMP];
+#pragma unroll
+						for (uint32_t j = 0; j < kMP; ++j) if (j < nW) q[j] = __ldcs(gq + (size_t)j * 32);
+#pragma unroll
+						for (uint32_t j = 0; j < kMP; ++j) {
+							if (j < nW) {
+								const uint32_t p0 = 4u * j;
+								addc(q[j].x & 0xffffu);
+								if (p0 + 1u < deg) addc(q[j].x >> 16);
+								if (p0 + 2u < deg) addc(q[j].y & 0xffffu);
+								if (p0 + 3u < deg) addc(q[j].y >> 16);
+							}
+						}
+						for (uint32_t j = kMP; j < nW; j += 2) {
 							const uint2 q0 = __ldcs(gq + (size_t)j * 32);
 							uint2 q1 = make_uint2(0u, 0u);
 							if (j + 1u < nW) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
