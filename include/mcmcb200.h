@@ -134,6 +134,13 @@ int mcmcb200_get_history(mcmcb200_handle * h, uint64_t * out, uint32_t cap, uint
  * of the remaining conflicts, colours tried in ascending class size.  rounds returns the passes used. */
 int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds);
 
+/* -------- cross-check -------- */
+/* Luby-style MIS colourer (replaces ColoringLuby::run, graph_coloring/coloringLuby.cu:364-501; cross-check only, not
+ * performance work): greedy colour classes as maximal independent sets.  colorsOut[n] receives 1-based colours like the
+ * reference's; numColors the number of classes, rounds the MIS rounds used.  Stand-alone: no handle needed. */
+int mcmcb200_luby_color(uint32_t n, uint64_t nnz, const uint32_t * cumulDegs, const uint32_t * neighs, uint64_t seed, int32_t device,
+                        uint32_t * colorsOut, uint32_t * numColors, uint32_t * rounds);
+
 /* -------- parity / debug -------- */
 /* Pure function of a colouring, evaluated by the sweep kernel's own counting path on the handle's graph. */
 int mcmcb200_conflicts_of(mcmcb200_handle * h, const uint32_t * colors, uint64_t * edges, uint64_t * vertices);

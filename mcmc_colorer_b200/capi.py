@@ -28,7 +28,7 @@ SYMBOLS = [
     "mcmcb200_get_class_sizes", "mcmcb200_get_history", "mcmcb200_tailcut", "mcmcb200_conflicts_of",
     "mcmcb200_debug_occupancy", "mcmcb200_debug_all_occupancy", "mcmcb200_device_view", "mcmcb200_finalize_sweep",
     "mcmcb200_stream", "mcmcb200_synchronize", "mcmcb200_last_sweep_ms", "mcmcb200_launch_count",
-    "mcmcb200_strerror", "mcmcb200_last_cuda_error", "mcmcb200_abi_version",
+    "mcmcb200_strerror", "mcmcb200_last_cuda_error", "mcmcb200_abi_version", "mcmcb200_luby_color",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
     L.mcmcb200_synchronize.argtypes = [vp]
     L.mcmcb200_last_sweep_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.mcmcb200_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mcmcb200_luby_color.argtypes = [C.c_uint32, C.c_uint64, vp, vp, C.c_uint64, C.c_int32, vp, u32p, u32p]
     L.mcmcb200_strerror.argtypes = [C.c_int]
     L.mcmcb200_strerror.restype = C.c_char_p
     L.mcmcb200_last_cuda_error.restype = C.c_char_p

@@ -216,6 +216,19 @@ class Chain:
         return k.value
 
 
+def luby_color(cumulDegs, neighs, seed=0, device=-1):
+    """ColoringLuby cross-check (graph_coloring/coloringLuby.cu:364-501): returns (colors uint32[n], 1-based; nCol; rounds)."""
+    L = capi.lib()
+    cumul, cp = capi._u32(cumulDegs)
+    nb, nbp = capi._u32(neighs if len(neighs) else np.zeros(1, np.uint32))
+    n = len(cumul) - 1
+    out = np.zeros(n, np.uint32)
+    ncol, rounds = C.c_uint32(), C.c_uint32()
+    capi.check(L.mcmcb200_luby_color(n, len(neighs), cp, nbp, seed, device, out.ctypes.data_as(C.c_void_p), C.byref(ncol),
+                                     C.byref(rounds)), "mcmcb200_luby_color")
+    return out, ncol.value, rounds.value
+
+
 def occupancy_bits(mask_words32, nCol):
     """uint32 mask words -> uint8[nCol] occupancy row (1 = a neighbour has that colour)."""
     bits = np.unpackbits(np.asarray(mask_words32, np.uint32).view(np.uint8), bitorder="little")

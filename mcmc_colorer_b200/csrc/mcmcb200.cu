@@ -3,6 +3,7 @@
 #include "sweep_kernel.cuh"
 #include "tailcut_kernel.cuh"
 #include "blocked_build.cuh"
+#include "luby_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -651,6 +652,56 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	CU(cudaMemcpyAsync(&h->d_state->convergedAt, &notConv, sizeof(notConv), cudaMemcpyHostToDevice, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	if (rounds) *rounds = used;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_luby_color(uint32_t n, uint64_t nnz, const uint32_t * cumulDegs, const uint32_t * neighs, uint64_t seed, int32_t device,
+                        uint32_t * colorsOut, uint32_t * numColors, uint32_t * rounds) {
+	if (!cumulDegs || (nnz && !neighs) || !colorsOut || n == 0) return MCMCB200_EINVAL;
+	mcmcb200_params p{}; p.device = device;
+	int dev = 0, sms = 0;
+	int rc = select_device(&p, &dev, &sms); if (rc) return rc;
+	uint32_t * d_rp = nullptr, * d_nb = nullptr, * d_col = nullptr, * d_flag = nullptr;
+	uint8_t * d_c = nullptr, * d_is = nullptr, * d_ch = nullptr, * d_keep = nullptr;
+	auto cleanup = [&]() { cudaFree(d_rp); cudaFree(d_nb); cudaFree(d_col); cudaFree(d_flag); cudaFree(d_c); cudaFree(d_is); cudaFree(d_ch); cudaFree(d_keep); };
+	cudaError_t e = cudaMalloc(&d_rp, sizeof(uint32_t) * ((size_t)n + 1));
+	if (e == cudaSuccess) e = cudaMalloc(&d_nb, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1));
+	if (e == cudaSuccess) e = cudaMalloc(&d_col, sizeof(uint32_t) * (size_t)n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_flag, sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&d_c, n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_is, n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_ch, n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_keep, n);
+	if (e == cudaSuccess) e = cudaMemcpy(d_rp, cumulDegs, sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && nnz) e = cudaMemcpy(d_nb, neighs, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemset(d_col, 0, sizeof(uint32_t) * (size_t)n);
+	if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby setup", __LINE__); }
+	const uint32_t blocks = (n + 127) / 128;                      // block 128 like the reference (coloringLuby.cu)
+	uint32_t color = 0, round = 0, flag = 1;
+	while (flag) {                                                // CICLO_1: one colour per iteration (coloringLuby.cu:389-470)
+		color++;
+		luby_prune_kernel<<<blocks, 128>>>(n, d_col, d_c, d_is);
+		uint32_t left = 1;
+		while (left) {                                            // CICLO_2: grow the independent set until no candidate is left
+			round++;
+			luby_choose_kernel<<<blocks, 128>>>(n, seed, round, d_c, d_ch);
+			luby_resolve_kernel<<<blocks, 128>>>(n, d_rp, d_nb, d_ch, d_keep);
+			luby_update_kernel<<<blocks, 128>>>(n, d_rp, d_nb, d_keep, d_c, d_is, d_flag);
+			cudaMemsetAsync(d_flag, 0, sizeof(uint32_t));
+			luby_left_kernel<<<blocks, 128>>>(n, d_c, d_flag);
+			e = cudaMemcpy(&left, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+			if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby round", __LINE__); }
+		}
+		cudaMemsetAsync(d_flag, 0, sizeof(uint32_t));
+		luby_color_kernel<<<blocks, 128>>>(n, color, d_is, d_col, d_flag);
+		e = cudaMemcpy(&flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby colour", __LINE__); }
+	}
+	e = cudaMemcpy(colorsOut, d_col, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost);
+	cleanup();
+	if (e != cudaSuccess) return cuda_fail(e, "luby copy", __LINE__);
+	if (numColors) *numColors = color;
+	if (rounds) *rounds = round;
 	return MCMCB200_OK;
 }
 

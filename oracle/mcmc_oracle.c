@@ -63,6 +63,10 @@ void orc_init_colors(uint64_t seed, uint32_t vb, uint32_t ve, uint32_t nCol, uin
 	for (uint32_t v = vb; v < ve; v++) out[v - vb] = orc_init_color(seed, v, nCol);
 }
 
+void orc_fill_bits(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, uint32_t purpose, uint32_t * out) {
+	for (uint32_t v = vb; v < ve; v++) out[v - vb] = orc_draw_bits(seed, sweep, v, purpose);
+}
+
 void orc_fill_tape(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, int proposal, float * u) {
 	for (uint32_t v = vb; v < ve; v++) u[v - vb] = orc_draw_uniform(seed, sweep, v, proposal);
 }

@@ -4,7 +4,7 @@
  *
  * Parity pin: this port is checked function by function against oracle/_ref/libmcmc_ref.so (the
  * UNMODIFIED reference CPU colourer compiled from /root/reference, see oracle/Makefile) in
- * tests/test_oracle_vs_ref.py, and against the committed fixtures in tests/golden/ that were
+ * tests/test_oracle.py, and against the committed fixtures in tests/golden/ that were
  * generated from that library (tests/golden/make_golden.py).  The reference's own test-suite holds
  * no golden vectors for this path, so those are the pins.
  *
@@ -22,13 +22,14 @@ extern "C" {
 enum { ORC_PROPOSAL_UNIFORM = 0, ORC_PROPOSAL_DYNAMIC = 1 };
 
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 v1.14 philox.h).  Third-party algorithm restated
- * from the publication; pinned by the Random123 known-answer vectors in tests/test_philox.py. */
+ * from the publication; pinned by the Random123 known-answer vectors in tests/test_oracle.py. */
 void     orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* draw conventions shared with the device code (include/mcmcb200.h "RNG contract") */
 uint32_t orc_draw_bits(uint64_t seed, uint32_t sweep, uint32_t vertex, uint32_t purpose);
 float    orc_draw_uniform(uint64_t seed, uint32_t sweep, uint32_t vertex, int proposal);
 uint32_t orc_init_color(uint64_t seed, uint32_t vertex, uint32_t nCol);
 void     orc_init_colors(uint64_t seed, uint32_t vb, uint32_t ve, uint32_t nCol, uint32_t * out /* [ve-vb] */);
+void     orc_fill_bits(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, uint32_t purpose, uint32_t * out /* [ve-vb] */);
 void     orc_fill_tape(uint64_t seed, uint32_t sweep, uint32_t vb, uint32_t ve, int proposal, float * u /* [ve-vb] */);
 
 /* graph/graphCPU.cpp:290-404  Graph::setupRnd2 -- libc rand() exact Erdos-Renyi generator.

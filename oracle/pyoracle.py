@@ -52,6 +52,7 @@ class Port:
         L.orc_init_color.restype = C.c_uint32
         L.orc_init_color.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_init_colors.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
+        L.orc_fill_bits.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u32p]
         L.orc_fill_tape.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _f32p]
         L.orc_setup_rnd2.restype = C.c_int
         L.orc_setup_rnd2.argtypes = [C.c_uint32, C.c_float, _u32p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -84,6 +85,11 @@ class Port:
         u = np.empty(n - vb, np.float32)
         self.L.orc_fill_tape(seed, sweep, vb, n, proposal, u)
         return u
+
+    def draw_bits(self, seed, sweep, n, purpose):
+        out = np.empty(n, np.uint32)
+        self.L.orc_fill_bits(seed, sweep, 0, n, purpose, out)
+        return out
 
     def init_colors(self, seed, n, nCol):
         out = np.empty(n, np.uint32)
