@@ -35,6 +35,8 @@ WORKLOADS = {
     "small": (200_000, 16, "smoke-sized Erdos-Renyi n=200k, mean degree 16"),
 }
 GRAPH_SEED = 42
+# measured DRAM traffic of one sweep (ncu dram__bytes_read.sum + dram__bytes_write.sum, both launches), bytes
+TRAFFIC = {"c3": 13.04e9}
 CHAIN_SEED = 1
 
 
@@ -284,8 +286,10 @@ def main():
         "edges_per_sec": value * nnz / n,
         "chain_ms_per_sweep": chain_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "mcmcb200::sweep_kernel", "launch_ms": ms_per_step},
+                     "traffic": TRAFFIC.get(args.workload), "traffic_source": "profiles/r01c_ncu_blocked_kernels_c3.md (ncu dram__bytes, one sweep)" if args.workload in TRAFFIC else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "one sweep = blocked_gather_kernel + blocked_sweep_kernel (source-blocked path; sweep_kernel on small graphs)",
+                     "launch_ms": ms_per_step, "launches_per_sweep": int(launches_per_step)},
         "e2e": {"value": e2e_value, "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n,
                 "d2h_bytes_per_step": 4 * n + 40 + 8 * nCol, "ms_per_step": 1e3 * float(np.mean(e2e_t))},
         "gpu_launches": int(launches_per_step * args.steps),
