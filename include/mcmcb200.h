@@ -159,6 +159,13 @@ int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_
 /* With MCMCB200_FLAG_NO_FUSED_FINALIZE: mcmcb200_sweep(h,1) stops after the local pass; the caller all-gathers the
  * NEXT colour slices, all-reduces COUNTERS (both on mcmcb200_stream) and then calls mcmcb200_finalize_sweep. */
 int mcmcb200_finalize_sweep(mcmcb200_handle * h);
+/* Fused exchange (one box, NVLink/NVSwitch): instead of an all-gather after the sweep, the sweep kernel itself stores
+ * every finished tile's new colours into ALL ranks' colour replicas through peer pointers.  Each rank exports the two
+ * cudaIpcMemHandle_t (64 bytes each) of its colour buffers, the caller exchanges them (any transport) and attaches the
+ * full table [nRanks][2][64]; afterwards only the counter all-reduce (which doubles as the inter-rank barrier) remains.
+ * Needs MCMCB200_FLAG_NO_FUSED_FINALIZE and the source-blocked sweep; nRanks <= 8. */
+int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [2][64] */);
+int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles);
 int mcmcb200_stream(mcmcb200_handle * h, void ** cudaStream);
 int mcmcb200_synchronize(mcmcb200_handle * h);
 /* elapsed milliseconds (CUDA events on the handle's stream) of the kernels launched by the last mcmcb200_sweep */

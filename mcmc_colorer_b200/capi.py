@@ -29,6 +29,7 @@ SYMBOLS = [
     "mcmcb200_debug_occupancy", "mcmcb200_debug_all_occupancy", "mcmcb200_device_view", "mcmcb200_finalize_sweep",
     "mcmcb200_stream", "mcmcb200_synchronize", "mcmcb200_last_sweep_ms", "mcmcb200_launch_count",
     "mcmcb200_strerror", "mcmcb200_last_cuda_error", "mcmcb200_abi_version", "mcmcb200_luby_color",
+    "mcmcb200_ipc_export", "mcmcb200_ipc_attach",
 ]
 
 
@@ -85,6 +86,8 @@ def lib():
     L.mcmcb200_debug_all_occupancy.argtypes = [vp, vp, vp]
     L.mcmcb200_device_view.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64), u32p]
     L.mcmcb200_finalize_sweep.argtypes = [vp]
+    L.mcmcb200_ipc_export.argtypes = [vp, vp]
+    L.mcmcb200_ipc_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.mcmcb200_stream.argtypes = [vp, C.POINTER(vp)]
     L.mcmcb200_synchronize.argtypes = [vp]
     L.mcmcb200_last_sweep_ms.argtypes = [vp, C.POINTER(C.c_float)]

@@ -197,6 +197,15 @@ class Chain:
                    "mcmcb200_device_view")
         return ptr.value, nbytes.value, eb.value
 
+    def ipc_export(self):
+        buf = (C.c_ubyte * 128)()
+        capi.check(self.L.mcmcb200_ipc_export(self.h, C.cast(buf, C.c_void_p)), "mcmcb200_ipc_export")
+        return bytes(buf)
+
+    def ipc_attach(self, n_ranks, my_rank, handles: bytes):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        capi.check(self.L.mcmcb200_ipc_attach(self.h, n_ranks, my_rank, C.cast(buf, C.c_void_p)), "mcmcb200_ipc_attach")
+
     def stream(self):
         s = C.c_void_p()
         capi.check(self.L.mcmcb200_stream(self.h, C.byref(s)), "mcmcb200_stream")

@@ -317,6 +317,7 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
 	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage (double buffered when pipelined)
+	b += (size_t)colBytes * (size_t)(TV + 16);             // s_new: the tile's new colours, written out coalesced (local + peers)
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -359,6 +360,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	}
 	ColT * stage2 = reinterpret_cast<ColT *>(smem_raw + off);                         // [2][stageCap+16]
 	const uint32_t stageStride = bl.stageCap + 16;
+	ColT * s_new = stage2 + (size_t)kBufs * stageStride;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nWarps = kThreadsB / 32;
@@ -503,14 +505,14 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 						for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
 					}
 					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
-					                             useQueue ? &wq : nullptr);
+					                             useQueue ? &wq : nullptr, s_new, v0);
 				}
 			}
 			if (useQueue) {                          // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
 				__syncwarp();
 				const uint32_t qn = min(*wq.count, wq.cap);
 				if (qn >= 32u) {
-					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn - 32u, 32u, s_dist, s_hist, lane);
+					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn - 32u, 32u, s_dist, s_hist, lane, s_new, v0);
 					__syncwarp();
 					if (lane == 0) *wq.count = qn - 32u;
 				}
@@ -520,7 +522,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		if (useQueue) {                              // remainder of this warp's queue
 			__syncwarp();
 			const uint32_t qn = min(*wq.count, wq.cap);
-			drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, s_dist, s_hist, lane);
+			drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, s_dist, s_hist, lane, s_new, v0);
 			__syncwarp();
 		}
 		__syncthreads();
@@ -544,10 +546,25 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
 			same = __reduce_add_sync(0xffffffffu, same);
 			if (lane == 0)
-				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol);
+				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
+				                             nullptr, s_new, v0);
 		}
-		__syncthreads();                                          // everybody has read the heavy list
+		__syncthreads();                                          // the tile is finished: everybody has read the heavy list, s_new is complete
 		if (tid == 0) s_ctl[1] = 0u;
+		if (!a.countOnly) {
+			// write the tile's new colours out, coalesced 16-byte stores: to the local replica and -- fused exchange -- straight
+			// into every peer GPU's replica over NVLink (peer pointers from cudaIpcOpenMemHandle); tiles start 256-vertex aligned
+			const size_t byteOff = (size_t)(a.vBegin + v0) * sizeof(ColT);
+			const uint32_t nBytes = nv * (uint32_t)sizeof(ColT), nVec = nBytes >> 4;
+			const uint4 * src4 = reinterpret_cast<const uint4 *>(s_new);
+			const uint32_t nDest = a.nPeers ? a.nPeers : 1u;
+			for (uint32_t d = 0; d < nDest; ++d) {
+				unsigned char * dst = a.nPeers ? static_cast<unsigned char *>(a.peerColors[(t + 1) & 1][d]) : reinterpret_cast<unsigned char *>(nxt);
+				uint4 * dst4 = reinterpret_cast<uint4 *>(dst + byteOff);
+				for (uint32_t i = tid; i < nVec; i += kThreadsB) dst4[i] = src4[i];
+				for (uint32_t i = (nVec << 4) + tid; i < nBytes; i += kThreadsB) dst[byteOff + i] = reinterpret_cast<const unsigned char *>(s_new)[i];
+			}
+		}
 	}
 	cp_async_commit_wait_all();
 

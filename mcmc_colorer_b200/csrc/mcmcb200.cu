@@ -65,6 +65,8 @@ struct mcmcb200_handle {
 	uint64_t z = 0;
 	int smCount = 0;
 	BlockedLayout bl;                    // source-blocked two-pass layout (valid => the sweeps use it)
+	void * peerColors[2][kMaxPeers] = {};  // fused multi-GPU exchange: IPC-mapped colour buffers of every rank (own = local)
+	uint32_t nPeers = 0, myPeerIndex = 0;
 };
 
 namespace {
@@ -160,6 +162,8 @@ SweepArgs make_args(mcmcb200_handle * h) {
 	a.countOnly = 0; a.countOut = nullptr;
 	a.fuseFinalize = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) ? 0u : 1u;
 	a.noEarlyStop = (h->p.flags & MCMCB200_FLAG_NO_EARLY_STOP) ? 1u : 0u;
+	a.nPeers = h->bl.valid ? h->nPeers : 0u;
+	for (int b = 0; b < 2; ++b) for (uint32_t q = 0; q < kMaxPeers; ++q) a.peerColors[b][q] = h->peerColors[b][q];
 	a.dbgMasks = nullptr; a.dbgSame = nullptr;
 	return a;
 }
@@ -398,6 +402,8 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_tape); cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
 	free_blocked_layout(h->bl);
+	for (uint32_t q = 0; q < h->nPeers; ++q)
+		if (q != h->myPeerIndex) for (int b = 0; b < 2; ++b) if (h->peerColors[b][q]) cudaIpcCloseMemHandle(h->peerColors[b][q]);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);
@@ -717,6 +723,37 @@ int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_
 	case MCMCB200_VIEW_COUNTERS:    *devPtr = h->d_scratch; if (bytes) *bytes = sizeof(unsigned long long) * (h->p.nCol + 2); if (elemBytes) *elemBytes = 8; break;
 	default: return MCMCB200_EINVAL;
 	}
+	return MCMCB200_OK;
+}
+
+int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [2][64] */) {
+	if (!h || !handles) return MCMCB200_EINVAL;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	CU(cudaSetDevice(h->device));
+	for (int b = 0; b < 2; ++b) {
+		cudaIpcMemHandle_t mh;
+		CU(cudaIpcGetMemHandle(&mh, h->d_colors[b]));
+		memcpy(handles + 64 * b, &mh, 64);
+	}
+	return MCMCB200_OK;
+}
+
+int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles /* [nRanks][2][64] */) {
+	if (!h || !handles || nRanks < 2 || nRanks > (uint32_t)kMaxPeers || myRank >= nRanks) return MCMCB200_EINVAL;
+	if (!(h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE)) return MCMCB200_ESTATE;
+	if (!h->bl.valid) return MCMCB200_EUNSUPPORTED;          // the fused exchange lives in the source-blocked sweep
+	if (h->nPeers) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	for (uint32_t q = 0; q < nRanks; ++q)
+		for (int b = 0; b < 2; ++b) {
+			if (q == myRank) { h->peerColors[b][q] = h->d_colors[b]; continue; }
+			cudaIpcMemHandle_t mh;
+			memcpy(&mh, handles + ((size_t)q * 2 + b) * 64, 64);
+			void * ptr = nullptr;
+			CU(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+			h->peerColors[b][q] = ptr;
+		}
+	h->nPeers = nRanks; h->myPeerIndex = myRank;
 	return MCMCB200_OK;
 }
 

@@ -35,6 +35,7 @@ constexpr int kTileV       = 256;   // vertices per tile (one per thread in phas
 constexpr int kCapEdges    = 8192;  // neighbour colours staged per sub-tile
 constexpr int kLightMaxDeg = 64;    // thread-per-vertex up to here, warp-per-vertex above
 constexpr int kMaxColWords = 8;     // nCol <= 512 on the bitmask-in-registers path
+constexpr int kMaxPeers    = 8;     // GPUs of one NVSwitch box whose colour replicas a sweep can store into directly
 
 struct DevState {
 	uint32_t sweep;          // index t of the current colouring C_t
@@ -73,6 +74,8 @@ struct SweepArgs {
 	unsigned long long * countOut; // count-only result [2]
 	uint32_t fuseFinalize;       // last CTA runs finalize_sweep
 	uint32_t noEarlyStop;        // keep sweeping even when C_t is already proper (replay / benchmarking)
+	void *   peerColors[2][kMaxPeers]; // fused exchange: every rank's two colour buffers (IPC-mapped; own entries = local)
+	uint32_t nPeers;             // 0: no fused exchange (single GPU, or NCCL all-gather by the caller)
 	unsigned long long * dbgMasks; // optional [nLocal][W]
 	uint32_t * dbgSame;          // optional [nLocal]
 };
@@ -207,11 +210,14 @@ struct WalkQueue {
 };
 
 // colour write + taboo + class-size deltas of a vertex whose new colour is known
+// nxtTile != nullptr: the new colour goes to the tile's shared-memory staging row (index lv - tileV0) and is written out
+// coalesced -- to the local replica and, in the fused multi-GPU exchange, to every peer's -- once the tile is finished
 template <typename ColT>
 __device__ __forceinline__ void finish_vertex(const SweepArgs & a, ColT * __restrict__ nxt, uint32_t lv, uint32_t myOwn, uint32_t newc,
-                                              int * s_hist, bool touchTaboo) {
+                                              int * s_hist, bool touchTaboo, ColT * nxtTile = nullptr, uint32_t tileV0 = 0) {
 	if (touchTaboo && a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);   // coloringMCMC_CPU.cpp:526
-	nxt[a.vBegin + lv] = (ColT)newc;
+	if (nxtTile) nxtTile[lv - tileV0] = (ColT)newc;
+	else nxt[a.vBegin + lv] = (ColT)newc;
 	if (newc != myOwn) { atomicAdd(&s_hist[myOwn], -1); atomicAdd(&s_hist[newc], 1); }
 }
 
@@ -225,7 +231,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
                                               uint32_t myOwn, const unsigned long long (&m)[W], uint32_t same,
                                               const float * s_S, const float * s_dist, int * s_hist, float stayW,
                                               unsigned long long & accDirected, unsigned long long & accViol,
-                                              const WalkQueue<W> * queue = nullptr) {
+                                              const WalkQueue<W> * queue = nullptr, ColT * nxtTile = nullptr, uint32_t tileV0 = 0) {
 	constexpr bool isDyn = kDyn;
 	const uint32_t nCol = a.nCol;
 	const float eps = a.eps;
@@ -292,17 +298,18 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 				}
 				newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
 			}
-			finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, true);
+			finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, true, nxtTile, tileV0);
 			return;
 		}
 	}
-	finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, false);
+	finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, false, nxtTile, tileV0);
 }
 
 // entries [first, first+count) of a queue, one per lane (called by the owning warp; count <= 32)
 template <int W, typename ColT, bool kDyn>
 __device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __restrict__ nxt, const WalkQueue<W> & q, uint32_t first,
-                                                 uint32_t count, const float * s_dist, int * s_hist, int lane) {
+                                                 uint32_t count, const float * s_dist, int * s_hist, int lane,
+                                                 ColT * nxtTile = nullptr, uint32_t tileV0 = 0) {
 	if ((uint32_t)lane < count) {
 		const uint32_t i = first + lane;
 		unsigned long long m[W];
@@ -311,7 +318,7 @@ __device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __r
 		const uint32_t lv = q.lvOwn[2 * i], own = q.lvOwn[2 * i + 1];
 		const float u = q.uw[2 * i], x = q.uw[2 * i + 1];
 		const uint32_t newc = walk_conflicting<W, kDyn>(m, a.nCol, a.eps, x, x, s_dist, u);
-		finish_vertex<ColT>(a, nxt, lv, own, newc, s_hist, true);
+		finish_vertex<ColT>(a, nxt, lv, own, newc, s_hist, true, nxtTile, tileV0);
 	}
 }
 

@@ -55,6 +55,33 @@ class GpuEngine:
         self.stream = torch.cuda.ExternalStream(self.chain.stream(), device=self.device)
         self.t = 0
         self._bufs = None
+        self.p2p = False
+
+    def enable_p2p(self, rank, world, group=None):
+        """Fused exchange: map every rank's colour replicas (CUDA IPC) so that the sweep kernel stores each finished tile's
+        new colours straight into all of them over NVLink; the NCCL all-gather disappears, the counter all-reduce stays
+        (it is also the inter-rank barrier).  Returns False (and keeps the all-gather) where it does not apply."""
+        import torch.distributed as dist
+        if world < 2 or world > 8:
+            return False
+        try:
+            mine = self.chain.ipc_export()
+        except Exception:
+            mine = None
+        table = [None] * world
+        dist.all_gather_object(table, mine, group=group)
+        if any(t is None for t in table):
+            return False
+        ok = True
+        try:
+            self.chain.ipc_attach(world, rank, b"".join(table))
+        except Exception:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        self.p2p = all(flags)
+        assert self.p2p or not ok, "fused exchange attached on some ranks only"
+        return self.p2p
 
     def _views(self):
         if self._bufs is None:
@@ -97,6 +124,7 @@ class GpuEngine:
         return self.chain.status()
 
     def colors_host(self, which="cur"):
+        self.chain.synchronize()
         buf = self._views()[(self.t if which == "cur" else self.t + 1) & 1]
         raw = buf[: self.n * self.elem_bytes].cpu().numpy()
         return (raw if self.elem_bytes == 1 else raw.view("<u2")).astype(np.uint32)
@@ -127,7 +155,7 @@ class DistributedSweeper:
     def sweep(self, k=1):
         for _ in range(k):
             self.e.local_sweep()
-            self._exchange(colours=True)
+            self._exchange(colours=not getattr(self.e, "p2p", False))   # fused exchange: the kernel already stored into the peers
             self.e.finalize(advanced=True)
 
     def status(self):
@@ -175,6 +203,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, seed=CHAIN_SEED,
                              convergence=capi.CONVERGE_VERTICES if proposal == capi.PROPOSAL_UNIFORM else capi.CONVERGE_EDGES)
     eng = GpuEngine(rp, nb, nnz_local, n, vb, ve, prm, local_rank)
+    fused = eng.enable_p2p(rank, world) if os.environ.get("MCMCB200_NO_P2P") is None else False
     sw = DistributedSweeper(eng, rank, world, chunk)
 
     def timed_step():
@@ -230,7 +259,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8 colours / u32 ids / f32 CDF", "data": "synthetic",
             "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": args.proposal,
-                       "parallelism": f"vertex partition x{world}, all-gather of u8 colour slices + all-reduce of counters per sweep",
+                       "parallelism": f"vertex partition x{world}; colour exchange: " + ("fused into the sweep kernel (peer stores over NVLink)" if fused else "NCCL all-gather of u8 slices") + "; counters: one NCCL all-reduce per sweep",
                        "step": "one sweep from the uniform random colouring incl. the colour exchange (max over ranks)",
                        "l2": "inputs larger than L2; no flush needed"},
             "edges_per_sec": value * nnz / n,

@@ -20,7 +20,7 @@ dev = f"cuda:{lr}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 P = Port()
 ok = True
-for n, deg, proposal in [(50_001, 12, 0), (50_001, 12, 1), (300_000, 20, 0)]:
+for n, deg, proposal, p2p in [(50_001, 12, 0, False), (50_001, 12, 1, False), (300_000, 20, 0, False), (300_000, 20, 1, True), (1_000_003, 16, 0, True)]:
     cumul, neighs = er_graph_numpy(n, deg, seed=5)
     nCol = int(np.diff(cumul.astype(np.int64)).max())
     parts, chunk = partition(n, world)
@@ -31,6 +31,10 @@ for n, deg, proposal in [(50_001, 12, 0), (50_001, 12, 1), (300_000, 20, 0)]:
     nb[: e1 - e0] = torch.from_numpy(neighs[e0:e1].astype(np.int32)).to(dev)
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=proposal, seed=11)
     eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr)
+    if p2p:
+        got_p2p = eng.enable_p2p(rank, world)
+        if rank == 0:
+            print(f"n={n}: fused P2P exchange {'ON' if got_p2p else 'not available -> all-gather'}")
     sw = DistributedSweeper(eng, rank, world, chunk)
     eng.init_colors(None)
     c = P.init_colors(11, n, nCol)
