@@ -305,5 +305,26 @@ def main():
     return 0
 
 
+class _QuietStdout:
+    """fd 1 is pointed at stderr while the benchmark runs (NCCL prints its version banner to stdout), so that the ONE
+    JSON line is the only thing the caller finds on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.py_stdout = sys.stdout
+        sys.stdout = os.fdopen(os.dup(self.saved), "w")
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        sys.stdout = self.py_stdout
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    with _QuietStdout():
+        rc = main()
+    sys.exit(rc)
