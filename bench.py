@@ -32,6 +32,9 @@ WORKLOADS = {
     "c3": (100_000_000, 16, "BASELINE config 3: Erdos-Renyi n=100M, mean degree 16, nCol=maxDeg"),
     "c2": (1_000_000, 32, "BASELINE config 2: Erdos-Renyi n=1M, mean degree 32, nCol=maxDeg"),
     "c5": (10_000_000, 16, "BASELINE config 5: Erdos-Renyi n=10M, mean degree 16, nCol=maxDeg"),
+    "c4": (50_000_000, 16, "BASELINE config 4: R-MAT (0.57,0.19,0.19,0.05) scale 26 trimmed to 50M vertices, edge factor 16, "
+                           "nCol=min(maxDeg,512) (numColRatio chosen so that the palette is tractable)"),
+    "c4small": (1_500_000, 16, "R-MAT (0.57,0.19,0.19,0.05) scale 21 trimmed to 1.5M vertices, edge factor 16, nCol=min(maxDeg,512)"),
     "small": (200_000, 16, "smoke-sized Erdos-Renyi n=200k, mean degree 16"),
 }
 GRAPH_SEED = 42
@@ -88,10 +91,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def gen_graph_device(n, deg, device):
+MAX_PALETTE = 512                                         # widest palette of this build (u16 colours, 8 mask words per lane)
+
+
+def palette_for(workload, max_deg):
+    """numColRatio 1.0: nCol = maxDeg (main.cu:162); the R-MAT hubs have degree ~1e6, there the ratio is raised so that
+    the palette stays tractable."""
+    return min(max_deg, MAX_PALETTE) if workload.startswith("c4") else max_deg
+
+
+def gen_graph_device(n, deg, device, workload="c3"):
     import torch
-    from mcmc_colorer_b200.graphgen import er_graph_torch
-    rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=device)
+    from mcmc_colorer_b200.graphgen import er_graph_torch, rmat_graph_torch
+    if workload.startswith("c4"):
+        scale = max(1, (n - 1).bit_length())
+        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(scale, deg, GRAPH_SEED, n_keep=n, device=device)
+    else:
+        rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=device)
     assert nnz < 2 ** 31, "this bench keeps CSR offsets in int32 tensors"
     rowptr = rowptr64.to(torch.int32)
     del rowptr64
@@ -166,8 +182,8 @@ def run_reference_arm(args):
         rowptr, neighs = torch.from_numpy(cumul.astype(np.int64)), torch.from_numpy(nb.astype(np.int64))
         nnz, max_deg = len(nb), int(np.diff(cumul.astype(np.int64)).max())
     else:
-        rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev)
-    nCol = max_deg
+        rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev, args.workload)
+    nCol = palette_for(args.workload, max_deg)
     rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=max(20.0, 6.0 * (args.steps + args.warmup)),
                                                      steps=args.steps, warmup=args.warmup)
     ms = 1e3 * sum(secs) / len(secs)
@@ -219,9 +235,9 @@ def main():
     if args.n:
         n = args.n
     t_gen = time.perf_counter()
-    rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev)
+    rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev, args.workload)
     t_gen = time.perf_counter() - t_gen
-    nCol = max_deg                                        # numColRatio 1.0: nCol = maxDeg (main.cu:162)
+    nCol = palette_for(args.workload, max_deg)
     proposal = mc.PROPOSAL_UNIFORM if args.proposal == "uniform" else mc.PROPOSAL_DYNAMIC
     prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal,
                                 convergence=mc.CONVERGE_VERTICES if proposal == mc.PROPOSAL_UNIFORM else mc.CONVERGE_EDGES,
@@ -279,7 +295,7 @@ def main():
         "metric": "vertex_updates_per_sec", "value": value, "unit": "vertex-updates/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8 colours / u32 ids / f32 CDF", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": args.proposal,
+        "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "maxDeg": max_deg, "proposal": args.proposal,
                    "step": "one sweep from the uniform random colouring (all vertices active)",
                    "l2": "inputs (CSR %.1f GB) larger than L2; no flush needed" % ((4 * nnz + 4 * n) / 1e9),
                    "graph_gen_s": round(t_gen, 2)},

@@ -159,6 +159,13 @@ int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_
 /* With MCMCB200_FLAG_NO_FUSED_FINALIZE: mcmcb200_sweep(h,1) stops after the local pass; the caller all-gathers the
  * NEXT colour slices, all-reduces COUNTERS (both on mcmcb200_stream) and then calls mcmcb200_finalize_sweep. */
 int mcmcb200_finalize_sweep(mcmcb200_handle * h);
+/* Sliced host interface for partitioned handles: a rank uploads / downloads only the colours of the vertices it owns
+ * (uint32, vEnd-vBegin entries).  After mcmcb200_init_colors_slice on every rank the caller all-gathers the
+ * MCMCB200_VIEW_COLORS_CUR buffers (owned slices) and then calls mcmcb200_init_colors_finish (class sizes, validation). */
+int mcmcb200_init_colors_slice(mcmcb200_handle * h, const uint32_t * ownedColors);
+int mcmcb200_init_colors_finish(mcmcb200_handle * h);
+int mcmcb200_get_colors_slice(mcmcb200_handle * h, uint32_t * out /* [vEnd - vBegin] */);
+
 /* Fused exchange (one box, NVLink/NVSwitch): instead of an all-gather after the sweep, the sweep kernel itself stores
  * every finished tile's new colours into ALL ranks' colour replicas through peer pointers.  Each rank exports the two
  * cudaIpcMemHandle_t (64 bytes each) of its colour buffers, the caller exchanges them (any transport) and attaches the

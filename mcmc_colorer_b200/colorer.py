@@ -197,6 +197,15 @@ class Chain:
                    "mcmcb200_device_view")
         return ptr.value, nbytes.value, eb.value
 
+    def init_colors_slice_ptr(self, host_ptr):
+        capi.check(self.L.mcmcb200_init_colors_slice(self.h, C.c_void_p(host_ptr)), "mcmcb200_init_colors_slice")
+
+    def init_colors_finish(self):
+        capi.check(self.L.mcmcb200_init_colors_finish(self.h), "mcmcb200_init_colors_finish")
+
+    def get_colors_slice_ptr(self, host_ptr):
+        capi.check(self.L.mcmcb200_get_colors_slice(self.h, C.c_void_p(host_ptr)), "mcmcb200_get_colors_slice")
+
     def ipc_export(self):
         buf = (C.c_ubyte * 128)()
         capi.check(self.L.mcmcb200_ipc_export(self.h, C.cast(buf, C.c_void_p)), "mcmcb200_ipc_export")

@@ -433,6 +433,53 @@ int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors) {
 	return MCMCB200_OK;
 }
 
+int mcmcb200_init_colors_slice(mcmcb200_handle * h, const uint32_t * ownedColors) {
+	if (!h || !ownedColors) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	int rc = reset_state(h); if (rc) return rc;
+	rc = ensure_stage(h); if (rc) return rc;
+	h->colorsInit = false;
+	if (h->nLocal) {
+		CU(cudaMemcpyAsync(h->d_stage32, ownedColors, sizeof(uint32_t) * (size_t)h->nLocal, cudaMemcpyHostToDevice, h->stream));
+		const uint32_t blocks = (h->nLocal + 255) / 256;
+		if (h->colBytes == 1) narrow_colors_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>(h->d_stage32, (uint8_t *)h->d_colors[0] + h->vBegin, h->nLocal, h->p.nCol, h->d_state);
+		else narrow_colors_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>(h->d_stage32, (uint16_t *)h->d_colors[0] + h->vBegin, h->nLocal, h->p.nCol, h->d_state);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	return MCMCB200_OK;
+}
+
+int mcmcb200_init_colors_finish(mcmcb200_handle * h) {
+	if (!h) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	int rc = compute_class_sizes(h, h->d_colors[0], h->d_hist[0]); if (rc) return rc;
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	if (s.errorFlag) { h->colorsInit = false; return MCMCB200_EINVAL; }
+	h->colorsInit = true;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_colors_slice(mcmcb200_handle * h, uint32_t * out) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	rc = ensure_stage(h); if (rc) return rc;
+	if (h->nLocal) {
+		const uint32_t blocks = (h->nLocal + 255) / 256;
+		if (h->colBytes == 1) widen_colors_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>((const uint8_t *)h->d_colors[s.sweep & 1] + h->vBegin, h->d_stage32, h->nLocal);
+		else widen_colors_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>((const uint16_t *)h->d_colors[s.sweep & 1] + h->vBegin, h->d_stage32, h->nLocal);
+		h->launches++;
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(out, h->d_stage32, sizeof(uint32_t) * (size_t)h->nLocal, cudaMemcpyDeviceToHost, h->stream));
+	}
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
 int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps) {
 	if (!h) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));

@@ -99,6 +99,14 @@ class GpuEngine:
         self._bufs = None
         self._views()
 
+    def init_colors_slice(self, host_ptr, sweeper):
+        """Host interface at N GPUs: every rank uploads only the colours it owns; the slices are all-gathered on the device."""
+        self.chain.init_colors_slice_ptr(host_ptr)
+        self.t = 0
+        self._views()
+        sweeper.gather_current()
+        self.chain.init_colors_finish()
+
     def local_sweep(self):
         self.chain.sweep(1)
 
@@ -151,6 +159,14 @@ class DistributedSweeper:
                 mine = full[self.rank * cb:(self.rank + 1) * cb]
                 dist.all_gather_into_tensor(full, mine, group=self.group)            # owned slices of C_{t+1}
             dist.all_reduce(self.e.counters(), op=dist.ReduceOp.SUM, group=self.group)  # conflicts, violations, class deltas
+
+    def gather_current(self):
+        """all-gather the owned slices of the CURRENT colouring (sliced init)"""
+        import torch.distributed as dist
+        with self._on_stream():
+            cb = self.chunk * self.e.elem_bytes
+            full = self.e.cur_colors()[: cb * self.world]
+            dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb], group=self.group)
 
     def sweep(self, k=1):
         for _ in range(k):
@@ -228,22 +244,24 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
         steps_ms = [timed_step() for _ in range(args.steps)]
     launches = eng.chain.launch_count() - l0
     ms_per_step = float(np.mean(steps_ms))
-    # end to end with host buffers: colouring H2D on every rank, sweep + exchange, counters + colouring D2H
-    pin_in = torch.empty(n, dtype=torch.int32).pin_memory()
-    pin_out = torch.empty(n, dtype=torch.int32).pin_memory()
+    # end to end with host buffers: every rank uploads the colours of the vertices it owns from pinned memory (H2D), the slices
+    # are exchanged on the device, then sweep + exchange, global counters (D2H) and the owned slice of the result (D2H)
+    n_own = ve - vb
+    pin_in = torch.empty(max(n_own, 1), dtype=torch.int32).pin_memory()
+    pin_out = torch.empty(max(n_own, 1), dtype=torch.int32).pin_memory()
     eng.init_colors(None)
-    eng.chain.get_colors_ptr(pin_in.data_ptr())
+    eng.chain.get_colors_slice_ptr(pin_in.data_ptr())
     e2e = []
-    for i in range(4):
+    for i in range(5):
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
-        eng.chain.init_colors_ptr(pin_in.data_ptr()); eng.t = 0
+        eng.init_colors_slice(pin_in.data_ptr(), sw)
         sw.sweep(1)
         st = sw.status()
-        eng.chain.get_colors_ptr(pin_out.data_ptr())
+        eng.chain.get_colors_slice_ptr(pin_out.data_ptr())
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if i >= 1:
+        if i >= 2:
             e2e.append(float(dt.item()))
     # ten chained sweeps, then the global counters (also checks the N-GPU trajectory against the 1-GPU invariants)
     eng.init_colors(None)
@@ -266,8 +284,9 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": "mcmcb200::sweep_kernel (+ NCCL exchange)"},
-            "e2e": {"value": n / float(np.mean(e2e)), "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n * world,
-                    "d2h_bytes_per_step": (4 * n + 40) * world, "ms_per_step": 1e3 * float(np.mean(e2e))},
+            "e2e": {"value": n / float(np.mean(e2e)), "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n,
+                    "d2h_bytes_per_step": 4 * n + 40 * world, "ms_per_step": 1e3 * float(np.mean(e2e)),
+                    "note": "each rank moves only the colours of the vertices it owns"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
         }

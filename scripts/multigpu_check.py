@@ -50,6 +50,20 @@ for n, deg, proposal, p2p in [(50_001, 12, 0, False), (50_001, 12, 1, False), (3
             ok = False; print(f"rank {rank}: colours differ at sweep {s + 1}: {np.flatnonzero(got != c)[:8]}")
     if not np.array_equal(eng.chain.class_sizes().astype(np.uint32), P.class_sizes(c, nCol)):
         ok = False; print(f"rank {rank}: class sizes differ")
+    # sliced host interface: every rank uploads only its own colours, the slices meet on the device
+    own = np.ascontiguousarray(c[vb:ve].astype(np.uint32))
+    eng.init_colors_slice(own.ctypes.data, sw)
+    st = sw.status()
+    if (st.conflictEdges, st.violatingVertices, st.sweep) != (P.conflict_edges(cumul, neighs, c), P.violation_count(cumul, neighs, c), 0):
+        ok = False; print(f"rank {rank}: sliced init counters differ")
+    if not np.array_equal(eng.colors_host(), c):
+        ok = False; print(f"rank {rank}: sliced init colours differ")
+    sw.sweep(1)
+    c2, _ = P.sweep(cumul, neighs, nCol, 1e-8, c, P.tape(11, 1, n, proposal), proposal)
+    back = np.zeros(max(ve - vb, 1), dtype=np.uint32)
+    eng.chain.get_colors_slice_ptr(back.ctypes.data)
+    if not np.array_equal(back[: ve - vb], c2[vb:ve]):
+        ok = False; print(f"rank {rank}: sliced download differs")
     eng.chain.close()
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)

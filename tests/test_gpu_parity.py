@@ -351,6 +351,31 @@ def test_argument_errors(mc, c1_graph):
     ch.close()
 
 
+def test_sliced_host_interface(mc, c1_graph, port):
+    """init_colors_slice / init_colors_finish / get_colors_slice on an unpartitioned handle: the slice is the whole colouring"""
+    cumul, neighs = c1_graph
+    from mcmc_colorer_b200 import capi
+    ch = make_chain(mc, cumul, neighs, 60, seed=1234)
+    c0 = port.init_colors(99, 1000, 60)
+    buf = np.ascontiguousarray(c0.astype(np.uint32))
+    ch.init_colors_slice_ptr(buf.ctypes.data)
+    ch.init_colors_finish()
+    st = ch.status()
+    assert (st.sweep, st.conflictEdges, st.violatingVertices) == (0, port.conflict_edges(cumul, neighs, c0), port.violation_count(cumul, neighs, c0))
+    assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c0, 60))
+    ch.sweep(1)
+    want, _ = port.sweep(cumul, neighs, 60, EPS, c0, port.tape(1234, 1, 1000, 0), 0)
+    out = np.zeros(1000, np.uint32)
+    ch.get_colors_slice_ptr(out.ctypes.data)
+    assert np.array_equal(out, want)
+    bad = buf.copy(); bad[7] = 60
+    ch.init_colors_slice_ptr(bad.ctypes.data)
+    with pytest.raises(mc.McmcError) as e:
+        ch.init_colors_finish()
+    assert e.value.code == capi.EINVAL
+    ch.close()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tail cutting and the reference-shaped driver
 # ------------------------------------------------------------------------------------------------------------
