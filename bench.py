@@ -100,6 +100,10 @@ def palette_for(workload, max_deg):
     return min(max_deg, MAX_PALETTE) if workload.startswith("c4") else max_deg
 
 
+def sample_start(workload, n):
+    return (n // 2) if workload.startswith("c4") else 0
+
+
 def gen_graph_device(n, deg, device, workload="c3"):
     import torch
     from mcmc_colorer_b200.graphgen import er_graph_torch, rmat_graph_torch
@@ -115,9 +119,10 @@ def gen_graph_device(n, deg, device, workload="c3"):
     return rowptr, neighs, nnz, max_deg
 
 
-def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=1, warmup=0):
+def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=1, warmup=0, v0=0):
     """Times the reference CPU sampler (oracle/_ref: the unmodified ColoringMCMC_CPU methods; else the C port) on the
-    first m vertices of the same graph, single thread (the reference has no threading at all).  m is sized by a short
+    m vertices [v0, v0+m) of the same graph (v0 = 0 on the Erdos-Renyi workloads; the middle of the id range on R-MAT, whose
+    lowest ids are the hubs), single thread (the reference has no threading at all).  m is sized by a short
     calibration so that the whole call costs about target_seconds of CPU work.
     Returns (vertex-updates/s, kind, sample description, per-step seconds, m)."""
     import numpy as np
@@ -128,11 +133,11 @@ def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=
     u = P.tape(CHAIN_SEED, 1, n)
 
     def run_sample(m, steps, warmup):
-        e_m = int(rowptr[m].item())
-        cumul = np.empty(n + 1, np.uint32)
-        cumul[:m + 1] = rowptr[:m + 1].cpu().numpy().astype(np.uint32)
-        cumul[m + 1:] = e_m                               # vertices outside the sample: empty rows, never visited
-        nb = neighs[:max(e_m, 1)].cpu().numpy().astype(np.uint32)[:e_m]
+        e_0, e_m = int(rowptr[v0].item()), int(rowptr[v0 + m].item())
+        cumul = np.zeros(n + 1, np.uint32)                # vertices outside the sample: empty rows, never visited
+        cumul[v0:v0 + m + 1] = (rowptr[v0:v0 + m + 1].cpu().numpy().astype(np.int64) - e_0).astype(np.uint32)
+        cumul[v0 + m + 1:] = e_m - e_0
+        nb = neighs[e_0:max(e_m, e_0 + 1)].cpu().numpy().astype(np.uint32)[:e_m - e_0]
         out = []
         if use_ref:
             R = Ref()
@@ -140,7 +145,7 @@ def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=
             h = R.mcmc(g, nCol, CHAIN_SEED)
             for i in range(warmup + steps):
                 R.set_colors(h, colors)
-                sec = R.sweep_range_timed(h, u, 0, m)     # the reference's own per-vertex loop, timed inside the harness
+                sec = R.sweep_range_timed(h, u, v0, v0 + m)     # the reference's own per-vertex loop, timed inside the harness
                 if i >= warmup:
                     out.append(sec)
             R.L.ref_mcmc_free(h)
@@ -148,18 +153,18 @@ def cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, steps=
         else:
             for i in range(warmup + steps):
                 t0 = time.perf_counter()
-                P.sweep(cumul, nb, nCol, 1e-8, colors, u, 0, vb=0, ve=m)
+                P.sweep(cumul, nb, nCol, 1e-8, colors, u, 0, vb=v0, ve=v0 + m)
                 if i >= warmup:
                     out.append(time.perf_counter() - t0)
         return out
 
-    m0 = min(n, 500_000)
+    m0 = min(n - v0, 500_000)
     rate0 = m0 / run_sample(m0, 1, 0)[0]
-    m = int(min(n, max(100_000, rate0 * target_seconds / max(1, steps + warmup))))
+    m = int(min(n - v0, max(100_000, rate0 * target_seconds / max(1, steps + warmup))))
     secs = run_sample(m, steps, warmup)
     rate = float(np.mean([m / s for s in secs]))
     kind = "reference" if use_ref else "port"
-    sample = (f"first {m} of {n} vertices of the same graph ({int(rowptr[m].item())} directed edges), "
+    sample = (f"vertices [{v0}, {v0 + m}) of the {n} of the same graph ({int(rowptr[v0 + m].item()) - int(rowptr[v0].item())} directed edges), "
               f"full {n}-entry colour array, first sweep from the uniform random colouring")
     return rate, kind, sample, secs, m
 
@@ -185,7 +190,7 @@ def run_reference_arm(args):
         rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev, args.workload)
     nCol = palette_for(args.workload, max_deg)
     rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=max(20.0, 6.0 * (args.steps + args.warmup)),
-                                                     steps=args.steps, warmup=args.warmup)
+                                                     steps=args.steps, warmup=args.warmup, v0=sample_start(args.workload, n))
     ms = 1e3 * sum(secs) / len(secs)
     line = {"impl": "reference", "metric": "vertex_updates_per_sec", "value": rate, "unit": "vertex-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -313,7 +318,7 @@ def main():
         "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
     }
     if not args.no_cpu_baseline:
-        rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0)
+        rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, v0=sample_start(args.workload, n))
         line["cpu_baseline"] = {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample,
                                 "host_cores_available": os.cpu_count()}
     ch.close()
