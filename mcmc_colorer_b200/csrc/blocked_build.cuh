@@ -9,7 +9,7 @@
 namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
-	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.sliceOff);
+	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.slotInfo); cudaFree(L.sliceOff);
 	cudaFree(L.granSrc); cudaFree(L.tileGran); cudaFree(L.items);
 	L = BlockedLayout{};
 }
@@ -26,7 +26,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	const uint32_t nnz = (uint32_t)nnzLocal;
 	const uint32_t P = (nGlobal + kChunkV - 1) / kChunkV;
 	const uint32_t stageCap = (stageCapBytes / (uint32_t)colBytes) & ~15u;
-	if (stageCap < 1024 || stageCap > 65536) return cudaSuccess;
+	if (stageCap < 1024 || stageCap > 65504) return cudaSuccess;    // stage positions (and the dummy slot at stageCap) are 16-bit
 
 	uint32_t * d_tmp = nullptr;          // [2]: scratch scalars
 	uint32_t * d_tileE = nullptr;
@@ -164,7 +164,9 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	if ((uint64_t)sellTotal > (uint64_t)nnz + 32ull * numSlices + 64ull * nLocal) goto done;              // 32-bit scan wrapped
 	BLK_CU(cudaMalloc(&L.gidxS, sizeof(uint2) * ((size_t)sellTotal + 64)));
 	BLK_CU(cudaMemsetAsync(L.gidxS, 0, sizeof(uint2) * ((size_t)sellTotal + 64), stream));
-	blk_sell_fill_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, L.gidx, TV, numSlices, L.sliceOff, L.gidxS); (*launches)++;
+	blk_sell_fill_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, L.gidx, TV, numSlices, L.sliceOff, stageCap, L.gidxS); (*launches)++;
+	BLK_CU(cudaMalloc(&L.slotInfo, sizeof(uint32_t) * (size_t)numTiles * TV));
+	blk_sell_slotinfo_kernel<<<(unsigned)(((size_t)numTiles * TV + 255) / 256), 256, 0, stream>>>(d_rowptr, L.order, TV, numTiles, L.slotInfo); (*launches)++;
 	// ---- pass-A work items: (bucket, begin, end), at most kItemEntries entries each ----
 	BLK_CU(cudaMalloc(&d_bs, sizeof(uint32_t) * ((size_t)P + 1)));
 	blk_bucket_starts_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.totalPadded, d_bs); (*launches)++;
@@ -181,6 +183,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * std::max<size_t>(items.size(), 3)));
 	BLK_CU(cudaMemcpyAsync(L.items, items.data(), sizeof(uint32_t) * items.size(), cudaMemcpyHostToDevice, stream));
 	BLK_CU(cudaStreamSynchronize(stream));
+	cudaFree(L.order); L.order = nullptr;                        // construction only
 	L.P = P; L.TV = TV; L.numTiles = numTiles; L.stageCap = stageCap;
 	L.valid = true;
 done:
@@ -196,11 +199,7 @@ done:
 inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	BlockedArgs b{};
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
-	{   // lanes per run from the mean padded run length (in 4-entry granules)
-		const double granules = (double)L.totalPadded / 4.0 / ((double)L.P * L.numTiles);
-		b.runLanes = granules > 12.0 ? 32u : granules > 5.0 ? 16u : 8u;
-	}
-	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.order = L.order; b.sliceOff = L.sliceOff;
+	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granSrc = L.granSrc; b.tileGran = L.tileGran;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;

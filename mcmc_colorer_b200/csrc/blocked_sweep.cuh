@@ -50,7 +50,8 @@ struct BlockedLayout {
 	void *     ecol = nullptr;       // ColT[totalPadded]
 	uint16_t * gidx = nullptr;       // [nnzLocal (+16)], CSR order (heavy rows and layout construction)
 	uint2 *    gidxS = nullptr;      // SELL-32-sigma copy of gidx for the light rows: slice-interleaved 4-entry words
-	uint16_t * order = nullptr;      // [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
+	uint16_t * order = nullptr;      // (construction only) [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
+	uint32_t * slotInfo = nullptr;   // [numTiles*TV] slot -> (local vertex | degree << 16); 0xffff = empty slot.  Staged per tile by cp.async
 	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
 	uint32_t * granSrc = nullptr;    // [totalPadded/4]  tile-major: where in ecol the i-th 4-entry granule of the tile's stage comes from
 	uint32_t * tileGran = nullptr;   // [numTiles+1]     first granule of each tile in granSrc
@@ -62,12 +63,11 @@ struct BlockedLayout {
 
 struct BlockedArgs {
 	uint32_t P, TV, numTiles, stageCap;
-	uint32_t runLanes;           // lanes cooperating on one (bucket, tile) run in pass B: 8, 16 or 32 (by mean run length)
 	const uint16_t * srcLocal;
 	void * ecol;
 	const uint16_t * gidx;
 	const uint2 * gidxS;
-	const uint16_t * order;
+	const uint32_t * slotInfo;
 	const uint32_t * sliceOff;
 	const uint32_t * granSrc;
 	const uint32_t * tileGran;
@@ -209,21 +209,33 @@ __global__ void blk_sell_width_kernel(const uint32_t * rowptr, const uint16_t * 
 	if (lane == 0) words[sl] = 32u * ((deg + 3u) >> 2);
 }
 
+// slotInfo[T*TV + s] = local vertex | degree << 16 (a tile's rows never exceed the stage, so the degree fits 16 bits)
+__global__ void blk_sell_slotinfo_kernel(const uint32_t * rowptr, const uint16_t * order, uint32_t TV, uint32_t numTiles, uint32_t * slotInfo) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)numTiles * TV) return;
+	const uint32_t T = (uint32_t)(i / TV), o = order[i];
+	uint32_t info = 0xffffu;
+	if (o != 0xffffu) { const uint32_t v = T * TV + o; info = o | ((rowptr[v + 1] - rowptr[v]) << 16); }
+	slotInfo[i] = info;
+}
+
+// Every row of a slice is filled to the slice's width: positions past the row's degree (and the whole row of an empty
+// slot or of a heavy vertex) hold `dummy`, the index of a stage byte that pass B keeps at the all-ones colour, which
+// matches no palette entry -- the mask loop needs no per-edge bounds test.
 __global__ void blk_sell_fill_kernel(const uint32_t * rowptr, const uint16_t * order, const uint16_t * gidx, uint32_t TV, uint32_t numSlices,
-                                     const uint32_t * sliceOff, uint2 * gidxS) {
+                                     const uint32_t * sliceOff, uint32_t dummy, uint2 * gidxS) {
 	const uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (sl >= numSlices) return;
 	const size_t slot = (size_t)sl * 32 + lane;
 	const uint32_t T = (uint32_t)(slot / TV);
 	const uint32_t o = order[slot];
-	if (o == 0xffffu) return;
-	const uint32_t v = T * TV + o, beg = rowptr[v], deg = rowptr[v + 1] - beg;
-	if (deg > (uint32_t)kLightMaxDeg) return;
-	const uint32_t base = sliceOff[sl];
-	for (uint32_t j = 0; 4u * j < deg; ++j) {
+	uint32_t beg = 0, deg = 0;
+	if (o != 0xffffu) { const uint32_t v = T * TV + o; beg = rowptr[v]; deg = rowptr[v + 1] - beg; if (deg > (uint32_t)kLightMaxDeg) deg = 0; }
+	const uint32_t base = sliceOff[sl], width = (sliceOff[sl + 1] - base) >> 5;
+	for (uint32_t j = 0; j < width; ++j) {
 		uint32_t e[4];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) e[k] = (4u * j + k < deg) ? (uint32_t)gidx[beg + 4u * j + k] : 0u;
+		for (int k = 0; k < 4; ++k) e[k] = (4u * j + k < deg) ? (uint32_t)gidx[beg + 4u * j + k] : dummy;
 		gidxS[(size_t)base + (size_t)j * 32 + lane] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
 	}
 }
@@ -306,9 +318,10 @@ constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per til
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	(void)P;
 	size_t b = 0;
-	b += kBufs * sizeof(uint32_t) * (size_t)(TV + 4);      // s_rp (double buffered when pipelined)
+	b += kBufs * sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16 (double buffered when pipelined)
+	b += kBufs * sizeof(uint32_t) * (size_t)((TV >> 5) + 4); // s_soff: SELL slice starts of the tile
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
-	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist
+	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist (DYNAMIC) / free-colour weight table (UNIFORM)
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
 	b += sizeof(uint32_t) * 8;                             // s_ctl
 	b += sizeof(uint32_t) * 128;                           // s_red (64 x u64)
@@ -316,8 +329,9 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage (double buffered when pipelined)
+	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage (double buffered when pipelined); [stageCap, +16) = dummy colour
 	b += (size_t)colBytes * (size_t)(TV + 16);             // s_new: the tile's new colours, written out coalesced (local + peers)
+	b += kBufs * (size_t)colBytes * (size_t)(TV + 16);     // s_own: the tile's current colours
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -327,17 +341,27 @@ __device__ __forceinline__ void cp_async_4(void * smem, const void * gmem) {
 __device__ __forceinline__ void cp_async_8(void * smem, const void * gmem) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async_16(void * smem, const void * gmem) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
 	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// 1 << c with PTX semantics: shift amounts >= 64 give 0 (the dummy colour sets no bit)
+__device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
+	unsigned long long r;
+	asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(1ull), "r"(c));
+	return r;
 }
 
 template <int W, typename ColT, bool kDyn>
 __global__ void __launch_bounds__(kThreadsB, (kPipe || W > 2) ? 1 : (1024 / kThreadsB))
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const uint32_t nCol = a.nCol, TV = bl.TV;
-	uint32_t * s_rp2  = reinterpret_cast<uint32_t *>(smem_raw);                       // [2][TV+4]
-	float *    s_S    = reinterpret_cast<float *>(s_rp2 + kBufs * (TV + 4));
+	const uint32_t nCol = a.nCol, TV = bl.TV, spt = TV >> 5;
+	uint32_t * s_slot2 = reinterpret_cast<uint32_t *>(smem_raw);                      // [kBufs][TV]
+	uint32_t * s_soff2 = s_slot2 + kBufs * TV;                                        // [kBufs][spt+4]
+	float *    s_S    = reinterpret_cast<float *>(s_soff2 + kBufs * (spt + 4));
 	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
 	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
 	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
@@ -358,9 +382,10 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kWarpQueueCap);
 		off += (size_t)(kThreadsB / 32) * perWarp;
 	}
-	ColT * stage2 = reinterpret_cast<ColT *>(smem_raw + off);                         // [2][stageCap+16]
+	ColT * stage2 = reinterpret_cast<ColT *>(smem_raw + off);                         // [kBufs][stageCap+16]
 	const uint32_t stageStride = bl.stageCap + 16;
 	ColT * s_new = stage2 + (size_t)kBufs * stageStride;
+	ColT * s_own2 = s_new + (TV + 16);                                                // [kBufs][TV+16]
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nWarps = kThreadsB / 32;
@@ -372,6 +397,9 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
 	const ColT * __restrict__ ecol = static_cast<const ColT *>(bl.ecol);
 	constexpr bool isDyn = kDyn;
+	// the padded SELL rows need a colour value outside every palette of this instance: all-ones (255 / 65535).
+	// u8 with W == 4 covers nCol up to 256, where 255 is a real colour: that instance keeps the per-edge degree test.
+	constexpr bool kPad = !(sizeof(ColT) == 1 && W == 4);
 	const float eps = a.eps;
 	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
 
@@ -380,30 +408,36 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		float s = 0.0f; s_S[0] = 0.0f;
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
 	}
-	if (isDyn && !a.countOnly) {
-		const unsigned long long * hc = a.hist[t & 1];
-		const float nF = __uint2float_rn(a.nGlobal), dF = __uint2float_rn(nCol - 1u);
-		for (uint32_t k = tid; k < nCol; k += kThreadsB)
-			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(__uint2float_rn((uint32_t)hc[k]), nF)), dF);
-	}
+	if (tid < 16) for (uint32_t b = 0; b < kBufs; ++b) stage2[(size_t)b * stageStride + bl.stageCap + tid] = (ColT)~(ColT)0;
+	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, s_dist, tid, kThreadsB);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 
-	// Software pipeline over the tiles of this CTA (static round robin: tile = blockIdx + k * gridDim).  The row pointers
-	// and the gathered colours of tile k+1 are fetched with cp.async (LDGSTS: no registers, no warp stalls) into the
-	// other half of the double buffers while tile k is being processed.  The colours sit in ecol as P short runs (one
-	// per source chunk); the static granule list says where each 4-entry granule of the stage comes from.
+	// Per tile everything the vertex loop needs is fetched with cp.async (LDGSTS: no registers, no dependent global
+	// loads later): the slot table (vertex | degree), the SELL slice starts, the tile's current colours and the gathered
+	// neighbour colours.  The colours sit in ecol as P short runs (one per source chunk); the static granule list says
+	// where each 4-entry granule of the stage comes from; its loads run one batch ahead of the copies they feed.
 	auto prefetch = [&](uint32_t T, uint32_t buf) {
 		const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
-		uint32_t * rp = s_rp2 + buf * (TV + 4);
-		for (uint32_t i = tid; i <= nv; i += kThreadsB) cp_async_4(rp + i, a.rowptr + v0 + i);
+		uint32_t * sl = s_slot2 + buf * TV;
+		const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
+		for (uint32_t i = tid; i < (TV >> 2); i += kThreadsB) cp_async_16(sl + 4u * i, gsl + i);
+		uint32_t * so = s_soff2 + buf * (spt + 4);
+		for (uint32_t i = tid; i <= spt; i += kThreadsB) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
+		unsigned char * ow = reinterpret_cast<unsigned char *>(s_own2 + (size_t)buf * (TV + 16));
+		const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
+		const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;      // (colour arrays are padded; tiles start 256-aligned)
+		for (uint32_t i = tid; i < n16; i += kThreadsB) cp_async_16(ow + 16u * i, cb + 16u * i);
 		const uint32_t gb = bl.tileGran[T], ng = bl.tileGran[T + 1] - gb;
 		const uint32_t * __restrict__ gs = bl.granSrc + gb;
 		ColT * stg = stage2 + (size_t)buf * stageStride;
 		constexpr uint32_t kU = 8;
-		for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
-			uint32_t src[kU];
+		uint32_t src[kU];
 #pragma unroll
-			for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
+		for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = tid + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
+		for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
+			uint32_t ahead[kU];
+#pragma unroll
+			for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + (kU + k) * kThreadsB; ahead[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
 #pragma unroll
 			for (uint32_t k = 0; k < kU; ++k) {
 				const uint32_t i = i0 + k * kThreadsB;
@@ -412,6 +446,8 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 					else cp_async_8(stg + 4u * i, ecol + src[k]);
 				}
 			}
+#pragma unroll
+			for (uint32_t k = 0; k < kU; ++k) src[k] = ahead[k];
 		}
 	};
 	if (tid == 0) s_ctl[1] = 0u;
@@ -425,89 +461,87 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		if (kPipe && T + gridDim.x < bl.numTiles) prefetch(T + gridDim.x, buf ^ 1u);
 		const uint32_t v0 = T * TV;
 		const uint32_t nv = min(TV, a.nLocal - v0);
-		const uint32_t * s_rp = s_rp2 + buf * (TV + 4);
+		const uint32_t * s_slot = s_slot2 + buf * TV;
+		const uint32_t * s_soff = s_soff2 + buf * (spt + 4);
+		const ColT * s_own = s_own2 + (size_t)buf * (TV + 16);
 		const ColT * stage = stage2 + (size_t)buf * stageStride;
-		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static permutation gidx
-		//      (CSR order, u16: where edge e's colour sits in this tile's stage).  Thread per vertex; the 2-byte
-		//      indices of a row are fetched 4 at a time once the row pointer is 8-byte aligned. ----
+		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static SELL index words (u16: where
+		//      each edge's colour sits in this tile's stage).  Thread per vertex; a warp's 32 rows are one slice of uniform
+		//      width, so the loop below is warp-uniform and branch free. ----
 		if (useQueue && lane == 0) *wq.count = 0u;
 		__syncwarp();
-		const uint32_t slicesPerTile = TV >> 5;
 		for (uint32_t g = 0; g < nv; g += kThreadsB) {
 			const uint32_t slot = g + tid;                        // slots are degree-sorted: a warp's 32 rows have (almost) equal length
-			const uint32_t sl = T * slicesPerTile + (slot >> 5);  // warp-uniform
-			uint32_t lv = 0xffffu;
-			if (slot < nv) lv = bl.order[(size_t)T * TV + slot];
-			if (lv != 0xffffu) {
-				const uint32_t myBeg = s_rp[lv], deg = s_rp[lv + 1] - myBeg;
-				bool light = deg <= (uint32_t)kLightMaxDeg;
-				if (!light) {                                          // warp-per-vertex list; if it is full the thread does the row itself
-					const uint32_t hi = atomicAdd(&s_ctl[1], 1u);
-					if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)lv; else light = true;
+			const bool inTile = slot < TV;                        // warp-uniform (TV is a multiple of 32)
+			const uint32_t info = inTile ? s_slot[slot] : 0xffffu;
+			const uint32_t lv = info & 0xffffu, deg = info >> 16;
+			const bool valid = lv != 0xffffu;
+			bool light = valid && deg <= (uint32_t)kLightMaxDeg;
+			bool inlineHeavy = false;
+			if (valid && !light) {                                // warp-per-vertex list; if it is full the thread does the row itself
+				const uint32_t hi = atomicAdd(&s_ctl[1], 1u);
+				if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)lv; else inlineHeavy = true;
+			}
+			const uint32_t own = valid ? (uint32_t)s_own[lv] : 0u;
+			unsigned long long m[W];
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] = 0ull;
+			uint32_t same = 0;
+			auto addc = [&](uint32_t idx) {
+				const uint32_t c = stage[idx];
+				same += (c == own);
+				if (W == 1) m[0] |= kPad ? bit64_clamped(c) : (1ull << c);
+				else {
+#pragma unroll
+					for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
 				}
-				if (light) {
-					const uint32_t gv = a.vBegin + v0 + lv;
-					const uint32_t own = (uint32_t)cur[gv];
-					unsigned long long m[W];
-#pragma unroll
-					for (int w = 0; w < W; ++w) m[w] = 0ull;
-					auto add = [&](uint32_t idx) {
-						const uint32_t c = stage[idx];
-						if (W == 1) m[0] |= 1ull << c;
-						else {
-#pragma unroll
-							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
-						}
-					};
-					uint32_t same = 0;
-					auto addc = [&](uint32_t idx) { const uint32_t c = stage[idx]; same += (c == own);
-						if (W == 1) m[0] |= 1ull << c;
-						else {
-#pragma unroll
-							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
-						} };
-					if (deg <= (uint32_t)kLightMaxDeg) {
-						// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
-						const uint32_t so0 = bl.sliceOff[sl], nW = (deg + 3u) >> 2;
-						const uint2 * gq = bl.gidxS + so0 + lane;
+			};
+			if (inTile) {
+				// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
+				const uint32_t so0 = s_soff[slot >> 5], nW = (s_soff[(slot >> 5) + 1] - so0) >> 5;
+				const uint2 * gq = bl.gidxS + so0 + lane;
+				const uint32_t degL = light ? deg : 0u;           // (only the kPad == false instance tests it)
 #ifndef MCMCB200_MASK_PF
 #define MCMCB200_MASK_PF 6
 #endif
-						constexpr uint32_t kMP = MCMCB200_MASK_PF;       // words fetched up front (covers degree <= 4*kMP in one round trip)
-						uint2 q[kMP];
+				constexpr uint32_t kMP = MCMCB200_MASK_PF;       // words fetched up front (covers degree <= 4*kMP in one round trip)
+				uint2 q[kMP];
 #pragma unroll
-						for (uint32_t j = 0; j < kMP; ++j) if (j < nW) q[j] = __ldcs(gq + (size_t)j * 32);
+				for (uint32_t j = 0; j < kMP; ++j) if (j < nW) q[j] = __ldcs(gq + (size_t)j * 32);
 #pragma unroll
-						for (uint32_t j = 0; j < kMP; ++j) {
-							if (j < nW) {
-								const uint32_t p0 = 4u * j;
-								addc(q[j].x & 0xffffu);
-								if (p0 + 1u < deg) addc(q[j].x >> 16);
-								if (p0 + 2u < deg) addc(q[j].y & 0xffffu);
-								if (p0 + 3u < deg) addc(q[j].y >> 16);
-							}
-						}
-						for (uint32_t j = kMP; j < nW; j += 2) {
-							const uint2 q0 = __ldcs(gq + (size_t)j * 32);
-							uint2 q1 = make_uint2(0u, 0u);
-							if (j + 1u < nW) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
-							const uint32_t p0 = 4u * j;
-							addc(q0.x & 0xffffu);
-							if (p0 + 1u < deg) addc(q0.x >> 16);
-							if (p0 + 2u < deg) addc(q0.y & 0xffffu);
-							if (p0 + 3u < deg) addc(q0.y >> 16);
-							if (p0 + 4u < deg) addc(q1.x & 0xffffu);
-							if (p0 + 5u < deg) addc(q1.x >> 16);
-							if (p0 + 6u < deg) addc(q1.y & 0xffffu);
-							if (p0 + 7u < deg) addc(q1.y >> 16);
-						}
-					} else {                                           // overflow of the heavy list: plain CSR-order indices
-						for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
+				for (uint32_t j = 0; j < kMP; ++j) {
+					if (j < nW) {
+						const uint32_t p0 = 4u * j;
+						if (kPad || p0 < degL) addc(q[j].x & 0xffffu);
+						if (kPad || p0 + 1u < degL) addc(q[j].x >> 16);
+						if (kPad || p0 + 2u < degL) addc(q[j].y & 0xffffu);
+						if (kPad || p0 + 3u < degL) addc(q[j].y >> 16);
 					}
-					commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
-					                             useQueue ? &wq : nullptr, s_new, v0);
+				}
+				for (uint32_t j = kMP; j < nW; j += 2) {
+					const uint2 q0 = __ldcs(gq + (size_t)j * 32);
+					uint2 q1 = make_uint2(bl.stageCap | (bl.stageCap << 16), bl.stageCap | (bl.stageCap << 16));
+					const bool two = j + 1u < nW;
+					if (two) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
+					const uint32_t p0 = 4u * j;
+					if (kPad || p0 < degL) addc(q0.x & 0xffffu);
+					if (kPad || p0 + 1u < degL) addc(q0.x >> 16);
+					if (kPad || p0 + 2u < degL) addc(q0.y & 0xffffu);
+					if (kPad || p0 + 3u < degL) addc(q0.y >> 16);
+					if (kPad ? two : (p0 + 4u < degL)) addc(q1.x & 0xffffu);
+					if (kPad ? two : (p0 + 5u < degL)) addc(q1.x >> 16);
+					if (kPad ? two : (p0 + 6u < degL)) addc(q1.y & 0xffffu);
+					if (kPad ? two : (p0 + 7u < degL)) addc(q1.y >> 16);
 				}
 			}
+			if (inlineHeavy) {                                    // overflow of the heavy list: plain CSR-order indices
+				const uint32_t myBeg = a.rowptr[v0 + lv];
+				for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
+				light = true;
+			}
+			if (light)
+				commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + v0 + lv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
+				                             useQueue ? &wq : nullptr, s_new, v0);
 			if (useQueue) {                          // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
 				__syncwarp();
 				const uint32_t qn = min(*wq.count, wq.cap);
@@ -528,10 +562,10 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		__syncthreads();
 		const uint32_t nHeavy = min(s_ctl[1], kHeavyCap);
 		for (uint32_t h = warp; h < nHeavy; h += nWarps) {       // warp per heavy vertex
-			const uint32_t slot = s_heavy[h];
-			const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
-			const uint32_t gv = a.vBegin + v0 + slot;
-			const uint32_t own = (uint32_t)cur[gv];
+			const uint32_t hv = s_heavy[h];
+			const uint32_t hb = a.rowptr[v0 + hv], hd = a.rowptr[v0 + hv + 1] - hb;
+			const uint32_t gv = a.vBegin + v0 + hv;
+			const uint32_t own = (uint32_t)s_own[hv];
 			unsigned long long m[W];
 #pragma unroll
 			for (int w = 0; w < W; ++w) m[w] = 0ull;
@@ -546,7 +580,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
 			same = __reduce_add_sync(0xffffffffu, same);
 			if (lane == 0)
-				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + slot, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
+				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + hv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
 				                             nullptr, s_new, v0);
 		}
 		__syncthreads();                                          // the tile is finished: everybody has read the heavy list, s_new is complete

@@ -135,6 +135,25 @@ __global__ void finalize_kernel(SweepArgs a) { finalize_sweep_device(a); }
 // reproduced addend by addend with __fadd_rn (never contracted); the loops below are kept as tight as possible
 // because they are the kernel's instruction hot spot (65 % of the warp instructions before this rewrite).
 // ---------------------------------------------------------------------------------------------
+// Per-CTA proposal table in shared memory (nCol floats).
+//   DYNAMIC: dist[k] = (1 - hist[k]/n) / (nCol-1)                        (genDynamicDistribution, coloringMCMC_utils.cu:69)
+//   UNIFORM: the same storage holds freeW[Zn] = (1 - eps*Zn) / (nCol-Zn), the weight of a free colour of a vertex with Zn
+//            occupied colours (coloringMCMC_CPU.cpp:416) -- one table lookup instead of a correctly rounded division per
+//            conflicting vertex; identical operations, identical bits.
+template <bool kDyn>
+__device__ __forceinline__ void fill_proposal_table(const SweepArgs & a, uint32_t t, float * s_dist, int tid, int nThreads) {
+	const uint32_t nCol = a.nCol;
+	if (kDyn) {
+		const unsigned long long * hc = a.hist[t & 1];
+		const float nF = __uint2float_rn(a.nGlobal), dF = __uint2float_rn(nCol - 1u);
+		for (uint32_t k = tid; k < nCol; k += nThreads)
+			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(__uint2float_rn((uint32_t)hc[k]), nF)), dF);
+	} else {
+		for (uint32_t k = tid; k < nCol; k += nThreads)     // Zn = k occupied, Zp = nCol - k >= 1 free
+			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(a.eps, __uint2float_rn(k))), __uint2float_rn(nCol - k));
+	}
+}
+
 // "stay" distribution (all colours eps, own colour 1-(nCol-1)eps) when the draw fell into an epsilon tail:
 // probability ~ nCol*eps per vertex, kept out of line.
 template <bool kDyn>
@@ -272,7 +291,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 			} else {
 				float freeW = 0.0f, r = 0.0f;
 				if (!isDyn) {                                 // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
-					freeW = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(eps, __uint2float_rn(Zn))), __uint2float_rn(Zp));
+					freeW = s_dist[Zn];                       // fill_proposal_table: (1 - eps*Zn) / Zp, Zp >= 1 here
 				} else {                                      // reminder / Zp, coloringMCMC_balance.cu:104-109,124
 					float rem = 0.0f;
 #pragma unroll
@@ -287,7 +306,14 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 					r = __fdiv_rn(rem, __uint2float_rn(Zp));
 				}
 				if (queue != nullptr) {
-					const uint32_t qi = atomicAdd(queue->count, 1u);
+					// one atomic per converged group of lanes instead of one per lane
+					const unsigned act = __activemask();
+					const int leader = __ffs((int)act) - 1;
+					const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+					uint32_t qbase = 0;
+					if ((int)(threadIdx.x & 31) == leader) qbase = atomicAdd(queue->count, (uint32_t)__popc(act));
+					qbase = __shfl_sync(act, qbase, leader);
+					const uint32_t qi = qbase + (uint32_t)__popc(act & lt);
 					if (qi < queue->cap) {                    // park the walk; drained by dense lanes (drain_walk_queue)
 #pragma unroll
 						for (int w = 0; w < W; ++w) queue->mask[(size_t)qi * W + w] = m[w];
@@ -359,12 +385,7 @@ sweep_kernel(const SweepArgs a) {
 		float s = 0.0f; s_S[0] = 0.0f;
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
 	}
-	if (isDyn && !a.countOnly) {   // genDynamicDistribution, coloringMCMC_utils.cu:69
-		const unsigned long long * hc = a.hist[t & 1];
-		const float nF = __uint2float_rn(a.nGlobal), dF = __uint2float_rn(nCol - 1u);
-		for (uint32_t k = tid; k < nCol; k += kThreads)
-			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(__uint2float_rn((uint32_t)hc[k]), nF)), dF);
-	}
+	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, s_dist, tid, kThreads);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 
 	// ---- persistent tile loop ----
