@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcmcb200.so")
+LIB_PATH = os.environ.get("MCMCB200_LIB") or os.path.join(HERE, "libmcmcb200.so")   # MCMCB200_LIB: kernel-variant experiments
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EUNSUPPORTED, ETAPE, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 PROPOSAL_UNIFORM, PROPOSAL_DYNAMIC = 0, 1

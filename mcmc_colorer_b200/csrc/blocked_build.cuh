@@ -10,7 +10,7 @@ namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
 	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.slotInfo); cudaFree(L.sliceOff);
-	cudaFree(L.granSrc); cudaFree(L.tileGran); cudaFree(L.items);
+	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items);
 	L = BlockedLayout{};
 }
 
@@ -50,7 +50,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 		blk_max_tile_edges_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, tv, nt, d_tmp); (*launches)++;
 		BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 		BLK_CU(cudaStreamSynchronize(stream));
-		const uint64_t worst = (uint64_t)h2[0] + 3ull * std::min<uint64_t>(P, h2[0]);
+		const uint64_t worst = (uint64_t)h2[0] + 3ull * std::min<uint64_t>(P, h2[0]) + 16ull;   // + run padding + start misalignment
 		if (worst <= stageCap) { TV = tv; numTiles = nt; break; }
 	}
 	if (TV == 0) goto done;                                     // a row (or 256 of them) exceeds the stage: direct kernel only
@@ -112,16 +112,16 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&d_stageOff, sizeof(uint32_t) * ((size_t)numTiles * (P + 1))));
 	BLK_CU(cudaMemsetAsync(d_tmp, 0, 2 * sizeof(uint32_t), stream));
 	blk_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_gs, d_scanT, d_plenT, P, numTiles, d_runStart, d_stageOff, d_tmp); (*launches)++;
-	BLK_CU(cudaMalloc(&L.granSrc, sizeof(uint32_t) * ((size_t)(L.totalPadded >> 2) + 16)));
-	BLK_CU(cudaMalloc(&L.tileGran, sizeof(uint32_t) * ((size_t)numTiles + 1)));
-	blk_gran_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_runStart, d_scanT, d_plenT, cells, L.granSrc); (*launches)++;
-	blk_tile_gran_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_scanT, P, numTiles, L.totalPadded, L.tileGran); (*launches)++;
+	BLK_CU(cudaMalloc(&L.granDst, sizeof(uint32_t) * ((size_t)(L.totalPadded >> 2) + 16)));
+	BLK_CU(cudaMalloc(&L.tileBase, sizeof(uint32_t) * ((size_t)numTiles + 1)));
+	blk_gran_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_runStart, d_scanT, d_plenT, cells, L.granDst); (*launches)++;
+	blk_tile_base_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_scanT, P, numTiles, L.totalPadded, L.tileBase); (*launches)++;
 	BLK_CU(cudaMalloc(&L.srcLocal, sizeof(uint16_t) * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.srcLocal, 0, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));
 	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
 	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
 	blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
-	                                                                d_stageOff, L.srcLocal, L.gidx); (*launches)++;
+	                                                                d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
 	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
 	// ---- SELL-32-sigma copy of gidx for the light rows: per tile, vertices by descending degree; 32-slot slices interleaved ----
@@ -174,11 +174,21 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMemcpyAsync(bs.data(), d_bs, sizeof(uint32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, stream));
 	BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	BLK_CU(cudaStreamSynchronize(stream));
-	if (h2[0] > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
-	for (uint32_t b = 0; b < P; ++b)
-		for (uint32_t beg = bs[b]; beg < bs[b + 1]; beg += kItemEntries) {
-			items.push_back(b); items.push_back(beg); items.push_back(std::min(bs[b + 1], beg + kItemEntries));
-		}
+	if (h2[0] + 16u > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
+	// part-major order: item k of every bucket before item k+1 of any.  Pass A hands the items out round robin, so the CTAs
+	// running at the same time hold neighbouring source chunks and write the same stretch of tiles: the runs of (T, b) and
+	// (T, b+1) are adjacent in the tile-major ecol, and their shared boundary sectors meet in L2 instead of going to DRAM half
+	// written (measured: 3.7 GB of read-for-fill traffic per sweep with the bucket-major order).
+	{
+		uint32_t maxParts = 0;
+		for (uint32_t b = 0; b < P; ++b) maxParts = std::max<uint32_t>(maxParts, (bs[b + 1] - bs[b] + kItemEntries - 1) / kItemEntries);
+		for (uint32_t part = 0; part < maxParts; ++part)
+			for (uint32_t b = 0; b < P; ++b) {
+				const uint64_t beg = (uint64_t)bs[b] + (uint64_t)part * kItemEntries;
+				if (beg >= bs[b + 1]) continue;
+				items.push_back(b); items.push_back((uint32_t)beg); items.push_back((uint32_t)std::min<uint64_t>(bs[b + 1], beg + kItemEntries));
+			}
+	}
 	L.numItems = (uint32_t)(items.size() / 3);
 	BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * std::max<size_t>(items.size(), 3)));
 	BLK_CU(cudaMemcpyAsync(L.items, items.data(), sizeof(uint32_t) * items.size(), cudaMemcpyHostToDevice, stream));
@@ -200,7 +210,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	BlockedArgs b{};
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
-	b.granSrc = L.granSrc; b.tileGran = L.tileGran;
+	b.granDst = L.granDst; b.tileBase = L.tileBase;
 	b.items = L.items; b.numItems = L.numItems;
 	return b;
 }

@@ -28,16 +28,39 @@ namespace mcmcb200 {
 constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
 constexpr int      kThreadsA  = 256;
+// pass-B geometry.  MCMCB200_WS = 0 (default): every thread stages, single buffer, 1024 / MCMCB200_THREADS_B CTAs per SM
+// (two CTAs hide each other's staging).  MCMCB200_WS = 1: warp-specialised -- kProdWarps producer warps stage tile k+1 with
+// cp.async into the other half of the double buffers while the consumer warps sweep tile k; one CTA of MCMCB200_THREADS_B
+// threads per SM.  Measured on B200 (config 3): 4.59 vs 4.80 ms/sweep, so the plain variant is the default.
+#ifndef MCMCB200_WS
+#define MCMCB200_WS 0
+#endif
 #ifndef MCMCB200_THREADS_B
-#define MCMCB200_THREADS_B 512
+#define MCMCB200_THREADS_B (MCMCB200_WS ? 1024 : 512)
 #endif
-#ifndef MCMCB200_PIPELINE
-#define MCMCB200_PIPELINE 0      /* measured on B200: 2 CTAs/SM x 512 threads beat the double-buffered 1 x 1024 variant (profiles/) */
+#ifndef MCMCB200_MIN_CTAS_B
+#define MCMCB200_MIN_CTAS_B (MCMCB200_WS ? 1 : (1024 / MCMCB200_THREADS_B))
 #endif
-constexpr bool kPipe = MCMCB200_PIPELINE != 0;   // 1: one CTA/SM, tiles double buffered; 0: two CTAs/SM, single buffer
-constexpr uint32_t kBufs = kPipe ? 2u : 1u;
-constexpr int      kThreadsB  = MCMCB200_THREADS_B;
-constexpr uint32_t kItemEntries = 1u << 17;          // pass-A work item: up to 131072 entries of one bucket
+#ifndef MCMCB200_PROD_WARPS
+#define MCMCB200_PROD_WARPS 2
+#endif
+#ifndef MCMCB200_QUEUE_CAP
+#define MCMCB200_QUEUE_CAP 48
+#endif
+#ifndef MCMCB200_HEAVY_CAP
+#define MCMCB200_HEAVY_CAP 1024
+#endif
+constexpr bool kWS = MCMCB200_WS != 0;
+constexpr uint32_t kBufs = kWS ? 2u : 1u;
+constexpr int      kProdWarps = kWS ? MCMCB200_PROD_WARPS : 0;
+// palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads
+template <int W> struct PassB { static constexpr int threads = (W <= 2) ? MCMCB200_THREADS_B : 512;
+                                static constexpr int consThreads = threads - 32 * kProdWarps;
+                                static constexpr int minCtas = (W <= 2) ? MCMCB200_MIN_CTAS_B : 1; };
+#ifndef MCMCB200_ITEM_BITS
+#define MCMCB200_ITEM_BITS 17
+#endif
+constexpr uint32_t kItemEntries = 1u << MCMCB200_ITEM_BITS;   // pass-A work item: up to this many entries of one bucket
 
 struct BlockedLayout {
 	bool      valid = false;
@@ -53,8 +76,8 @@ struct BlockedLayout {
 	uint16_t * order = nullptr;      // (construction only) [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
 	uint32_t * slotInfo = nullptr;   // [numTiles*TV] slot -> (local vertex | degree << 16); 0xffff = empty slot.  Staged per tile by cp.async
 	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
-	uint32_t * granSrc = nullptr;    // [totalPadded/4]  tile-major: where in ecol the i-th 4-entry granule of the tile's stage comes from
-	uint32_t * tileGran = nullptr;   // [numTiles+1]     first granule of each tile in granSrc
+	uint32_t * granDst = nullptr;    // [totalPadded/4]  chunk-major granule (4 entries of srcLocal) -> its granule in the tile-major ecol
+	uint32_t * tileBase = nullptr;   // [numTiles+1]     first entry of each tile's stage image in ecol
 	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
 	uint32_t  numItems = 0;
 	size_t    smemA = 0, smemB = 0;
@@ -69,8 +92,8 @@ struct BlockedArgs {
 	const uint2 * gidxS;
 	const uint32_t * slotInfo;
 	const uint32_t * sliceOff;
-	const uint32_t * granSrc;
-	const uint32_t * tileGran;
+	const uint32_t * granDst;
+	const uint32_t * tileBase;
 	const uint32_t * items;
 	uint32_t numItems;
 };
@@ -144,7 +167,8 @@ __global__ void blk_tables_kernel(const uint32_t * gs, const uint32_t * scanT, c
 
 __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * vals, uint32_t nnz, const uint32_t * neighs,
                                         const uint32_t * tileE, uint32_t numTiles, uint32_t P, const uint32_t * us /* [P][numTiles] first sorted index */,
-                                        const uint32_t * gs /* [P][numTiles] */, const uint32_t * stageOff, uint16_t * srcLocal, uint16_t * gidx) {
+                                        const uint32_t * gs /* [P][numTiles] */, const uint32_t * stageOff, const uint32_t * scanT, uint32_t alignMask,
+                                        uint16_t * srcLocal, uint16_t * gidx) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nnz) return;
 	const uint32_t e = vals[i], b = keys[i];
@@ -152,7 +176,8 @@ __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * 
 	const size_t idx = (size_t)b * numTiles + T;
 	const uint32_t r = i - us[idx];
 	srcLocal[gs[idx] + r] = (uint16_t)(neighs[e] & (kChunkV - 1u));
-	gidx[e] = (uint16_t)(stageOff[(size_t)T * (P + 1) + b] + r);
+	// position in the tile's stage: pass B copies the tile's block from the 16-byte boundary below its first entry
+	gidx[e] = (uint16_t)((scanT[(size_t)T * P] & alignMask) + stageOff[(size_t)T * (P + 1) + b] + r);
 }
 
 __global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32_t numTiles, uint32_t total, uint32_t * bs) {
@@ -161,20 +186,21 @@ __global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32
 	if (b == P) bs[P] = total;
 }
 
-// granSrc: one descriptor per 4-entry granule of every tile's stage buffer (tile-major, contiguous per tile), so that
-// pass B stages a tile with a flat, fully parallel copy loop instead of walking P run descriptors.
-__global__ void blk_gran_kernel(const uint32_t * runStart /* [T][b] */, const uint32_t * scanT /* [T][b] */, const uint32_t * plenT /* [T][b] */,
-                                size_t cells, uint32_t * granSrc) {
+// granDst: pass A reads srcLocal chunk-major (so that the gather runs out of one 64 Ki-colour chunk in shared memory) and
+// writes ecol TILE-major, so that pass B finds the whole stage image of a tile as one contiguous block.  One entry per
+// 4-entry granule: where the granule of run (chunk b, tile T) lands.
+__global__ void blk_gran_kernel(const uint32_t * runStart /* [T][b] chunk-major start */, const uint32_t * scanT /* [T][b] tile-major start */,
+                                const uint32_t * plenT /* [T][b] */, size_t cells, uint32_t * granDst) {
 	const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= cells) return;
-	const uint32_t g0 = scanT[idx] >> 2, ng = plenT[idx] >> 2, src = runStart[idx];
-	for (uint32_t g = 0; g < ng; ++g) granSrc[g0 + g] = src + 4u * g;
+	const uint32_t g0 = runStart[idx] >> 2, ng = plenT[idx] >> 2, d0 = scanT[idx] >> 2;
+	for (uint32_t g = 0; g < ng; ++g) granDst[g0 + g] = d0 + g;
 }
 
-__global__ void blk_tile_gran_kernel(const uint32_t * scanT, uint32_t P, uint32_t numTiles, uint32_t totalPadded, uint32_t * tileGran) {
+__global__ void blk_tile_base_kernel(const uint32_t * scanT, uint32_t P, uint32_t numTiles, uint32_t totalPadded, uint32_t * tileBase) {
 	const uint32_t T = blockIdx.x * blockDim.x + threadIdx.x;
-	if (T < numTiles) tileGran[T] = scanT[(size_t)T * P] >> 2;
-	if (T == numTiles) tileGran[T] = totalPadded >> 2;
+	if (T < numTiles) tileBase[T] = scanT[(size_t)T * P];
+	if (T == numTiles) tileBase[T] = totalPadded;
 }
 
 // SELL-32-sigma (sigma = one tile) construction -------------------------------------------------------------------
@@ -240,6 +266,18 @@ __global__ void blk_sell_fill_kernel(const uint32_t * rowptr, const uint16_t * o
 	}
 }
 
+#ifndef MCMCB200_ST_LAST
+#define MCMCB200_ST_LAST 1      /* ecol stores keep their L2 lines (evict_last) until the neighbouring run completes the sector */
+#endif
+__device__ __forceinline__ void st_ecol32(void * p, uint32_t v, unsigned long long pol) {
+	if (MCMCB200_ST_LAST) asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+	else *reinterpret_cast<uint32_t *>(p) = v;
+}
+__device__ __forceinline__ void st_ecol64(void * p, uint2 v, unsigned long long pol) {
+	if (MCMCB200_ST_LAST) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+	else *reinterpret_cast<uint2 *>(p) = v;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // pass A: ecol[pos] = cur[bucket * 65536 + srcLocal[pos]]  -- the gather runs out of shared memory
 // ------------------------------------------------------------------------------------------------------------------
@@ -255,11 +293,11 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ ecol = static_cast<ColT *>(bl.ecol);
 	const int tid = threadIdx.x;
-	// contiguous share of the work items, so that consecutive items of one bucket reuse the chunk already in shared memory
-	const uint32_t per = (bl.numItems + gridDim.x - 1) / gridDim.x;
-	const uint32_t it0 = blockIdx.x * per, it1 = min(bl.numItems, it0 + per);
+	// items round robin in part-major order (see build_blocked_layout): concurrently running CTAs write neighbouring runs
+	unsigned long long pol = 0ull;
+	if (MCMCB200_ST_LAST) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	uint32_t have = 0xffffffffu;
-	for (uint32_t it = it0; it < it1; ++it) {
+	for (uint32_t it = blockIdx.x; it < bl.numItems; it += gridDim.x) {
 		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
 		if (b != have) {
 			__syncthreads();
@@ -272,17 +310,21 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 			__syncthreads();
 		}
 		// runs are padded to 4 entries, so an item may start 4 (mod 8): scalar head up to the next multiple of 8,
-		// then 8 entries per thread per step: one 128-bit load of local ids, 8 shared-memory gathers, one packed store
+		// then 8 entries (2 granules) per thread per step: one 128-bit load of local ids, one 64-bit load of the two granule
+		// destinations, 8 shared-memory gathers, two packed stores into the tile-major ecol
 		const uint32_t body = min(end, (beg + 7u) & ~7u);
-		if (beg + tid < body) ecol[beg + tid] = chunk[bl.srcLocal[beg + tid]];
-		// four 128-bit id loads in flight per thread (the pass is pure streaming: bytes in flight = bandwidth)
+		if (beg + tid < body) { const uint32_t j = beg + tid; ecol[4u * (size_t)bl.granDst[j >> 2] + (j & 3u)] = chunk[bl.srcLocal[j]]; }
 		constexpr uint32_t kU = 4;
 		for (uint32_t i0 = body + 8u * tid; i0 < end; i0 += 8u * kThreadsA * kU) {
 			uint4 ids[kU];
+			uint2 gd[kU];
 #pragma unroll
 			for (uint32_t k = 0; k < kU; ++k) {
 				const uint32_t i = i0 + k * 8u * kThreadsA;
-				if (i + 8u <= end) ids[k] = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
+				if (i + 8u <= end) {
+					ids[k] = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
+					gd[k] = __ldcs(reinterpret_cast<const uint2 *>(bl.granDst + (i >> 2)));
+				}
 			}
 #pragma unroll
 			for (uint32_t k = 0; k < kU; ++k) {
@@ -292,17 +334,14 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 					const uint32_t c0 = chunk[d.x & 0xffffu], c1 = chunk[d.x >> 16], c2 = chunk[d.y & 0xffffu], c3 = chunk[d.y >> 16];
 					const uint32_t c4 = chunk[d.z & 0xffffu], c5 = chunk[d.z >> 16], c6 = chunk[d.w & 0xffffu], c7 = chunk[d.w >> 16];
 					if (sizeof(ColT) == 1) {
-						uint2 pk;
-						pk.x = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-						pk.y = c4 | (c5 << 8) | (c6 << 16) | (c7 << 24);
-						__stcs(reinterpret_cast<uint2 *>(ecol + i), pk);
+						st_ecol32(ecol + 4u * (size_t)gd[k].x, c0 | (c1 << 8) | (c2 << 16) | (c3 << 24), pol);
+						st_ecol32(ecol + 4u * (size_t)gd[k].y, c4 | (c5 << 8) | (c6 << 16) | (c7 << 24), pol);
 					} else {
-						uint4 pk;
-						pk.x = c0 | (c1 << 16); pk.y = c2 | (c3 << 16); pk.z = c4 | (c5 << 16); pk.w = c6 | (c7 << 16);
-						__stcs(reinterpret_cast<uint4 *>(ecol + i), pk);
+						st_ecol64(ecol + 4u * (size_t)gd[k].x, make_uint2(c0 | (c1 << 16), c2 | (c3 << 16)), pol);
+						st_ecol64(ecol + 4u * (size_t)gd[k].y, make_uint2(c4 | (c5 << 16), c6 | (c7 << 16)), pol);
 					}
 				} else if (i < end) {
-					for (uint32_t j = i; j < end; ++j) ecol[j] = chunk[bl.srcLocal[j]];
+					for (uint32_t j = i; j < end; ++j) ecol[4u * (size_t)bl.granDst[j >> 2] + (j & 3u)] = chunk[bl.srcLocal[j]];
 				}
 			}
 		}
@@ -312,13 +351,15 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 // ------------------------------------------------------------------------------------------------------------------
 // pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kWarpQueueCap = 48;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier; overflow walks inline)
-constexpr uint32_t kHeavyCap = 1024;        // warp-per-vertex work list per tile (overflow is handled by the owning thread)
+constexpr uint32_t kWarpQueueCap = MCMCB200_QUEUE_CAP;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier; overflow walks inline)
+__host__ __device__ constexpr uint32_t warp_queue_cap(int W) { return W == 1 ? kWarpQueueCap : (kWarpQueueCap * 5u) / 6u; }   // 24- vs 32-byte entries
+constexpr uint32_t kHeavyCap = MCMCB200_HEAVY_CAP;        // warp-per-vertex work list per tile (overflow is handled by the owning thread)
 
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	(void)P;
+	const int consWarps = (((W <= 2) ? MCMCB200_THREADS_B : 512) >> 5) - kProdWarps;
 	size_t b = 0;
-	b += kBufs * sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16 (double buffered when pipelined)
+	b += kBufs * sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16
 	b += kBufs * sizeof(uint32_t) * (size_t)((TV >> 5) + 4); // s_soff: SELL slice starts of the tile
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist (DYNAMIC) / free-colour weight table (UNIFORM)
@@ -328,9 +369,9 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint32_t) * 32;                            // per-warp queue counters
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
-	if (W <= 2) b += (size_t)(kThreadsB / 32) * kWarpQueueCap * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage (double buffered when pipelined); [stageCap, +16) = dummy colour
-	b += (size_t)colBytes * (size_t)(TV + 16);             // s_new: the tile's new colours, written out coalesced (local + peers)
+	if (W <= 2) b += (size_t)consWarps * warp_queue_cap(W) * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
+	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage; [stageCap, +16) = dummy colour
+	b += kBufs * (size_t)colBytes * (size_t)(TV + 16);     // s_new: the tile's new colours, written out coalesced (local + peers)
 	b += kBufs * (size_t)colBytes * (size_t)(TV + 16);     // s_own: the tile's current colours
 	return (b + 15) & ~(size_t)15;
 }
@@ -347,6 +388,10 @@ __device__ __forceinline__ void cp_async_16(void * smem, const void * gmem) {
 __device__ __forceinline__ void cp_async_commit_wait_all() {
 	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+// named barriers (ids 1..15; id 0 is __syncthreads): producer/consumer hand-over of the tile buffers
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;   // kBarFull + buf, kBarEmpty + buf
 // 1 << c with PTX semantics: shift amounts >= 64 give 0 (the dummy colour sets no bit)
 __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 	unsigned long long r;
@@ -354,278 +399,349 @@ __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 	return r;
 }
 
+// shared-memory views of one pass-B CTA
+template <int W, typename ColT>
+struct PassBShared {
+	uint32_t * slot2; uint32_t * soff2; float * S; float * dist; int * hist; uint32_t * ctl; unsigned long long * red;
+	uint32_t * qcnt; uint16_t * heavy; unsigned char * queues; ColT * stage2; ColT * new2; ColT * own2;
+	uint32_t stageStride, tvStride, soffStride;
+	__device__ __forceinline__ PassBShared(unsigned char * raw, uint32_t nCol, uint32_t TV, uint32_t stageCap) {
+		const uint32_t spt = TV >> 5;
+		slot2 = reinterpret_cast<uint32_t *>(raw);
+		soff2 = slot2 + kBufs * TV;
+		soffStride = spt + 4;
+		S = reinterpret_cast<float *>(soff2 + kBufs * soffStride);
+		dist = S + ((nCol + 1 + 3) & ~3u);
+		hist = reinterpret_cast<int *>(dist + ((nCol + 3) & ~3u));
+		ctl = reinterpret_cast<uint32_t *>(hist + ((nCol + 3) & ~3u));
+		red = reinterpret_cast<unsigned long long *>(ctl + 8);
+		qcnt = ctl + 8 + 128;
+		heavy = reinterpret_cast<uint16_t *>(ctl + 8 + 160);
+		size_t off = (size_t)(reinterpret_cast<unsigned char *>(heavy + kHeavyCap) - raw);
+		off = (off + 15) & ~(size_t)15;
+		queues = raw + off;
+		if (W <= 2) off += (size_t)(PassB<W>::consThreads / 32) * warp_queue_cap(W) * (8 * W + 16);
+		stage2 = reinterpret_cast<ColT *>(raw + off);
+		stageStride = stageCap + 16;
+		tvStride = TV + 16;
+		new2 = stage2 + (size_t)kBufs * stageStride;
+		own2 = new2 + (size_t)kBufs * tvStride;
+	}
+};
+
+// cp.async copies of everything tile T needs into buffer `buf`, spread over nThr threads (this thread = thr; whole warps).
+// tb, te = the tile's entry range in ecol (bl.tileBase[T], bl.tileBase[T+1]).
+template <int W, typename ColT>
+__device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const ColT * cur,
+                                           uint32_t T, uint32_t tb, uint32_t te, uint32_t buf, uint32_t thr, uint32_t nThr) {
+	const uint32_t TV = bl.TV, spt = TV >> 5;
+	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
+	uint32_t * sl = sm.slot2 + buf * TV;
+	const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
+	for (uint32_t i = thr; i < (TV >> 2); i += nThr) cp_async_16(sl + 4u * i, gsl + i);
+	uint32_t * so = sm.soff2 + buf * sm.soffStride;
+	for (uint32_t i = thr; i <= spt; i += nThr) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
+	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.own2 + (size_t)buf * sm.tvStride);
+	const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
+	const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;          // (colour arrays are padded; tiles start 256-aligned)
+	for (uint32_t i = thr; i < n16; i += nThr) cp_async_16(ow + 16u * i, cb + 16u * i);
+	// the gathered neighbour colours: pass A left the tile's whole stage image contiguous in ecol; copy it from the 16-byte
+	// boundary below its first entry (the static indices in gidx / gidxS include that offset)
+	constexpr uint32_t alignE = 16u / (uint32_t)sizeof(ColT);
+	const uint32_t a0 = tb & ~(alignE - 1u);
+	const uint32_t nC = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) >> 4;
+	const unsigned char * eb = reinterpret_cast<const unsigned char *>(static_cast<const ColT *>(bl.ecol) + a0);
+	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stage2 + (size_t)buf * sm.stageStride);
+	for (uint32_t i = thr; i < nC; i += nThr) cp_async_16(stg + 16u * i, eb + 16u * i);
+}
+
+// per-tile views handed to the slot / heavy-list routines
+template <int W, typename ColT>
+struct TileView {
+	const uint32_t * slot; const uint32_t * soff; const ColT * own; const ColT * stage; ColT * snew; uint32_t * heavyCount;
+	uint32_t v0, nv;
+};
+
+// ---- phases 1'+2+3 for one slot (thread per vertex): occupancy mask straight from the stage buffer through the static SELL
+//      index words (u16: where each edge's colour sits in this tile's stage), then commit_vertex.  A warp's 32 rows are one
+//      slice of uniform width, so the mask loop is warp-uniform and branch free. ----
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsB, (kPipe || W > 2) ? 1 : (1024 / kThreadsB))
+__device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const TileView<W, ColT> & tv,
+                                           uint32_t t, ColT * __restrict__ nxt, uint32_t slot, int lane, float stayW,
+                                           const WalkQueue<W> * wq, unsigned long long & accDirected, unsigned long long & accViol) {
+	// the padded SELL rows need a colour value outside every palette of this instance: all-ones (255 / 65535).
+	// u8 with W == 4 covers nCol up to 256, where 255 is a real colour: that instance keeps the per-edge degree test.
+	constexpr bool kPad = !(sizeof(ColT) == 1 && W == 4);
+	const uint32_t TV = bl.TV;
+	const ColT * stage = tv.stage;
+	const bool inTile = slot < TV;                            // warp-uniform (TV is a multiple of 32)
+	const uint32_t info = inTile ? tv.slot[slot] : 0xffffu;
+	const uint32_t lv = info & 0xffffu, deg = info >> 16;
+	const bool valid = lv != 0xffffu;
+	bool light = valid && deg <= (uint32_t)kLightMaxDeg;
+	bool inlineHeavy = false;
+	if (valid && !light) {                                    // warp-per-vertex list; if it is full the thread does the row itself
+		const uint32_t hi = atomicAdd(tv.heavyCount, 1u);
+		if (hi < kHeavyCap) sm.heavy[hi] = (uint16_t)lv; else inlineHeavy = true;
+	}
+	const uint32_t own = valid ? (uint32_t)tv.own[lv] : 0u;
+	unsigned long long m[W];
+#pragma unroll
+	for (int w = 0; w < W; ++w) m[w] = 0ull;
+	uint32_t same = 0;
+	auto addc = [&](uint32_t idx) {
+		const uint32_t c = stage[idx];
+		asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(same) : "r"(c), "r"(own));   // same += (c == own)
+		if (W == 1) m[0] |= kPad ? bit64_clamped(c) : (1ull << c);
+		else {
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+		}
+	};
+	if (inTile) {
+		// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
+		const uint32_t so0 = tv.soff[slot >> 5], nW = (tv.soff[(slot >> 5) + 1] - so0) >> 5;
+		const uint2 * gq = bl.gidxS + so0 + lane;
+		const uint32_t degL = light ? deg : 0u;               // (only the kPad == false instance tests it)
+#ifndef MCMCB200_MASK_PF
+#define MCMCB200_MASK_PF 6
+#endif
+		constexpr uint32_t kMP = MCMCB200_MASK_PF;           // words fetched up front (covers degree <= 4*kMP in one round trip)
+		uint2 q[kMP];
+#pragma unroll
+		for (uint32_t j = 0; j < kMP; ++j) if (j < nW) q[j] = __ldcs(gq + (size_t)j * 32);
+#pragma unroll
+		for (uint32_t j = 0; j < kMP; ++j) {
+			if (j < nW) {
+				const uint32_t p0 = 4u * j;
+				if (kPad || p0 < degL) addc(q[j].x & 0xffffu);
+				if (kPad || p0 + 1u < degL) addc(q[j].x >> 16);
+				if (kPad || p0 + 2u < degL) addc(q[j].y & 0xffffu);
+				if (kPad || p0 + 3u < degL) addc(q[j].y >> 16);
+			}
+		}
+		for (uint32_t j = kMP; j < nW; j += 2) {
+			const uint2 q0 = __ldcs(gq + (size_t)j * 32);
+			uint2 q1 = make_uint2(0u, 0u);
+			const bool two = j + 1u < nW;
+			if (two) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
+			const uint32_t p0 = 4u * j;
+			if (kPad || p0 < degL) addc(q0.x & 0xffffu);
+			if (kPad || p0 + 1u < degL) addc(q0.x >> 16);
+			if (kPad || p0 + 2u < degL) addc(q0.y & 0xffffu);
+			if (kPad || p0 + 3u < degL) addc(q0.y >> 16);
+			if (kPad ? two : (p0 + 4u < degL)) addc(q1.x & 0xffffu);
+			if (kPad ? two : (p0 + 5u < degL)) addc(q1.x >> 16);
+			if (kPad ? two : (p0 + 6u < degL)) addc(q1.y & 0xffffu);
+			if (kPad ? two : (p0 + 7u < degL)) addc(q1.y >> 16);
+		}
+	}
+	if (inlineHeavy) {                                        // overflow of the heavy list: plain CSR-order indices
+		const uint32_t myBeg = a.rowptr[tv.v0 + lv];
+		for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
+		light = true;
+	}
+	if (light)
+		commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + tv.v0 + lv, tv.v0 + lv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
+		                             wq, tv.snew, tv.v0);
+	if (wq != nullptr) {                                      // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
+		__syncwarp();
+		const uint32_t qn = min(*wq->count, wq->cap);
+		if (qn >= 32u) {
+			drain_walk_queue<W, ColT, kDyn>(a, nxt, *wq, qn - 32u, 32u, sm.dist, sm.hist, lane, tv.snew, tv.v0);
+			__syncwarp();
+			if (lane == 0) *wq->count = qn - 32u;
+		}
+		__syncwarp();
+	}
+}
+
+// warp per heavy vertex (deg > kLightMaxDeg): lanes stride the row through the plain CSR-order index array
+template <int W, typename ColT, bool kDyn>
+__device__ __forceinline__ void sweep_heavy_list(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const TileView<W, ColT> & tv,
+                                                 uint32_t t, ColT * __restrict__ nxt, uint32_t nHeavy, int warp, int nWarps, int lane, float stayW,
+                                                 unsigned long long & accDirected, unsigned long long & accViol) {
+	for (uint32_t h = warp; h < nHeavy; h += nWarps) {
+		const uint32_t hv = sm.heavy[h];
+		const uint32_t hb = a.rowptr[tv.v0 + hv], hd = a.rowptr[tv.v0 + hv + 1] - hb;
+		const uint32_t gv = a.vBegin + tv.v0 + hv;
+		const uint32_t own = (uint32_t)tv.own[hv];
+		unsigned long long m[W];
+#pragma unroll
+		for (int w = 0; w < W; ++w) m[w] = 0ull;
+		uint32_t same = 0;
+		for (uint32_t i = lane; i < hd; i += 32) {
+			const uint32_t c = tv.stage[__ldg(bl.gidx + hb + i)];
+			same += (c == own);
+#pragma unroll
+			for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+		}
+#pragma unroll
+		for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
+		same = __reduce_add_sync(0xffffffffu, same);
+		if (lane == 0)
+			commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, tv.v0 + hv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
+			                             nullptr, tv.snew, tv.v0);
+	}
+}
+
+// the tile's new colours, coalesced 16-byte stores: to the local replica and -- fused exchange -- straight into every peer
+// GPU's replica over NVLink (peer pointers from cudaIpcOpenMemHandle); tiles start 256-vertex aligned
+template <typename ColT>
+__device__ __forceinline__ void write_out_tile(const SweepArgs & a, uint32_t t, ColT * nxt, const ColT * snew, uint32_t v0, uint32_t nv,
+                                               uint32_t thr, uint32_t nThr) {
+	const size_t byteOff = (size_t)(a.vBegin + v0) * sizeof(ColT);
+	const uint32_t nBytes = nv * (uint32_t)sizeof(ColT), nVec = nBytes >> 4;
+	const uint4 * src4 = reinterpret_cast<const uint4 *>(snew);
+	const uint32_t nDest = a.nPeers ? a.nPeers : 1u;
+	for (uint32_t d = 0; d < nDest; ++d) {
+		unsigned char * dst = a.nPeers ? static_cast<unsigned char *>(a.peerColors[(t + 1) & 1][d]) : reinterpret_cast<unsigned char *>(nxt);
+		uint4 * dst4 = reinterpret_cast<uint4 *>(dst + byteOff);
+		for (uint32_t i = thr; i < nVec; i += nThr) dst4[i] = src4[i];
+		for (uint32_t i = (nVec << 4) + thr; i < nBytes; i += nThr) dst[byteOff + i] = reinterpret_cast<const unsigned char *>(snew)[i];
+	}
+}
+
+template <int W, typename ColT, bool kDyn>
+__global__ void __launch_bounds__(PassB<W>::threads, PassB<W>::minCtas)
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const uint32_t nCol = a.nCol, TV = bl.TV, spt = TV >> 5;
-	uint32_t * s_slot2 = reinterpret_cast<uint32_t *>(smem_raw);                      // [kBufs][TV]
-	uint32_t * s_soff2 = s_slot2 + kBufs * TV;                                        // [kBufs][spt+4]
-	float *    s_S    = reinterpret_cast<float *>(s_soff2 + kBufs * (spt + 4));
-	float *    s_dist = s_S + ((nCol + 1 + 3) & ~3u);
-	int *      s_hist = reinterpret_cast<int *>(s_dist + ((nCol + 3) & ~3u));
-	uint32_t * s_ctl  = reinterpret_cast<uint32_t *>(s_hist + ((nCol + 3) & ~3u));
-	unsigned long long * s_red = reinterpret_cast<unsigned long long *>(s_ctl + 8);   // 64 x u64
-	uint32_t * s_qcnt = s_ctl + 8 + 128;                                              // 32 x u32
-	uint16_t * s_heavy = reinterpret_cast<uint16_t *>(s_ctl + 8 + 160);
-	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + kHeavyCap) - smem_raw);
-	off = (off + 15) & ~(size_t)15;
-	WalkQueue<W> wq{};
-	constexpr bool useQueue = W <= 2;
-	if (useQueue) {                                           // this warp's private queue
-		constexpr size_t perWarp = (size_t)kWarpQueueCap * (8 * W + 16);
-		unsigned char * qb = smem_raw + off + (size_t)(threadIdx.x >> 5) * perWarp;
-		wq.count = s_qcnt + (threadIdx.x >> 5);
-		wq.cap = kWarpQueueCap;
-		wq.mask = reinterpret_cast<unsigned long long *>(qb);
-		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)kWarpQueueCap * W);
-		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kWarpQueueCap);
-		off += (size_t)(kThreadsB / 32) * perWarp;
-	}
-	ColT * stage2 = reinterpret_cast<ColT *>(smem_raw + off);                         // [kBufs][stageCap+16]
-	const uint32_t stageStride = bl.stageCap + 16;
-	ColT * s_new = stage2 + (size_t)kBufs * stageStride;
-	ColT * s_own2 = s_new + (TV + 16);                                                // [kBufs][TV+16]
-
+	constexpr int kT = PassB<W>::threads, kCons = PassB<W>::consThreads;
+	const uint32_t nCol = a.nCol, TV = bl.TV;
+	const PassBShared<W, ColT> sm(smem_raw, nCol, TV, bl.stageCap);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	constexpr int nWarps = kThreadsB / 32;
+	constexpr int nConsWarps = kCons / 32;
+	constexpr bool useQueue = W <= 2;
+	WalkQueue<W> wq{};
+	if (useQueue && warp < nConsWarps) {                      // this warp's private queue
+		constexpr uint32_t qcap = warp_queue_cap(W);
+		constexpr size_t perWarp = (size_t)qcap * (8 * W + 16);
+		unsigned char * qb = sm.queues + (size_t)warp * perWarp;
+		wq.count = sm.qcnt + warp;
+		wq.cap = qcap;
+		wq.mask = reinterpret_cast<unsigned long long *>(qb);
+		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)qcap * W);
+		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * qcap);
+	}
 	DevState * st = a.st;
 	if (!a.countOnly && st->convergedAt >= 0) return;
 	const uint32_t t = st->sweep;
 	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
-	const ColT * __restrict__ ecol = static_cast<const ColT *>(bl.ecol);
-	constexpr bool isDyn = kDyn;
-	// the padded SELL rows need a colour value outside every palette of this instance: all-ones (255 / 65535).
-	// u8 with W == 4 covers nCol up to 256, where 255 is a real colour: that instance keeps the per-edge degree test.
-	constexpr bool kPad = !(sizeof(ColT) == 1 && W == 4);
 	const float eps = a.eps;
 	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
 
-	for (uint32_t k = tid; k < nCol; k += kThreadsB) s_hist[k] = 0;
+	for (uint32_t k = tid; k < nCol; k += kT) sm.hist[k] = 0;
 	if (tid == 0) {
-		float s = 0.0f; s_S[0] = 0.0f;
-		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
+		float s = 0.0f; sm.S[0] = 0.0f;
+		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); sm.S[k + 1] = s; }
+		sm.ctl[1] = 0u; sm.ctl[2] = 0u;                       // heavy-list counters (alternating per tile)
 	}
-	if (tid < 16) for (uint32_t b = 0; b < kBufs; ++b) stage2[(size_t)b * stageStride + bl.stageCap + tid] = (ColT)~(ColT)0;
-	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, s_dist, tid, kThreadsB);
+	if (tid < 16) for (uint32_t b = 0; b < kBufs; ++b) sm.stage2[(size_t)b * sm.stageStride + bl.stageCap + tid] = (ColT)~(ColT)0;
+	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, sm.dist, tid, kT);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
+	__syncthreads();
 
-	// Per tile everything the vertex loop needs is fetched with cp.async (LDGSTS: no registers, no dependent global
-	// loads later): the slot table (vertex | degree), the SELL slice starts, the tile's current colours and the gathered
-	// neighbour colours.  The colours sit in ecol as P short runs (one per source chunk); the static granule list says
-	// where each 4-entry granule of the stage comes from; its loads run one batch ahead of the copies they feed.
-	auto prefetch = [&](uint32_t T, uint32_t buf) {
-		const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
-		uint32_t * sl = s_slot2 + buf * TV;
-		const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
-		for (uint32_t i = tid; i < (TV >> 2); i += kThreadsB) cp_async_16(sl + 4u * i, gsl + i);
-		uint32_t * so = s_soff2 + buf * (spt + 4);
-		for (uint32_t i = tid; i <= spt; i += kThreadsB) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
-		unsigned char * ow = reinterpret_cast<unsigned char *>(s_own2 + (size_t)buf * (TV + 16));
-		const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
-		const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;      // (colour arrays are padded; tiles start 256-aligned)
-		for (uint32_t i = tid; i < n16; i += kThreadsB) cp_async_16(ow + 16u * i, cb + 16u * i);
-		const uint32_t gb = bl.tileGran[T], ng = bl.tileGran[T + 1] - gb;
-		const uint32_t * __restrict__ gs = bl.granSrc + gb;
-		ColT * stg = stage2 + (size_t)buf * stageStride;
-		constexpr uint32_t kU = 8;
-		uint32_t src[kU];
-#pragma unroll
-		for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = tid + k * kThreadsB; src[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
-		for (uint32_t i0 = tid; i0 < ng; i0 += kThreadsB * kU) {
-			uint32_t ahead[kU];
-#pragma unroll
-			for (uint32_t k = 0; k < kU; ++k) { const uint32_t i = i0 + (kU + k) * kThreadsB; ahead[k] = (i < ng) ? __ldcs(gs + i) : 0u; }
-#pragma unroll
-			for (uint32_t k = 0; k < kU; ++k) {
-				const uint32_t i = i0 + k * kThreadsB;
-				if (i < ng) {
-					if (sizeof(ColT) == 1) cp_async_4(stg + 4u * i, ecol + src[k]);
-					else cp_async_8(stg + 4u * i, ecol + src[k]);
-				}
+	if (kWS) {
+		if (warp >= nConsWarps) {
+			// ---------------- producer warps: stage tile it+1.. while the consumers sweep tile it ----------------
+			const uint32_t thr = (uint32_t)(tid - kCons), nThr = 32u * kProdWarps;
+			uint32_t it = 0;
+			for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x, ++it) {
+				const uint32_t buf = it & 1u;
+				const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
+				if (it >= 2u) named_bar_sync(kBarEmpty + (int)buf, kT);      // the consumers are done with this buffer (tile it-2)
+				stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, buf, thr, nThr);
+				cp_async_commit_wait_all();
+				named_bar_arrive(kBarFull + (int)buf, kT);
 			}
-#pragma unroll
-			for (uint32_t k = 0; k < kU; ++k) src[k] = ahead[k];
+		} else {
+			// ---------------- consumer warps ----------------
+			uint32_t it = 0;
+			for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x, ++it) {
+				const uint32_t buf = it & 1u;
+				TileView<W, ColT> tv;
+				tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
+				tv.slot = sm.slot2 + buf * TV; tv.soff = sm.soff2 + buf * sm.soffStride;
+				tv.own = sm.own2 + (size_t)buf * sm.tvStride; tv.stage = sm.stage2 + (size_t)buf * sm.stageStride;
+				tv.snew = sm.new2 + (size_t)buf * sm.tvStride; tv.heavyCount = sm.ctl + 1 + buf;
+				if (tid == 0) sm.ctl[1 + (buf ^ 1u)] = 0u;                  // next tile's heavy counter (its last readers are past the barriers below)
+				if (useQueue && lane == 0) *wq.count = 0u;
+				named_bar_sync(kBarFull + (int)buf, kT);                     // tile `it` has landed
+				for (uint32_t g = 0; g < tv.nv; g += kCons)
+					sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
+				if (useQueue) {                                              // remainder of this warp's queue
+					__syncwarp();
+					const uint32_t qn = min(*wq.count, wq.cap);
+					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, sm.dist, sm.hist, lane, tv.snew, tv.v0);
+					__syncwarp();
+				}
+				named_bar_sync(kBarCons, kCons);                             // every light vertex of the tile is committed; the heavy list is complete
+				const uint32_t nHeavy = min(*tv.heavyCount, kHeavyCap);
+				if (nHeavy) {
+					sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, nConsWarps, lane, stayW, accDirected, accViol);
+					named_bar_sync(kBarCons, kCons);
+				}
+				if (T + 2u * gridDim.x < bl.numTiles) named_bar_arrive(kBarEmpty + (int)buf, kT);   // stage / slot / own of `buf` may be refilled
+				if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kCons);
+			}
 		}
-	};
-	if (tid == 0) s_ctl[1] = 0u;
-	uint32_t T = blockIdx.x;
-	if (kPipe && T < bl.numTiles) prefetch(T, 0u);
-	for (uint32_t it = 0; T < bl.numTiles; T += gridDim.x, ++it) {
-		const uint32_t buf = kPipe ? (it & 1u) : 0u;
-		if (!kPipe) prefetch(T, 0u);
-		cp_async_commit_wait_all();
-		__syncthreads();                                          // tile `it` is staged; everybody is done with tile it-1
-		if (kPipe && T + gridDim.x < bl.numTiles) prefetch(T + gridDim.x, buf ^ 1u);
-		const uint32_t v0 = T * TV;
-		const uint32_t nv = min(TV, a.nLocal - v0);
-		const uint32_t * s_slot = s_slot2 + buf * TV;
-		const uint32_t * s_soff = s_soff2 + buf * (spt + 4);
-		const ColT * s_own = s_own2 + (size_t)buf * (TV + 16);
-		const ColT * stage = stage2 + (size_t)buf * stageStride;
-		// ---- phases 1'+2: occupancy masks straight from the stage buffer through the static SELL index words (u16: where
-		//      each edge's colour sits in this tile's stage).  Thread per vertex; a warp's 32 rows are one slice of uniform
-		//      width, so the loop below is warp-uniform and branch free. ----
-		if (useQueue && lane == 0) *wq.count = 0u;
-		__syncwarp();
-		for (uint32_t g = 0; g < nv; g += kThreadsB) {
-			const uint32_t slot = g + tid;                        // slots are degree-sorted: a warp's 32 rows have (almost) equal length
-			const bool inTile = slot < TV;                        // warp-uniform (TV is a multiple of 32)
-			const uint32_t info = inTile ? s_slot[slot] : 0xffffu;
-			const uint32_t lv = info & 0xffffu, deg = info >> 16;
-			const bool valid = lv != 0xffffu;
-			bool light = valid && deg <= (uint32_t)kLightMaxDeg;
-			bool inlineHeavy = false;
-			if (valid && !light) {                                // warp-per-vertex list; if it is full the thread does the row itself
-				const uint32_t hi = atomicAdd(&s_ctl[1], 1u);
-				if (hi < kHeavyCap) s_heavy[hi] = (uint16_t)lv; else inlineHeavy = true;
-			}
-			const uint32_t own = valid ? (uint32_t)s_own[lv] : 0u;
-			unsigned long long m[W];
-#pragma unroll
-			for (int w = 0; w < W; ++w) m[w] = 0ull;
-			uint32_t same = 0;
-			auto addc = [&](uint32_t idx) {
-				const uint32_t c = stage[idx];
-				same += (c == own);
-				if (W == 1) m[0] |= kPad ? bit64_clamped(c) : (1ull << c);
-				else {
-#pragma unroll
-					for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
-				}
-			};
-			if (inTile) {
-				// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
-				const uint32_t so0 = s_soff[slot >> 5], nW = (s_soff[(slot >> 5) + 1] - so0) >> 5;
-				const uint2 * gq = bl.gidxS + so0 + lane;
-				const uint32_t degL = light ? deg : 0u;           // (only the kPad == false instance tests it)
-#ifndef MCMCB200_MASK_PF
-#define MCMCB200_MASK_PF 6
-#endif
-				constexpr uint32_t kMP = MCMCB200_MASK_PF;       // words fetched up front (covers degree <= 4*kMP in one round trip)
-				uint2 q[kMP];
-#pragma unroll
-				for (uint32_t j = 0; j < kMP; ++j) if (j < nW) q[j] = __ldcs(gq + (size_t)j * 32);
-#pragma unroll
-				for (uint32_t j = 0; j < kMP; ++j) {
-					if (j < nW) {
-						const uint32_t p0 = 4u * j;
-						if (kPad || p0 < degL) addc(q[j].x & 0xffffu);
-						if (kPad || p0 + 1u < degL) addc(q[j].x >> 16);
-						if (kPad || p0 + 2u < degL) addc(q[j].y & 0xffffu);
-						if (kPad || p0 + 3u < degL) addc(q[j].y >> 16);
-					}
-				}
-				for (uint32_t j = kMP; j < nW; j += 2) {
-					const uint2 q0 = __ldcs(gq + (size_t)j * 32);
-					uint2 q1 = make_uint2(bl.stageCap | (bl.stageCap << 16), bl.stageCap | (bl.stageCap << 16));
-					const bool two = j + 1u < nW;
-					if (two) q1 = __ldcs(gq + (size_t)(j + 1u) * 32);
-					const uint32_t p0 = 4u * j;
-					if (kPad || p0 < degL) addc(q0.x & 0xffffu);
-					if (kPad || p0 + 1u < degL) addc(q0.x >> 16);
-					if (kPad || p0 + 2u < degL) addc(q0.y & 0xffffu);
-					if (kPad || p0 + 3u < degL) addc(q0.y >> 16);
-					if (kPad ? two : (p0 + 4u < degL)) addc(q1.x & 0xffffu);
-					if (kPad ? two : (p0 + 5u < degL)) addc(q1.x >> 16);
-					if (kPad ? two : (p0 + 6u < degL)) addc(q1.y & 0xffffu);
-					if (kPad ? two : (p0 + 7u < degL)) addc(q1.y >> 16);
-				}
-			}
-			if (inlineHeavy) {                                    // overflow of the heavy list: plain CSR-order indices
-				const uint32_t myBeg = a.rowptr[v0 + lv];
-				for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
-				light = true;
-			}
-			if (light)
-				commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + v0 + lv, v0 + lv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
-				                             useQueue ? &wq : nullptr, s_new, v0);
-			if (useQueue) {                          // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
+	} else {
+		uint32_t tbN = 0, teN = 0;
+		if (blockIdx.x < bl.numTiles) { tbN = __ldg(bl.tileBase + blockIdx.x); teN = __ldg(bl.tileBase + blockIdx.x + 1); }
+		for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x) {
+			const uint32_t tb = tbN, te = teN;
+			if (T + gridDim.x < bl.numTiles) { tbN = __ldg(bl.tileBase + T + gridDim.x); teN = __ldg(bl.tileBase + T + gridDim.x + 1); }   // next tile's range: off the critical path
+			stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, 0u, (uint32_t)tid, (uint32_t)kT);
+			cp_async_commit_wait_all();
+			__syncthreads();                                      // the tile is staged
+			TileView<W, ColT> tv;
+			tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
+			tv.slot = sm.slot2; tv.soff = sm.soff2; tv.own = sm.own2; tv.stage = sm.stage2; tv.snew = sm.new2; tv.heavyCount = sm.ctl + 1;
+			if (useQueue && lane == 0) *wq.count = 0u;
+			__syncwarp();
+			for (uint32_t g = 0; g < tv.nv; g += kT)
+				sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
+			if (useQueue) {
 				__syncwarp();
 				const uint32_t qn = min(*wq.count, wq.cap);
-				if (qn >= 32u) {
-					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, qn - 32u, 32u, s_dist, s_hist, lane, s_new, v0);
-					__syncwarp();
-					if (lane == 0) *wq.count = qn - 32u;
-				}
+				drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, sm.dist, sm.hist, lane, tv.snew, tv.v0);
 				__syncwarp();
 			}
-		}
-		if (useQueue) {                              // remainder of this warp's queue
-			__syncwarp();
-			const uint32_t qn = min(*wq.count, wq.cap);
-			drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, s_dist, s_hist, lane, s_new, v0);
-			__syncwarp();
-		}
-		__syncthreads();
-		const uint32_t nHeavy = min(s_ctl[1], kHeavyCap);
-		for (uint32_t h = warp; h < nHeavy; h += nWarps) {       // warp per heavy vertex
-			const uint32_t hv = s_heavy[h];
-			const uint32_t hb = a.rowptr[v0 + hv], hd = a.rowptr[v0 + hv + 1] - hb;
-			const uint32_t gv = a.vBegin + v0 + hv;
-			const uint32_t own = (uint32_t)s_own[hv];
-			unsigned long long m[W];
-#pragma unroll
-			for (int w = 0; w < W; ++w) m[w] = 0ull;
-			uint32_t same = 0;
-			for (uint32_t i = lane; i < hd; i += 32) {
-				const uint32_t c = stage[__ldg(bl.gidx + hb + i)];
-				same += (c == own);
-#pragma unroll
-				for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
-			}
-#pragma unroll
-			for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
-			same = __reduce_add_sync(0xffffffffu, same);
-			if (lane == 0)
-				commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, v0 + hv, own, m, same, s_S, s_dist, s_hist, stayW, accDirected, accViol,
-				                             nullptr, s_new, v0);
-		}
-		__syncthreads();                                          // the tile is finished: everybody has read the heavy list, s_new is complete
-		if (tid == 0) s_ctl[1] = 0u;
-		if (!a.countOnly) {
-			// write the tile's new colours out, coalesced 16-byte stores: to the local replica and -- fused exchange -- straight
-			// into every peer GPU's replica over NVLink (peer pointers from cudaIpcOpenMemHandle); tiles start 256-vertex aligned
-			const size_t byteOff = (size_t)(a.vBegin + v0) * sizeof(ColT);
-			const uint32_t nBytes = nv * (uint32_t)sizeof(ColT), nVec = nBytes >> 4;
-			const uint4 * src4 = reinterpret_cast<const uint4 *>(s_new);
-			const uint32_t nDest = a.nPeers ? a.nPeers : 1u;
-			for (uint32_t d = 0; d < nDest; ++d) {
-				unsigned char * dst = a.nPeers ? static_cast<unsigned char *>(a.peerColors[(t + 1) & 1][d]) : reinterpret_cast<unsigned char *>(nxt);
-				uint4 * dst4 = reinterpret_cast<uint4 *>(dst + byteOff);
-				for (uint32_t i = tid; i < nVec; i += kThreadsB) dst4[i] = src4[i];
-				for (uint32_t i = (nVec << 4) + tid; i < nBytes; i += kThreadsB) dst[byteOff + i] = reinterpret_cast<const unsigned char *>(s_new)[i];
-			}
+			__syncthreads();
+			const uint32_t nHeavy = min(sm.ctl[1], kHeavyCap);
+			sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
+			__syncthreads();                                      // the tile is finished: everybody has read the heavy list, s_new is complete
+			if (tid == 0) sm.ctl[1] = 0u;
+			if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kT);
 		}
 	}
-	cp_async_commit_wait_all();
 
 	// ---- epilogue (same protocol as sweep_kernel) ----
 	accDirected = warp_reduce_add64(accDirected);
 	accViol = warp_reduce_add64(accViol);
 	__syncthreads();
-	if (lane == 0) { s_red[warp] = accDirected; s_red[32 + warp] = accViol; }
+	if (lane == 0) { sm.red[warp] = accDirected; sm.red[32 + warp] = accViol; }
 	__syncthreads();
 	if (tid == 0) {
 		unsigned long long d = 0, vv = 0;
-		for (int w = 0; w < nWarps; ++w) { d += s_red[w]; vv += s_red[32 + w]; }
+		for (int w = 0; w < kT / 32; ++w) { d += sm.red[w]; vv += sm.red[32 + w]; }
 		if (d) atomicAdd(a.scratch + 0, d);
 		if (vv) atomicAdd(a.scratch + 1, vv);
 	}
 	if (!a.countOnly) {
-		for (uint32_t k = tid; k < nCol; k += kThreadsB) {
-			const int dlt = s_hist[k];
+		for (uint32_t k = tid; k < nCol; k += kT) {
+			const int dlt = sm.hist[k];
 			if (dlt) atomicAdd(a.scratch + 2 + k, (unsigned long long)(long long)dlt);
 		}
 	}
 	if (a.fuseFinalize) {
 		__threadfence();
 		__syncthreads();
-		if (tid == 0) s_ctl[2] = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+		if (tid == 0) sm.ctl[3] = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
 		__syncthreads();
-		if (s_ctl[2]) {
+		if (sm.ctl[3]) {
 			__threadfence();
 			finalize_sweep_device(a);
 		}

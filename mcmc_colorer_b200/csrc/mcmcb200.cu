@@ -78,8 +78,8 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 		const BlockedArgs b = make_blocked_args(h->bl);
 		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, h->stream>>>(a, b);
 		h->launches++;
-		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, kThreadsB, h->bl.smemB, h->stream>>>(a, b);
-		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, kThreadsB, h->bl.smemB, h->stream>>>(a, b);
+		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		return cudaGetLastError();
 	}
 	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) sweep_kernel<W, ColT, true><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
@@ -93,14 +93,19 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	BlockedLayout & L = h->bl;
 	L.smemA = (size_t)kChunkV * sizeof(ColT);
 	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.P, L.TV, L.stageCap, (int)sizeof(ColT), W);
-	cudaError_t e = cudaFuncSetAttribute(blocked_gather_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemA);
+	int dev = 0, optin = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	if (e != cudaSuccess) return e;
+	if (L.smemA > (size_t)optin || L.smemB > (size_t)optin) { L.valid = false; return cudaSuccess; }   // does not fit: direct kernel
+	e = cudaFuncSetAttribute(blocked_gather_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemA);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
 	if (e != cudaSuccess) return e;
 	int oa = 0, ob0 = 0, ob1 = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, blocked_gather_kernel<ColT>, kThreadsA, L.smemA);
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob0, blocked_sweep_kernel<W, ColT, false>, kThreadsB, L.smemB);
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob1, blocked_sweep_kernel<W, ColT, true>, kThreadsB, L.smemB);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob0, blocked_sweep_kernel<W, ColT, false>, PassB<W>::threads, L.smemB);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob1, blocked_sweep_kernel<W, ColT, true>, PassB<W>::threads, L.smemB);
 	if (e != cudaSuccess) return e;
 	const int ob = ob0 < ob1 ? ob0 : ob1;
 	if (oa < 1 || ob < 1) { L.valid = false; return cudaSuccess; }
@@ -333,6 +338,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes,
 			                                     h->stream, &h->launches);
 			if (e == cudaSuccess && h->bl.valid) e = configure_blocked(h);
+			if (e == cudaSuccess && !h->bl.valid) free_blocked_layout(h->bl);
 			if (e != cudaSuccess) return fail(cuda_fail(e, "build_blocked_layout", __LINE__));
 			if (forceBlocked && !h->bl.valid) return fail(MCMCB200_EUNSUPPORTED);
 		}

@@ -373,7 +373,6 @@ sweep_kernel(const SweepArgs a) {
 	const ColT * __restrict__ cur = a.colorsOverride ? static_cast<const ColT *>(a.colorsOverride)
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
-	constexpr bool isDyn = kDyn;
 	const float eps = a.eps;
 	// "stay" weight 1 - (nCol-1)*eps, two roundings like the reference's x86 build (coloringMCMC_CPU.cpp:406,474)
 	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
