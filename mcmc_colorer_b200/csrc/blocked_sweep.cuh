@@ -309,39 +309,26 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 			have = b;
 			__syncthreads();
 		}
-		// runs are padded to 4 entries, so an item may start 4 (mod 8): scalar head up to the next multiple of 8,
-		// then 8 entries (2 granules) per thread per step: one 128-bit load of local ids, one 64-bit load of the two granule
-		// destinations, 8 shared-memory gathers, two packed stores into the tile-major ecol
-		const uint32_t body = min(end, (beg + 7u) & ~7u);
-		if (beg + tid < body) { const uint32_t j = beg + tid; ecol[4u * (size_t)bl.granDst[j >> 2] + (j & 3u)] = chunk[bl.srcLocal[j]]; }
-		constexpr uint32_t kU = 4;
-		for (uint32_t i0 = body + 8u * tid; i0 < end; i0 += 8u * kThreadsA * kU) {
-			uint4 ids[kU];
-			uint2 gd[kU];
+		// one 4-entry granule per lane per step: a warp reads 256 contiguous bytes of local ids and 128 of destinations, and
+		// its store covers whole 32-byte sectors wherever a run spans them (full-sector first touches need no fill in L2)
+		constexpr uint32_t kU = 8;
+		const uint32_t g0 = beg >> 2, g1 = end >> 2;           // runs are padded to 4 entries: items are whole granules
+		for (uint32_t j0 = g0 + tid; j0 < g1; j0 += kThreadsA * kU) {
+			uint2 ids[kU];
+			uint32_t gd[kU];
 #pragma unroll
 			for (uint32_t k = 0; k < kU; ++k) {
-				const uint32_t i = i0 + k * 8u * kThreadsA;
-				if (i + 8u <= end) {
-					ids[k] = __ldcs(reinterpret_cast<const uint4 *>(bl.srcLocal + i));
-					gd[k] = __ldcs(reinterpret_cast<const uint2 *>(bl.granDst + (i >> 2)));
-				}
+				const uint32_t j = j0 + k * kThreadsA;
+				if (j < g1) { ids[k] = __ldcs(reinterpret_cast<const uint2 *>(bl.srcLocal) + j); gd[k] = __ldcs(bl.granDst + j); }
 			}
 #pragma unroll
 			for (uint32_t k = 0; k < kU; ++k) {
-				const uint32_t i = i0 + k * 8u * kThreadsA;
-				if (i + 8u <= end) {
-					const uint4 d = ids[k];
+				const uint32_t j = j0 + k * kThreadsA;
+				if (j < g1) {
+					const uint2 d = ids[k];
 					const uint32_t c0 = chunk[d.x & 0xffffu], c1 = chunk[d.x >> 16], c2 = chunk[d.y & 0xffffu], c3 = chunk[d.y >> 16];
-					const uint32_t c4 = chunk[d.z & 0xffffu], c5 = chunk[d.z >> 16], c6 = chunk[d.w & 0xffffu], c7 = chunk[d.w >> 16];
-					if (sizeof(ColT) == 1) {
-						st_ecol32(ecol + 4u * (size_t)gd[k].x, c0 | (c1 << 8) | (c2 << 16) | (c3 << 24), pol);
-						st_ecol32(ecol + 4u * (size_t)gd[k].y, c4 | (c5 << 8) | (c6 << 16) | (c7 << 24), pol);
-					} else {
-						st_ecol64(ecol + 4u * (size_t)gd[k].x, make_uint2(c0 | (c1 << 16), c2 | (c3 << 16)), pol);
-						st_ecol64(ecol + 4u * (size_t)gd[k].y, make_uint2(c4 | (c5 << 16), c6 | (c7 << 16)), pol);
-					}
-				} else if (i < end) {
-					for (uint32_t j = i; j < end; ++j) ecol[4u * (size_t)bl.granDst[j >> 2] + (j & 3u)] = chunk[bl.srcLocal[j]];
+					if (sizeof(ColT) == 1) st_ecol32(ecol + 4u * (size_t)gd[k], c0 | (c1 << 8) | (c2 << 16) | (c3 << 24), pol);
+					else st_ecol64(ecol + 4u * (size_t)gd[k], make_uint2(c0 | (c1 << 16), c2 | (c3 << 16)), pol);
 				}
 			}
 		}
