@@ -10,7 +10,7 @@ namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
 	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.slotInfo); cudaFree(L.sliceOff);
-	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items);
+	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items); cudaFree(L.sync);
 	L = BlockedLayout{};
 }
 
@@ -40,7 +40,6 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	uint32_t * d_v32[2] = {nullptr, nullptr};
 	uint32_t * d_words = nullptr, * d_runStart = nullptr, * d_stageOff = nullptr;
 	uint32_t numSlices = 0, sellTotal = 0;
-	std::vector<uint32_t> bs, items;
 
 	BLK_CU(cudaMalloc(&d_tmp, 2 * sizeof(uint32_t)));
 	// ---- tile size: the largest multiple of 256 vertices whose worst tile (edges + run padding) fits the stage ----
@@ -167,32 +166,25 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	blk_sell_fill_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, L.gidx, TV, numSlices, L.sliceOff, stageCap, L.gidxS); (*launches)++;
 	BLK_CU(cudaMalloc(&L.slotInfo, sizeof(uint32_t) * (size_t)numTiles * TV));
 	blk_sell_slotinfo_kernel<<<(unsigned)(((size_t)numTiles * TV + 255) / 256), 256, 0, stream>>>(d_rowptr, L.order, TV, numTiles, L.slotInfo); (*launches)++;
-	// ---- pass-A work items: (bucket, begin, end), at most kItemEntries entries each ----
-	BLK_CU(cudaMalloc(&d_bs, sizeof(uint32_t) * ((size_t)P + 1)));
-	blk_bucket_starts_kernel<<<(P + 1 + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.totalPadded, d_bs); (*launches)++;
-	bs.resize((size_t)P + 1);
-	BLK_CU(cudaMemcpyAsync(bs.data(), d_bs, sizeof(uint32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, stream));
+	// ---- pass-A work items: (part, bucket) -> entry range; parts are stretches of tiles so that "part p finished" means the
+	//      stage images of its tiles are complete (pass B follows pass A part by part) ----
 	BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	BLK_CU(cudaStreamSynchronize(stream));
 	if (h2[0] + 16u > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
-	// part-major order: item k of every bucket before item k+1 of any.  Pass A hands the items out round robin, so the CTAs
-	// running at the same time hold neighbouring source chunks and write the same stretch of tiles: the runs of (T, b) and
-	// (T, b+1) are adjacent in the tile-major ecol, and their shared boundary sectors meet in L2 instead of going to DRAM half
-	// written (measured: 3.7 GB of read-for-fill traffic per sweep with the bucket-major order).
 	{
-		uint32_t maxParts = 0;
-		for (uint32_t b = 0; b < P; ++b) maxParts = std::max<uint32_t>(maxParts, (bs[b + 1] - bs[b] + kItemEntries - 1) / kItemEntries);
-		for (uint32_t part = 0; part < maxParts; ++part)
-			for (uint32_t b = 0; b < P; ++b) {
-				const uint64_t beg = (uint64_t)bs[b] + (uint64_t)part * kItemEntries;
-				if (beg >= bs[b + 1]) continue;
-				items.push_back(b); items.push_back((uint32_t)beg); items.push_back((uint32_t)std::min<uint64_t>(bs[b + 1], beg + kItemEntries));
-			}
+		// about kItemEntries entries per item: parts = entries per bucket / kItemEntries, at least 1, at most 64
+		const uint64_t perBucket = ((uint64_t)L.totalPadded + P - 1) / P;
+		uint32_t np = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (perBucket + kItemEntries - 1) / kItemEntries));
+		np = std::min<uint32_t>(np, numTiles);
+		L.tilesPerPart = (numTiles + np - 1) / np;
+		L.numParts = (numTiles + L.tilesPerPart - 1) / L.tilesPerPart;
+		L.numItems = L.numParts * P;
+		BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * 3 * (size_t)L.numItems));
+		blk_items_kernel<<<(L.numItems + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.tilesPerPart, L.numParts, L.totalPadded, L.items); (*launches)++;
+		BLK_CU(cudaMalloc(&L.sync, sizeof(uint32_t) * (2 + (size_t)L.numParts)));
+		BLK_CU(cudaMemsetAsync(L.sync, 0, sizeof(uint32_t) * (2 + (size_t)L.numParts), stream));
+		BLK_CU(cudaStreamSynchronize(stream));
 	}
-	L.numItems = (uint32_t)(items.size() / 3);
-	BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * std::max<size_t>(items.size(), 3)));
-	BLK_CU(cudaMemcpyAsync(L.items, items.data(), sizeof(uint32_t) * items.size(), cudaMemcpyHostToDevice, stream));
-	BLK_CU(cudaStreamSynchronize(stream));
 	cudaFree(L.order); L.order = nullptr;                        // construction only
 	L.P = P; L.TV = TV; L.numTiles = numTiles; L.stageCap = stageCap;
 	L.valid = true;
@@ -211,7 +203,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granDst = L.granDst; b.tileBase = L.tileBase;
-	b.items = L.items; b.numItems = L.numItems;
+	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilesPerPart = L.tilesPerPart; b.sync = L.sync;
 	return b;
 }
 

@@ -27,7 +27,10 @@ namespace mcmcb200 {
 
 constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
-constexpr int      kThreadsA  = 256;
+#ifndef MCMCB200_THREADS_A
+#define MCMCB200_THREADS_A 256
+#endif
+constexpr int      kThreadsA  = MCMCB200_THREADS_A;
 // pass-B geometry.  MCMCB200_WS = 0 (default): every thread stages, single buffer, 1024 / MCMCB200_THREADS_B CTAs per SM
 // (two CTAs hide each other's staging).  MCMCB200_WS = 1: warp-specialised -- kProdWarps producer warps stage tile k+1 with
 // cp.async into the other half of the double buffers while the consumer warps sweep tile k; one CTA of MCMCB200_THREADS_B
@@ -36,10 +39,10 @@ constexpr int      kThreadsA  = 256;
 #define MCMCB200_WS 0
 #endif
 #ifndef MCMCB200_THREADS_B
-#define MCMCB200_THREADS_B (MCMCB200_WS ? 1024 : 512)
+#define MCMCB200_THREADS_B (MCMCB200_WS ? 1024 : 384)
 #endif
 #ifndef MCMCB200_MIN_CTAS_B
-#define MCMCB200_MIN_CTAS_B (MCMCB200_WS ? 1 : (1024 / MCMCB200_THREADS_B))
+#define MCMCB200_MIN_CTAS_B (MCMCB200_WS ? 1 : 2)      /* 2 x 384 threads leave registers and shared memory for a pass-A CTA on the same SM */
 #endif
 #ifndef MCMCB200_PROD_WARPS
 #define MCMCB200_PROD_WARPS 2
@@ -56,7 +59,8 @@ constexpr int      kProdWarps = kWS ? MCMCB200_PROD_WARPS : 0;
 // palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads
 template <int W> struct PassB { static constexpr int threads = (W <= 2) ? MCMCB200_THREADS_B : 512;
                                 static constexpr int consThreads = threads - 32 * kProdWarps;
-                                static constexpr int minCtas = (W <= 2) ? MCMCB200_MIN_CTAS_B : 1; };
+                                static constexpr int minCtas = (W <= 2) ? MCMCB200_MIN_CTAS_B : 1;
+                                static constexpr int maxRegs = (W <= 2) ? 64 : 128; };   // 64: 2 x 384 pass-B threads + 256 pass-A threads fill the register file exactly
 #ifndef MCMCB200_ITEM_BITS
 #define MCMCB200_ITEM_BITS 17
 #endif
@@ -78,8 +82,11 @@ struct BlockedLayout {
 	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
 	uint32_t * granDst = nullptr;    // [totalPadded/4]  chunk-major granule (4 entries of srcLocal) -> its granule in the tile-major ecol
 	uint32_t * tileBase = nullptr;   // [numTiles+1]     first entry of each tile's stage image in ecol
-	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries)
+	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries); item = part * P + bucket (empty items allowed)
 	uint32_t  numItems = 0;
+	uint32_t  numParts = 0;          // pass A works through the tiles in numParts stretches of tilesPerPart tiles ...
+	uint32_t  tilesPerPart = 0;
+	uint32_t * sync = nullptr;       // [2 + numParts]: next item, next tile, buckets finished per part  (... and pass B follows behind)
 	size_t    smemA = 0, smemB = 0;
 	int       gridA = 0, gridB = 0;
 };
@@ -95,7 +102,8 @@ struct BlockedArgs {
 	const uint32_t * granDst;
 	const uint32_t * tileBase;
 	const uint32_t * items;
-	uint32_t numItems;
+	uint32_t numItems, numParts, tilesPerPart;
+	uint32_t * sync;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -180,10 +188,17 @@ __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * 
 	gidx[e] = (uint16_t)((scanT[(size_t)T * P] & alignMask) + stageOff[(size_t)T * (P + 1) + b] + r);
 }
 
-__global__ void blk_bucket_starts_kernel(const uint32_t * gs, uint32_t P, uint32_t numTiles, uint32_t total, uint32_t * bs) {
-	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b < P) bs[b] = gs[(size_t)b * numTiles];
-	if (b == P) bs[P] = total;
+// pass-A work items: item (part p, bucket b) = the entries of bucket b that belong to tiles [p*K, (p+1)*K)
+__global__ void blk_items_kernel(const uint32_t * gs /* [P][numTiles] */, uint32_t P, uint32_t numTiles, uint32_t K, uint32_t numParts,
+                                 uint32_t total, uint32_t * items) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= numParts * P) return;
+	const uint32_t p = i / P, b = i % P;
+	const uint32_t t0 = p * K, t1 = t0 + K;
+	const uint32_t nextBucket = (b + 1 < P) ? gs[(size_t)(b + 1) * numTiles] : total;
+	items[3 * (size_t)i] = b;
+	items[3 * (size_t)i + 1] = gs[(size_t)b * numTiles + t0];
+	items[3 * (size_t)i + 2] = (t1 < numTiles) ? gs[(size_t)b * numTiles + t1] : nextBucket;
 }
 
 // granDst: pass A reads srcLocal chunk-major (so that the gather runs out of one 64 Ki-colour chunk in shared memory) and
@@ -293,14 +308,23 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ ecol = static_cast<ColT *>(bl.ecol);
 	const int tid = threadIdx.x;
-	// items round robin in part-major order (see build_blocked_layout): concurrently running CTAs write neighbouring runs
+	// Items are handed out dynamically in part-major order (item = part * P + bucket): the CTAs running at the same time hold
+	// neighbouring source chunks and write the same stretch of tiles, so the runs of (T, b) and (T, b+1) -- adjacent in the
+	// tile-major ecol -- meet in L2 instead of going to DRAM half written (3.7 GB of read-for-fill traffic per sweep otherwise).
+	// Every finished item bumps its part's counter; pass B, running concurrently on another stream, starts a tile as soon as
+	// all P buckets of the tile's part are in.
 	unsigned long long pol = 0ull;
 	if (MCMCB200_ST_LAST) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	__shared__ uint32_t s_item;
 	uint32_t have = 0xffffffffu;
-	for (uint32_t it = blockIdx.x; it < bl.numItems; it += gridDim.x) {
+	for (;;) {
+		__syncthreads();                                      // everybody is done with the previous item (and its chunk)
+		if (tid == 0) s_item = atomicAdd(bl.sync + 0, 1u);
+		__syncthreads();
+		const uint32_t it = s_item;
+		if (it >= bl.numItems) break;
 		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
-		if (b != have) {
-			__syncthreads();
+		if (b != have && beg < end) {
 			// the colour buffers are padded by 64 Ki entries, so a whole chunk is always readable
 			const uint4 * src = reinterpret_cast<const uint4 *>(cur + (size_t)b * kChunkV);
 			uint4 * dst = reinterpret_cast<uint4 *>(chunk);
@@ -332,6 +356,9 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 				}
 			}
 		}
+		__threadfence();                                      // this item's ecol stores are visible device-wide ...
+		__syncthreads();
+		if (tid == 0) atomicAdd(bl.sync + 2 + it / bl.P, 1u);  // ... before its part is reported
 	}
 }
 
@@ -378,7 +405,21 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // named barriers (ids 1..15; id 0 is __syncthreads): producer/consumer hand-over of the tile buffers
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;   // kBarFull + buf, kBarEmpty + buf
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;
+// pass B waits until pass A has delivered all P buckets of the tile's part.  Bounded: if the producer kernel never shows up
+// (launch failure) the sweep flags an error instead of hanging the device.
+__device__ __forceinline__ void wait_part_ready(const BlockedArgs & bl, uint32_t T, DevState * st) {
+	const uint32_t * flag = bl.sync + 2 + T / bl.tilesPerPart;
+	uint32_t v;
+	long long t0 = 0;
+	for (uint32_t spins = 0;; ++spins) {
+		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if (v >= bl.P) return;
+		if (spins == 0) t0 = clock64();
+		else if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000ll) { st->errorFlag = 2; return; }   // ~3 s
+		__nanosleep(100);
+	}
+}   // kBarFull + buf, kBarEmpty + buf
 // 1 << c with PTX semantics: shift amounts >= 64 give 0 (the dummy colour sets no bit)
 __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 	unsigned long long r;
@@ -590,7 +631,7 @@ __device__ __forceinline__ void write_out_tile(const SweepArgs & a, uint32_t t, 
 }
 
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(PassB<W>::threads, PassB<W>::minCtas)
+__global__ void __launch_bounds__(PassB<W>::threads) __maxnreg__(PassB<W>::maxRegs)
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int kT = PassB<W>::threads, kCons = PassB<W>::consThreads;
@@ -638,6 +679,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x, ++it) {
 				const uint32_t buf = it & 1u;
 				const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
+				wait_part_ready(bl, T, st);
 				if (it >= 2u) named_bar_sync(kBarEmpty + (int)buf, kT);      // the consumers are done with this buffer (tile it-2)
 				stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, buf, thr, nThr);
 				cp_async_commit_wait_all();
@@ -675,11 +717,16 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 			}
 		}
 	} else {
-		uint32_t tbN = 0, teN = 0;
-		if (blockIdx.x < bl.numTiles) { tbN = __ldg(bl.tileBase + blockIdx.x); teN = __ldg(bl.tileBase + blockIdx.x + 1); }
-		for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x) {
-			const uint32_t tb = tbN, te = teN;
-			if (T + gridDim.x < bl.numTiles) { tbN = __ldg(bl.tileBase + T + gridDim.x); teN = __ldg(bl.tileBase + T + gridDim.x + 1); }   // next tile's range: off the critical path
+		for (;;) {
+			if (tid == 0) {                                       // tiles in ascending order: the order pass A completes them in
+				const uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
+				if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
+				sm.ctl[4] = Tn;
+			}
+			__syncthreads();
+			const uint32_t T = sm.ctl[4];
+			if (T >= bl.numTiles) break;
+			const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
 			stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, 0u, (uint32_t)tid, (uint32_t)kT);
 			cp_async_commit_wait_all();
 			__syncthreads();                                      // the tile is staged

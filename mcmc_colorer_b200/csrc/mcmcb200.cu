@@ -60,6 +60,9 @@ struct mcmcb200_handle {
 	int gridBlocks = 0;
 	size_t smemBytes = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t streamA = nullptr;      // pass A of the blocked sweep runs here, concurrently with pass B on `stream`
+	cudaEvent_t evFork = nullptr, evReset = nullptr;
+	bool overlap = false;                // both passes co-resident on every SM (decided in configure_blocked)
 	bool timed = false;
 	uint64_t launches = 0;
 	uint64_t z = 0;
@@ -76,8 +79,23 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 	if (h->bl.valid) {
 		// source-blocked path: pass A (gather through shared memory) + pass B (tile sweep); two launches per sweep
 		const BlockedArgs b = make_blocked_args(h->bl);
-		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, h->stream>>>(a, b);
+		const size_t syncBytes = sizeof(uint32_t) * (2 + (size_t)h->bl.numParts);
+		cudaStream_t sA = h->stream;
+		cudaError_t e = cudaSuccess;
+		if (h->overlap) {
+			// pass A on its own stream, after everything queued on the main stream so far (previous sweep, colour exchange);
+			// pass B on the main stream follows A part by part through the counters in bl.sync
+			sA = h->streamA;
+			e = cudaEventRecord(h->evFork, h->stream);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(sA, h->evFork, 0);
+		}
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->bl.sync, 0, syncBytes, sA);
+		if (e == cudaSuccess && h->overlap) e = cudaEventRecord(h->evReset, sA);   // B may start as soon as the counters are clean
+		if (e != cudaSuccess) return e;
+		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b);
 		h->launches++;
+		if ((e = cudaGetLastError()) != cudaSuccess) return e;    // (pass B must not be launched without its producer)
+		if (h->overlap && (e = cudaStreamWaitEvent(h->stream, h->evReset, 0)) != cudaSuccess) return e;
 		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		return cudaGetLastError();
@@ -107,10 +125,36 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob0, blocked_sweep_kernel<W, ColT, false>, PassB<W>::threads, L.smemB);
 	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob1, blocked_sweep_kernel<W, ColT, true>, PassB<W>::threads, L.smemB);
 	if (e != cudaSuccess) return e;
-	const int ob = ob0 < ob1 ? ob0 : ob1;
+	int ob = ob0 < ob1 ? ob0 : ob1;
 	if (oa < 1 || ob < 1) { L.valid = false; return cudaSuccess; }
-	L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(oa * h->smCount)));
+	if (const char * env = getenv("MCMCB200_B_PER_SM")) ob = std::max(1, std::min(ob, atoi(env)));   // experiments
+	if (const char * env = getenv("MCMCB200_A_PER_SM")) oa = std::max(1, std::min(oa, atoi(env)));
 	L.gridB = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numTiles, (uint32_t)(ob * h->smCount)));
+	// Overlap: pass A is DRAM bound, pass B issue bound.  With `ob` pass-B CTAs resident an SM must still have room
+	// (shared memory, registers, threads) for at least one pass-A CTA -- otherwise a grid of waiting B CTAs could keep A out.
+	cudaFuncAttributes fa{}, fb{};
+	e = cudaFuncGetAttributes(&fa, blocked_gather_kernel<ColT>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&fb, blocked_sweep_kernel<W, ColT, false>);
+	if (e != cudaSuccess) return e;
+	int smemSM = 0, regsSM = 0, thrSM = 0;
+	cudaDeviceGetAttribute(&smemSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+	cudaDeviceGetAttribute(&regsSM, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+	cudaDeviceGetAttribute(&thrSM, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+	auto regsOf = [](int perThread, int threads) { return ((perThread + 7) / 8 * 8) * ((threads + 31) / 32 * 32); };
+	const long freeSmem = (long)smemSM - (long)ob * (long)(L.smemB + 1024);
+	const long freeRegs = (long)regsSM - (long)ob * regsOf(fb.numRegs, PassB<W>::threads);
+	const long freeThr = (long)thrSM - (long)ob * PassB<W>::threads;
+	long aFit = std::min<long>(freeSmem / (long)(L.smemA + 1024), std::min<long>(freeRegs / regsOf(fa.numRegs, kThreadsA), freeThr / kThreadsA));
+	h->overlap = aFit >= 1 && getenv("MCMCB200_NO_OVERLAP") == nullptr;
+	if (h->overlap) {
+		L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(std::min<long>(aFit, oa) * h->smCount)));
+		if (!h->streamA) e = cudaStreamCreateWithFlags(&h->streamA, cudaStreamNonBlocking);
+		if (e == cudaSuccess && !h->evFork) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
+		if (e == cudaSuccess && !h->evReset) e = cudaEventCreateWithFlags(&h->evReset, cudaEventDisableTiming);
+		if (e != cudaSuccess) return e;
+	} else {
+		L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(oa * h->smCount)));
+	}
 	return cudaSuccess;
 }
 
@@ -333,7 +377,10 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
 		const bool want = forceBlocked || (!forceDirect && nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18));
 		if (want) {
-			uint32_t capBytes = 65504;   // colour bytes a tile stages in shared memory (u8: just under the u16 index limit; 2 CTAs/SM)
+			// colour bytes a tile stages in shared memory.  Large partitions: 44 KiB, so that two pass-B CTAs and one pass-A CTA
+			// (64 KiB chunk) share an SM and the two passes overlap; smaller ones (fill/drain of the A->B pipeline would eat the
+			// gain; measured on config 5): the largest stage the 16-bit positions allow, passes back to back
+			uint32_t capBytes = nnzLocal >= (1ull << 29) ? 45056u : 65504u;
 			if (const char * env = getenv("MCMCB200_STAGE_CAP_BYTES")) capBytes = (uint32_t)strtoul(env, nullptr, 10);
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes,
 			                                     h->stream, &h->launches);
@@ -411,6 +458,9 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	for (uint32_t q = 0; q < h->nPeers; ++q)
 		if (q != h->myPeerIndex) for (int b = 0; b < 2; ++b) if (h->peerColors[b][q]) cudaIpcCloseMemHandle(h->peerColors[b][q]);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
+	if (h->streamA) { cudaStreamSynchronize(h->streamA); cudaStreamDestroy(h->streamA); }
+	if (h->evFork) cudaEventDestroy(h->evFork);
+	if (h->evReset) cudaEventDestroy(h->evReset);
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);
 	if (h->stream) cudaStreamDestroy(h->stream);
@@ -541,6 +591,10 @@ int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
 	CU(cudaSetDevice(h->device));
 	DevState s;
 	int rc = read_state(h, &s); if (rc) return rc;
+	if (s.errorFlag == 2u) {                                  // wait_part_ready gave up: pass B never saw pass A's output
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "blocked sweep: pass B timed out waiting for pass A (sweep %u)", s.sweep);
+		return MCMCB200_ECUDA;
+	}
 	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
 	if (s.countsSweep != s.sweep) {
 		if (split) {

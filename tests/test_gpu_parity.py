@@ -26,7 +26,10 @@ def mc():
     return m
 
 
-KERNELS = ["direct", "blocked"]   # single-pass direct-gather kernel / source-blocked two-pass kernel
+# single-pass direct-gather kernel / source-blocked two-pass kernel with pass A and pass B overlapped on two streams (default
+# stage) / the same with the largest stage, which leaves no room for a pass-A CTA next to pass B: the two passes run one after
+# the other
+KERNELS = ["direct", "blocked", "blocked-serial"]
 
 
 def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence=0, tailcut=False, max_rip=250,
@@ -35,14 +38,22 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
                                 seed=seed, tailcut=tailcut, maxRip=max_rip)
     # replay=True: keep sweeping past convergence, like the oracle's tape harness does
     flags = mc.FLAG_NO_EARLY_STOP if replay else 0
-    flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED}[kernel]
+    flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED, "blocked-serial": mc.FLAG_FORCE_BLOCKED}[kernel]
+    saved = os.environ.get("MCMCB200_STAGE_CAP_BYTES")
+    if kernel == "blocked-serial":
+        os.environ["MCMCB200_STAGE_CAP_BYTES"] = "65504"
     try:
         return mc.Chain(cumul, neighs, prm, device=0, flags=flags)
     except mc.McmcError as e:
         from mcmc_colorer_b200 import capi
-        if kernel == "blocked" and e.code == capi.EUNSUPPORTED:
+        if kernel in ("blocked", "blocked-serial") and e.code == capi.EUNSUPPORTED:
             pytest.skip("a 256-vertex tile of this graph does not fit the blocked kernel's stage (by design: direct kernel)")
         raise
+    finally:
+        if saved is None:
+            os.environ.pop("MCMCB200_STAGE_CAP_BYTES", None)
+        else:
+            os.environ["MCMCB200_STAGE_CAP_BYTES"] = saved
 
 
 @pytest.fixture(scope="module")
