@@ -1,22 +1,30 @@
-// Source-blocked two-pass sweep ("v2").  Same result as sweep_kernel, different data movement.
+// Source-blocked two-pass sweep.  Same result as sweep_kernel, different data movement.
 //
 // Why: the direct kernel issues one random 1-byte gather per directed edge into the L2-resident colour array; ncu
 // shows it pinned on the L1->L2 request port (one 32-byte sector request per cycle per SM, profiles/r01a_*).  Here
-// every random access is served from SHARED memory and every byte of DRAM traffic is a streaming read or write:
+// every random access is served from SHARED memory and DRAM sees streams:
 //
 //   static, once per graph (build_blocked_layout):
 //     the directed edges (v <- u) are binned by SOURCE chunk b = u / 65536 (stable radix sort, so inside a bucket
 //     they stay in CSR order, i.e. grouped by destination tile T and vertex); each (bucket, tile) run is padded to
-//     4 entries.  srcLocal[pos] = u % 65536 (u16, bucket-major) and gidx[e] (u16, CSR order) = where edge e's colour
-//     lands in its tile's stage buffer.
-//   pass A  blocked_gather_kernel: per bucket, load the 64 Ki colours of the chunk into shared memory (coalesced),
-//     stream srcLocal (2 B/edge), gather from shared memory, write ecol (1 B/edge) sequentially.
-//   pass B  blocked_sweep_kernel: per destination tile, copy the tile's P short runs of ecol into a stage buffer in
-//     shared memory, permute them into CSR order through gidx (2 B/edge, shared-memory gather), then run exactly the
-//     phases 2-3 of the direct kernel (masks, proposal, draw, colour write, counters, device-side finalize).
+//     4 entries.  srcLocal[pos] = u % 65536 (u16, bucket-major).  ecol, the gathered neighbour colours, is TILE-major:
+//     tile T's stage image (its P runs back to back) is one contiguous block; granDst maps every 4-entry granule of
+//     srcLocal to its place in ecol.  gidxS (SELL-32, u16) says where each edge's colour sits in its tile's image.
+//   pass A  blocked_gather_kernel: per (part, bucket) item, load the 64 Ki colours of the chunk into shared memory
+//     (coalesced), stream srcLocal (2 B/edge) + granDst (1 B/edge), gather from shared memory, scatter 4-byte granules
+//     into ecol (1 B/edge; neighbouring runs are written by concurrently running CTAs and meet in L2).
+//   pass B  blocked_sweep_kernel: per destination tile, ONE contiguous cp.async block copy of the tile's image into
+//     shared memory (+ slot table, slice starts, own colours), occupancy masks through the SELL index words
+//     (2 B/edge, shared-memory gather), then exactly phases 2-3 of the direct kernel (proposal, draw, colour write,
+//     counters, device-side finalize).
+//   overlap: pass A is DRAM bound, pass B instruction-issue bound.  They run concurrently on two streams; pass A
+//     works through the tiles in `parts` and counts finished buckets per part, pass B takes tiles in the same order and
+//     starts a tile when its part is complete (bl.sync).  Two 384-thread pass-B CTAs and one 256-thread pass-A CTA fill
+//     an SM's registers exactly.
 //
-// DRAM bytes per directed edge: 2 + 1 (pass A) + 2 + 1*a (pass B; a = sector amplification of the short runs), versus
-// the 8 of the reference layout -- the static preprocessing shrinks the index stream from u32 to 2 x u16.
+// DRAM bytes per directed edge: 2 + 1 + 1 (pass A) + 2 + 1 (pass B) = 7 versus the 8 of the reference layout, all of it
+// streaming; measured per sweep on config 3: pass A 6.9 GB read (incl. ~1 GB partial-sector fills) + 2.1 GB written,
+// pass B 5.7 GB read + 0.1 GB written (profiles/r01g_*).
 #pragma once
 #include <cub/cub.cuh>
 #include <type_traits>
@@ -31,21 +39,13 @@ constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vert
 #define MCMCB200_THREADS_A 256
 #endif
 constexpr int      kThreadsA  = MCMCB200_THREADS_A;
-// pass-B geometry.  MCMCB200_WS = 0 (default): every thread stages, single buffer, 1024 / MCMCB200_THREADS_B CTAs per SM
-// (two CTAs hide each other's staging).  MCMCB200_WS = 1: warp-specialised -- kProdWarps producer warps stage tile k+1 with
-// cp.async into the other half of the double buffers while the consumer warps sweep tile k; one CTA of MCMCB200_THREADS_B
-// threads per SM.  Measured on B200 (config 3): 4.59 vs 4.80 ms/sweep, so the plain variant is the default.
-#ifndef MCMCB200_WS
-#define MCMCB200_WS 0
-#endif
+// pass-B geometry: MCMCB200_THREADS_B threads per CTA, two CTAs per SM for the narrow-palette instances.  Every thread helps
+// staging a tile (one contiguous cp.async block), the second CTA of the SM hides the wait.  Together with the 64-register cap
+// below, 2 x 384 pass-B threads leave exactly the registers, threads and shared memory one 256-thread pass-A CTA needs on the
+// same SM -- that is what lets the two passes overlap.  (A warp-specialised producer/consumer variant with double-buffered
+// tiles was measured slower -- 4.80 vs 4.59 ms per sweep on config 3 -- and removed.)
 #ifndef MCMCB200_THREADS_B
-#define MCMCB200_THREADS_B (MCMCB200_WS ? 1024 : 384)
-#endif
-#ifndef MCMCB200_MIN_CTAS_B
-#define MCMCB200_MIN_CTAS_B (MCMCB200_WS ? 1 : 2)      /* 2 x 384 threads leave registers and shared memory for a pass-A CTA on the same SM */
-#endif
-#ifndef MCMCB200_PROD_WARPS
-#define MCMCB200_PROD_WARPS 2
+#define MCMCB200_THREADS_B 384
 #endif
 #ifndef MCMCB200_QUEUE_CAP
 #define MCMCB200_QUEUE_CAP 48
@@ -53,14 +53,9 @@ constexpr int      kThreadsA  = MCMCB200_THREADS_A;
 #ifndef MCMCB200_HEAVY_CAP
 #define MCMCB200_HEAVY_CAP 1024
 #endif
-constexpr bool kWS = MCMCB200_WS != 0;
-constexpr uint32_t kBufs = kWS ? 2u : 1u;
-constexpr int      kProdWarps = kWS ? MCMCB200_PROD_WARPS : 0;
-// palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads
+// palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads, one CTA
 template <int W> struct PassB { static constexpr int threads = (W <= 2) ? MCMCB200_THREADS_B : 512;
-                                static constexpr int consThreads = threads - 32 * kProdWarps;
-                                static constexpr int minCtas = (W <= 2) ? MCMCB200_MIN_CTAS_B : 1;
-                                static constexpr int maxRegs = (W <= 2) ? 64 : 128; };   // 64: 2 x 384 pass-B threads + 256 pass-A threads fill the register file exactly
+                                static constexpr int maxRegs = (W <= 2) ? 64 : 128; };
 #ifndef MCMCB200_ITEM_BITS
 #define MCMCB200_ITEM_BITS 17
 #endif
@@ -371,10 +366,10 @@ constexpr uint32_t kHeavyCap = MCMCB200_HEAVY_CAP;        // warp-per-vertex wor
 
 __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	(void)P;
-	const int consWarps = (((W <= 2) ? MCMCB200_THREADS_B : 512) >> 5) - kProdWarps;
+	const int warps = ((W <= 2) ? MCMCB200_THREADS_B : 512) >> 5;
 	size_t b = 0;
-	b += kBufs * sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16
-	b += kBufs * sizeof(uint32_t) * (size_t)((TV >> 5) + 4); // s_soff: SELL slice starts of the tile
+	b += sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16
+	b += sizeof(uint32_t) * (size_t)((TV >> 5) + 4); // s_soff: SELL slice starts of the tile
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist (DYNAMIC) / free-colour weight table (UNIFORM)
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
@@ -383,10 +378,10 @@ __host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P
 	b += sizeof(uint32_t) * 32;                            // per-warp queue counters
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
-	if (W <= 2) b += (size_t)consWarps * warp_queue_cap(W) * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += kBufs * (size_t)colBytes * (stageCap + 16);       // stage; [stageCap, +16) = dummy colour
-	b += kBufs * (size_t)colBytes * (size_t)(TV + 16);     // s_new: the tile's new colours, written out coalesced (local + peers)
-	b += kBufs * (size_t)colBytes * (size_t)(TV + 16);     // s_own: the tile's current colours
+	if (W <= 2) b += (size_t)warps * warp_queue_cap(W) * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
+	b += (size_t)colBytes * (stageCap + 16);               // stage; [stageCap, +16) = dummy colour
+	b += (size_t)colBytes * (size_t)(TV + 16);             // s_new: the tile's new colours, written out coalesced (local + peers)
+	b += (size_t)colBytes * (size_t)(TV + 16);             // s_own: the tile's current colours
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -402,10 +397,6 @@ __device__ __forceinline__ void cp_async_16(void * smem, const void * gmem) {
 __device__ __forceinline__ void cp_async_commit_wait_all() {
 	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-// named barriers (ids 1..15; id 0 is __syncthreads): producer/consumer hand-over of the tile buffers
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;
 // pass B waits until pass A has delivered all P buckets of the tile's part.  Bounded: if the producer kernel never shows up
 // (launch failure) the sweep flags an error instead of hanging the device.
 __device__ __forceinline__ void wait_part_ready(const BlockedArgs & bl, uint32_t T, DevState * st) {
@@ -419,7 +410,7 @@ __device__ __forceinline__ void wait_part_ready(const BlockedArgs & bl, uint32_t
 		else if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000ll) { st->errorFlag = 2; return; }   // ~3 s
 		__nanosleep(100);
 	}
-}   // kBarFull + buf, kBarEmpty + buf
+}
 // 1 << c with PTX semantics: shift amounts >= 64 give 0 (the dummy colour sets no bit)
 __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 	unsigned long long r;
@@ -436,9 +427,9 @@ struct PassBShared {
 	__device__ __forceinline__ PassBShared(unsigned char * raw, uint32_t nCol, uint32_t TV, uint32_t stageCap) {
 		const uint32_t spt = TV >> 5;
 		slot2 = reinterpret_cast<uint32_t *>(raw);
-		soff2 = slot2 + kBufs * TV;
+		soff2 = slot2 + TV;
 		soffStride = spt + 4;
-		S = reinterpret_cast<float *>(soff2 + kBufs * soffStride);
+		S = reinterpret_cast<float *>(soff2 + soffStride);
 		dist = S + ((nCol + 1 + 3) & ~3u);
 		hist = reinterpret_cast<int *>(dist + ((nCol + 3) & ~3u));
 		ctl = reinterpret_cast<uint32_t *>(hist + ((nCol + 3) & ~3u));
@@ -448,28 +439,28 @@ struct PassBShared {
 		size_t off = (size_t)(reinterpret_cast<unsigned char *>(heavy + kHeavyCap) - raw);
 		off = (off + 15) & ~(size_t)15;
 		queues = raw + off;
-		if (W <= 2) off += (size_t)(PassB<W>::consThreads / 32) * warp_queue_cap(W) * (8 * W + 16);
+		if (W <= 2) off += (size_t)(PassB<W>::threads / 32) * warp_queue_cap(W) * (8 * W + 16);
 		stage2 = reinterpret_cast<ColT *>(raw + off);
 		stageStride = stageCap + 16;
 		tvStride = TV + 16;
-		new2 = stage2 + (size_t)kBufs * stageStride;
-		own2 = new2 + (size_t)kBufs * tvStride;
+		new2 = stage2 + stageStride;
+		own2 = new2 + tvStride;
 	}
 };
 
-// cp.async copies of everything tile T needs into buffer `buf`, spread over nThr threads (this thread = thr; whole warps).
+// cp.async copies of everything tile T needs, spread over nThr threads (this thread = thr).
 // tb, te = the tile's entry range in ecol (bl.tileBase[T], bl.tileBase[T+1]).
 template <int W, typename ColT>
 __device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const ColT * cur,
-                                           uint32_t T, uint32_t tb, uint32_t te, uint32_t buf, uint32_t thr, uint32_t nThr) {
+                                           uint32_t T, uint32_t tb, uint32_t te, uint32_t thr, uint32_t nThr) {
 	const uint32_t TV = bl.TV, spt = TV >> 5;
 	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
-	uint32_t * sl = sm.slot2 + buf * TV;
+	uint32_t * sl = sm.slot2;
 	const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
 	for (uint32_t i = thr; i < (TV >> 2); i += nThr) cp_async_16(sl + 4u * i, gsl + i);
-	uint32_t * so = sm.soff2 + buf * sm.soffStride;
+	uint32_t * so = sm.soff2;
 	for (uint32_t i = thr; i <= spt; i += nThr) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
-	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.own2 + (size_t)buf * sm.tvStride);
+	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.own2);
 	const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
 	const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;          // (colour arrays are padded; tiles start 256-aligned)
 	for (uint32_t i = thr; i < n16; i += nThr) cp_async_16(ow + 16u * i, cb + 16u * i);
@@ -479,7 +470,7 @@ __device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArg
 	const uint32_t a0 = tb & ~(alignE - 1u);
 	const uint32_t nC = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) >> 4;
 	const unsigned char * eb = reinterpret_cast<const unsigned char *>(static_cast<const ColT *>(bl.ecol) + a0);
-	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stage2 + (size_t)buf * sm.stageStride);
+	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stage2);
 	for (uint32_t i = thr; i < nC; i += nThr) cp_async_16(stg + 16u * i, eb + 16u * i);
 }
 
@@ -634,14 +625,13 @@ template <int W, typename ColT, bool kDyn>
 __global__ void __launch_bounds__(PassB<W>::threads) __maxnreg__(PassB<W>::maxRegs)
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	constexpr int kT = PassB<W>::threads, kCons = PassB<W>::consThreads;
+	constexpr int kT = PassB<W>::threads;
 	const uint32_t nCol = a.nCol, TV = bl.TV;
 	const PassBShared<W, ColT> sm(smem_raw, nCol, TV, bl.stageCap);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	constexpr int nConsWarps = kCons / 32;
 	constexpr bool useQueue = W <= 2;
 	WalkQueue<W> wq{};
-	if (useQueue && warp < nConsWarps) {                      // this warp's private queue
+	if (useQueue) {                                           // this warp's private queue
 		constexpr uint32_t qcap = warp_queue_cap(W);
 		constexpr size_t perWarp = (size_t)qcap * (8 * W + 16);
 		unsigned char * qb = sm.queues + (size_t)warp * perWarp;
@@ -664,92 +654,45 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	if (tid == 0) {
 		float s = 0.0f; sm.S[0] = 0.0f;
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); sm.S[k + 1] = s; }
-		sm.ctl[1] = 0u; sm.ctl[2] = 0u;                       // heavy-list counters (alternating per tile)
+		sm.ctl[1] = 0u;                                       // heavy-list counter
 	}
-	if (tid < 16) for (uint32_t b = 0; b < kBufs; ++b) sm.stage2[(size_t)b * sm.stageStride + bl.stageCap + tid] = (ColT)~(ColT)0;
+	if (tid < 16) sm.stage2[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
 	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, sm.dist, tid, kT);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 	__syncthreads();
 
-	if (kWS) {
-		if (warp >= nConsWarps) {
-			// ---------------- producer warps: stage tile it+1.. while the consumers sweep tile it ----------------
-			const uint32_t thr = (uint32_t)(tid - kCons), nThr = 32u * kProdWarps;
-			uint32_t it = 0;
-			for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x, ++it) {
-				const uint32_t buf = it & 1u;
-				const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
-				wait_part_ready(bl, T, st);
-				if (it >= 2u) named_bar_sync(kBarEmpty + (int)buf, kT);      // the consumers are done with this buffer (tile it-2)
-				stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, buf, thr, nThr);
-				cp_async_commit_wait_all();
-				named_bar_arrive(kBarFull + (int)buf, kT);
-			}
-		} else {
-			// ---------------- consumer warps ----------------
-			uint32_t it = 0;
-			for (uint32_t T = blockIdx.x; T < bl.numTiles; T += gridDim.x, ++it) {
-				const uint32_t buf = it & 1u;
-				TileView<W, ColT> tv;
-				tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
-				tv.slot = sm.slot2 + buf * TV; tv.soff = sm.soff2 + buf * sm.soffStride;
-				tv.own = sm.own2 + (size_t)buf * sm.tvStride; tv.stage = sm.stage2 + (size_t)buf * sm.stageStride;
-				tv.snew = sm.new2 + (size_t)buf * sm.tvStride; tv.heavyCount = sm.ctl + 1 + buf;
-				if (tid == 0) sm.ctl[1 + (buf ^ 1u)] = 0u;                  // next tile's heavy counter (its last readers are past the barriers below)
-				if (useQueue && lane == 0) *wq.count = 0u;
-				named_bar_sync(kBarFull + (int)buf, kT);                     // tile `it` has landed
-				for (uint32_t g = 0; g < tv.nv; g += kCons)
-					sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
-				if (useQueue) {                                              // remainder of this warp's queue
-					__syncwarp();
-					const uint32_t qn = min(*wq.count, wq.cap);
-					drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, sm.dist, sm.hist, lane, tv.snew, tv.v0);
-					__syncwarp();
-				}
-				named_bar_sync(kBarCons, kCons);                             // every light vertex of the tile is committed; the heavy list is complete
-				const uint32_t nHeavy = min(*tv.heavyCount, kHeavyCap);
-				if (nHeavy) {
-					sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, nConsWarps, lane, stayW, accDirected, accViol);
-					named_bar_sync(kBarCons, kCons);
-				}
-				if (T + 2u * gridDim.x < bl.numTiles) named_bar_arrive(kBarEmpty + (int)buf, kT);   // stage / slot / own of `buf` may be refilled
-				if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kCons);
-			}
+	for (;;) {
+		if (tid == 0) {                                       // tiles in ascending order: the order pass A completes them in
+			const uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
+			if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
+			sm.ctl[4] = Tn;
 		}
-	} else {
-		for (;;) {
-			if (tid == 0) {                                       // tiles in ascending order: the order pass A completes them in
-				const uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
-				if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
-				sm.ctl[4] = Tn;
-			}
-			__syncthreads();
-			const uint32_t T = sm.ctl[4];
-			if (T >= bl.numTiles) break;
-			const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
-			stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, 0u, (uint32_t)tid, (uint32_t)kT);
-			cp_async_commit_wait_all();
-			__syncthreads();                                      // the tile is staged
-			TileView<W, ColT> tv;
-			tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
-			tv.slot = sm.slot2; tv.soff = sm.soff2; tv.own = sm.own2; tv.stage = sm.stage2; tv.snew = sm.new2; tv.heavyCount = sm.ctl + 1;
-			if (useQueue && lane == 0) *wq.count = 0u;
+		__syncthreads();
+		const uint32_t T = sm.ctl[4];
+		if (T >= bl.numTiles) break;
+		const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
+		stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, (uint32_t)tid, (uint32_t)kT);
+		cp_async_commit_wait_all();
+		__syncthreads();                                      // the tile is staged
+		TileView<W, ColT> tv;
+		tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
+		tv.slot = sm.slot2; tv.soff = sm.soff2; tv.own = sm.own2; tv.stage = sm.stage2; tv.snew = sm.new2; tv.heavyCount = sm.ctl + 1;
+		if (useQueue && lane == 0) *wq.count = 0u;
+		__syncwarp();
+		for (uint32_t g = 0; g < tv.nv; g += kT)
+			sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
+		if (useQueue) {
 			__syncwarp();
-			for (uint32_t g = 0; g < tv.nv; g += kT)
-				sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
-			if (useQueue) {
-				__syncwarp();
-				const uint32_t qn = min(*wq.count, wq.cap);
-				drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, sm.dist, sm.hist, lane, tv.snew, tv.v0);
-				__syncwarp();
-			}
-			__syncthreads();
-			const uint32_t nHeavy = min(sm.ctl[1], kHeavyCap);
-			sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
-			__syncthreads();                                      // the tile is finished: everybody has read the heavy list, s_new is complete
-			if (tid == 0) sm.ctl[1] = 0u;
-			if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kT);
+			const uint32_t qn = min(*wq.count, wq.cap);
+			drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, sm.dist, sm.hist, lane, tv.snew, tv.v0);
+			__syncwarp();
 		}
+		__syncthreads();
+		const uint32_t nHeavy = min(sm.ctl[1], kHeavyCap);
+		sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
+		__syncthreads();                                      // the tile is finished: everybody has read the heavy list, s_new is complete
+		if (tid == 0) sm.ctl[1] = 0u;
+		if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kT);
 	}
 
 	// ---- epilogue (same protocol as sweep_kernel) ----
