@@ -10,7 +10,7 @@ namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
 	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.slotInfo); cudaFree(L.sliceOff);
-	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items); cudaFree(L.sync);
+	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items); cudaFree(L.sync); cudaFree(L.tilePart);
 	L = BlockedLayout{};
 }
 
@@ -172,15 +172,39 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaStreamSynchronize(stream));
 	if (h2[0] + 16u > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
 	{
-		// about kItemEntries entries per item: parts = entries per bucket / kItemEntries, at least 1, at most 64
+		// about kItemEntries entries per item in the body: K = tiles per body part.  The first and the last K tiles are cut
+		// into K/4, K/4, K/2 (and mirrored): pass B can start after 1/4 of a part and has only 1/4 of a part left when pass A ends.
 		const uint64_t perBucket = ((uint64_t)L.totalPadded + P - 1) / P;
-		uint32_t np = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (perBucket + kItemEntries - 1) / kItemEntries));
-		np = std::min<uint32_t>(np, numTiles);
-		L.tilesPerPart = (numTiles + np - 1) / np;
-		L.numParts = (numTiles + L.tilesPerPart - 1) / L.tilesPerPart;
+		const uint32_t np0 = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (perBucket + kItemEntries - 1) / kItemEntries));
+		const uint32_t K = std::max<uint32_t>(1u, (numTiles + np0 - 1) / np0);
+		std::vector<uint32_t> ps;
+		ps.push_back(0);
+		auto cut = [&](uint32_t len) { const uint32_t nx = std::min<uint64_t>(numTiles, (uint64_t)ps.back() + std::max<uint32_t>(1u, len)); if (nx > ps.back()) ps.push_back(nx); };
+		if (numTiles >= 4u * K && K >= 8u) {
+			cut(K / 4); cut(K / 4); cut(K - 2 * (K / 4));
+			while (numTiles - ps.back() > 2u * K) cut(K);
+			const uint32_t rest = numTiles - ps.back();               // in (K, 2K]
+			const uint32_t tail = std::min(K, rest);
+			if (rest > tail) cut(rest - tail);
+			cut(tail - 2 * (tail / 4)); cut(tail / 4); cut(tail / 4);
+			if (ps.back() < numTiles) ps.push_back(numTiles);
+		} else {
+			while (ps.back() < numTiles) cut(K);
+		}
+		L.numParts = (uint32_t)ps.size() - 1;
+		if (L.numParts > 255u) goto done;
 		L.numItems = L.numParts * P;
-		BLK_CU(cudaMalloc(&L.items, sizeof(uint32_t) * 3 * (size_t)L.numItems));
-		blk_items_kernel<<<(L.numItems + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, L.tilesPerPart, L.numParts, L.totalPadded, L.items); (*launches)++;
+		uint32_t * d_ps = nullptr;
+		BLK_CU(cudaMalloc(&d_ps, sizeof(uint32_t) * ps.size()));
+		err = cudaMemcpyAsync(d_ps, ps.data(), sizeof(uint32_t) * ps.size(), cudaMemcpyHostToDevice, stream);
+		if (err == cudaSuccess) err = cudaMalloc(&L.items, sizeof(uint32_t) * 3 * (size_t)L.numItems);
+		if (err == cudaSuccess) err = cudaMalloc(&L.tilePart, numTiles);
+		if (err == cudaSuccess) {
+			blk_items_kernel<<<(L.numItems + 255) / 256, 256, 0, stream>>>(d_gs, P, numTiles, d_ps, L.numParts, L.totalPadded, L.items, L.tilePart); (*launches)++;
+			err = cudaStreamSynchronize(stream);
+		}
+		cudaFree(d_ps);
+		if (err != cudaSuccess) goto done;
 		BLK_CU(cudaMalloc(&L.sync, sizeof(uint32_t) * (2 + (size_t)L.numParts)));
 		BLK_CU(cudaMemsetAsync(L.sync, 0, sizeof(uint32_t) * (2 + (size_t)L.numParts), stream));
 		BLK_CU(cudaStreamSynchronize(stream));
@@ -203,7 +227,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granDst = L.granDst; b.tileBase = L.tileBase;
-	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilesPerPart = L.tilesPerPart; b.sync = L.sync;
+	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilePart = L.tilePart; b.sync = L.sync;
 	return b;
 }
 

@@ -79,8 +79,8 @@ struct BlockedLayout {
 	uint32_t * tileBase = nullptr;   // [numTiles+1]     first entry of each tile's stage image in ecol
 	uint32_t * items = nullptr;      // [numItems][3] = bucket, begin, end (entries); item = part * P + bucket (empty items allowed)
 	uint32_t  numItems = 0;
-	uint32_t  numParts = 0;          // pass A works through the tiles in numParts stretches of tilesPerPart tiles ...
-	uint32_t  tilesPerPart = 0;
+	uint32_t  numParts = 0;          // pass A works through the tiles in numParts stretches (short ones first and last) ...
+	uint8_t * tilePart = nullptr;    // [numTiles] part of each tile
 	uint32_t * sync = nullptr;       // [2 + numParts]: next item, next tile, buckets finished per part  (... and pass B follows behind)
 	size_t    smemA = 0, smemB = 0;
 	int       gridA = 0, gridB = 0;
@@ -97,7 +97,8 @@ struct BlockedArgs {
 	const uint32_t * granDst;
 	const uint32_t * tileBase;
 	const uint32_t * items;
-	uint32_t numItems, numParts, tilesPerPart;
+	uint32_t numItems, numParts;
+	const uint8_t * tilePart;
 	uint32_t * sync;
 };
 
@@ -183,17 +184,18 @@ __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * 
 	gidx[e] = (uint16_t)((scanT[(size_t)T * P] & alignMask) + stageOff[(size_t)T * (P + 1) + b] + r);
 }
 
-// pass-A work items: item (part p, bucket b) = the entries of bucket b that belong to tiles [p*K, (p+1)*K)
-__global__ void blk_items_kernel(const uint32_t * gs /* [P][numTiles] */, uint32_t P, uint32_t numTiles, uint32_t K, uint32_t numParts,
-                                 uint32_t total, uint32_t * items) {
+// pass-A work items: item (part p, bucket b) = the entries of bucket b that belong to tiles [partStart[p], partStart[p+1])
+__global__ void blk_items_kernel(const uint32_t * gs /* [P][numTiles] */, uint32_t P, uint32_t numTiles, const uint32_t * partStart, uint32_t numParts,
+                                 uint32_t total, uint32_t * items, uint8_t * tilePart) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= numParts * P) return;
 	const uint32_t p = i / P, b = i % P;
-	const uint32_t t0 = p * K, t1 = t0 + K;
+	const uint32_t t0 = partStart[p], t1 = partStart[p + 1];
 	const uint32_t nextBucket = (b + 1 < P) ? gs[(size_t)(b + 1) * numTiles] : total;
 	items[3 * (size_t)i] = b;
 	items[3 * (size_t)i + 1] = gs[(size_t)b * numTiles + t0];
 	items[3 * (size_t)i + 2] = (t1 < numTiles) ? gs[(size_t)b * numTiles + t1] : nextBucket;
+	if (b == 0) for (uint32_t T = t0; T < t1; ++T) tilePart[T] = (uint8_t)p;
 }
 
 // granDst: pass A reads srcLocal chunk-major (so that the gather runs out of one 64 Ki-colour chunk in shared memory) and
@@ -400,7 +402,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // pass B waits until pass A has delivered all P buckets of the tile's part.  Bounded: if the producer kernel never shows up
 // (launch failure) the sweep flags an error instead of hanging the device.
 __device__ __forceinline__ void wait_part_ready(const BlockedArgs & bl, uint32_t T, DevState * st) {
-	const uint32_t * flag = bl.sync + 2 + T / bl.tilesPerPart;
+	const uint32_t * flag = bl.sync + 2 + bl.tilePart[T];
 	uint32_t v;
 	long long t0 = 0;
 	for (uint32_t spins = 0;; ++spins) {

@@ -26,10 +26,11 @@ def mc():
     return m
 
 
-# single-pass direct-gather kernel / source-blocked two-pass kernel with pass A and pass B overlapped on two streams (default
-# stage) / the same with the largest stage, which leaves no room for a pass-A CTA next to pass B: the two passes run one after
-# the other
+# single-pass direct-gather kernel / source-blocked two-pass kernel with the 44 KiB stage of the large-graph configuration: pass A
+# and pass B overlap on two streams / the same with the largest stage (the default for graphs of this size), which leaves no
+# room for a pass-A CTA next to pass B: the two passes run one after the other
 KERNELS = ["direct", "blocked", "blocked-serial"]
+STAGE_CAP = {"blocked": "45056", "blocked-serial": "65504"}
 
 
 def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence=0, tailcut=False, max_rip=250,
@@ -40,8 +41,8 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
     flags = mc.FLAG_NO_EARLY_STOP if replay else 0
     flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED, "blocked-serial": mc.FLAG_FORCE_BLOCKED}[kernel]
     saved = os.environ.get("MCMCB200_STAGE_CAP_BYTES")
-    if kernel == "blocked-serial":
-        os.environ["MCMCB200_STAGE_CAP_BYTES"] = "65504"
+    if kernel in STAGE_CAP:
+        os.environ["MCMCB200_STAGE_CAP_BYTES"] = STAGE_CAP[kernel]
     try:
         return mc.Chain(cumul, neighs, prm, device=0, flags=flags)
     except mc.McmcError as e:
