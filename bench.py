@@ -39,7 +39,7 @@ WORKLOADS = {
 }
 GRAPH_SEED = 42
 # measured DRAM traffic of one sweep (ncu dram__bytes_read.sum + dram__bytes_write.sum, both launches), bytes
-TRAFFIC = {"c3": 13.04e9}
+TRAFFIC = {"c3": 13.56e9}
 CHAIN_SEED = 1
 
 
@@ -307,9 +307,13 @@ def main():
         "edges_per_sec": value * nnz / n,
         "chain_ms_per_sweep": chain_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC.get(args.workload), "traffic_source": "profiles/r01c_ncu_blocked_kernels_c3.md (ncu dram__bytes, one sweep)" if args.workload in TRAFFIC else None,
+                     "traffic": TRAFFIC.get(args.workload), "traffic_source": "profiles/r01g_ncu_blocked_kernels_c3.md (ncu dram__bytes of both kernels of one sweep)" if args.workload in TRAFFIC else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "one sweep = blocked_gather_kernel + blocked_sweep_kernel (source-blocked path; sweep_kernel on small graphs)",
+                     "kernel": {"direct": "sweep_kernel (one launch per sweep)",
+                                "blocked": "blocked_gather_kernel then blocked_sweep_kernel (two launches per sweep)",
+                                "blocked-overlapped": "blocked_gather_kernel || blocked_sweep_kernel (two launches per sweep, concurrent on two "
+                                                      "streams; launch_ms = CUDA events around the pair)"}[ch.kernel_mode()],
+                     "kernel_mode": ch.kernel_mode(),
                      "launch_ms": ms_per_step, "launches_per_sweep": int(launches_per_step)},
         "e2e": {"value": e2e_value, "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n,
                 "d2h_bytes_per_step": 4 * n + 40 + 8 * nCol, "ms_per_step": 1e3 * float(np.mean(e2e_t))},

@@ -179,6 +179,14 @@ int mcmcb200_synchronize(mcmcb200_handle * h);
 int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms);
 /* number of kernels this library launched on behalf of the handle so far */
 int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches);
+/* Which sweep implementation this handle runs (chosen at create from the graph size, the palette and the FORCE flags):
+ * MCMCB200_MODE_DIRECT  one launch per sweep, neighbour colours gathered from the L2-resident colour array;
+ * MCMCB200_MODE_BLOCKED two launches per sweep (source-blocked gather, tile sweep), one after the other;
+ * MCMCB200_MODE_BLOCKED_OVERLAPPED the same two kernels running concurrently on two streams. */
+#define MCMCB200_MODE_DIRECT 0
+#define MCMCB200_MODE_BLOCKED 1
+#define MCMCB200_MODE_BLOCKED_OVERLAPPED 2
+int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode);
 
 const char * mcmcb200_strerror(int code);
 const char * mcmcb200_last_cuda_error(void);

@@ -228,6 +228,14 @@ class Chain:
         capi.check(self.L.mcmcb200_last_sweep_ms(self.h, C.byref(ms)), "mcmcb200_last_sweep_ms")
         return ms.value
 
+    KERNEL_MODES = ("direct", "blocked", "blocked-overlapped")
+
+    def kernel_mode(self):
+        """which sweep implementation the handle runs: 'direct', 'blocked' or 'blocked-overlapped' (mcmcb200_kernel_mode)"""
+        m = C.c_int(0)
+        capi.check(self.L.mcmcb200_kernel_mode(self.h, C.byref(m)), "mcmcb200_kernel_mode")
+        return self.KERNEL_MODES[m.value]
+
     def launch_count(self):
         k = C.c_uint64()
         capi.check(self.L.mcmcb200_launch_count(self.h, C.byref(k)), "mcmcb200_launch_count")

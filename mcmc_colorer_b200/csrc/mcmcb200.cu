@@ -886,6 +886,12 @@ int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms) {
 	return MCMCB200_OK;
 }
 
+int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode) {
+	if (!h || !mode) return MCMCB200_EINVAL;
+	*mode = !h->bl.valid ? MCMCB200_MODE_DIRECT : h->overlap ? MCMCB200_MODE_BLOCKED_OVERLAPPED : MCMCB200_MODE_BLOCKED;
+	return MCMCB200_OK;
+}
+
 int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches) {
 	if (!h || !launches) return MCMCB200_EINVAL;
 	*launches = h->launches;

@@ -283,7 +283,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
             "edges_per_sec": value * nnz / n,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "mcmcb200::sweep_kernel (+ NCCL exchange)"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "per rank: " + eng.chain.kernel_mode() + " sweep + colour exchange + counter all-reduce"},
             "e2e": {"value": n / float(np.mean(e2e)), "unit": "vertex-updates/s", "h2d_bytes_per_step": 4 * n,
                     "d2h_bytes_per_step": 4 * n + 40 * world, "ms_per_step": 1e3 * float(np.mean(e2e)),
                     "note": "each rank moves only the colours of the vertices it owns"},

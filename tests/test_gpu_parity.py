@@ -44,7 +44,11 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
     if kernel in STAGE_CAP:
         os.environ["MCMCB200_STAGE_CAP_BYTES"] = STAGE_CAP[kernel]
     try:
-        return mc.Chain(cumul, neighs, prm, device=0, flags=flags)
+        ch = mc.Chain(cumul, neighs, prm, device=0, flags=flags)
+        want = {"direct": ("direct",), "blocked": ("blocked-overlapped", "blocked") if nCol > 128 else ("blocked-overlapped",),
+                "blocked-serial": ("blocked",)}.get(kernel)
+        assert want is None or ch.kernel_mode() in want, (kernel, ch.kernel_mode())
+        return ch
     except mc.McmcError as e:
         from mcmc_colorer_b200 import capi
         if kernel in ("blocked", "blocked-serial") and e.code == capi.EUNSUPPORTED:
