@@ -91,6 +91,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(uint32_t nCol, int W, int col
 	b += sizeof(uint16_t) * kTileV;                       // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	b += sizeof(unsigned long long) * (size_t)kTileV * W; // s_mask
+	if (W > 2) b += sizeof(uint32_t) * (kThreads / 32) * 2 * W;   // s_wm: per-warp mask accumulators of the wide palettes
 	b += (size_t)colBytes * (kCapEdges + 16);             // s_col
 	return (b + 15) & ~(size_t)15;
 }
@@ -363,7 +364,19 @@ sweep_kernel(const SweepArgs a) {
 	size_t off = (size_t)(reinterpret_cast<unsigned char *>(s_heavy + kTileV) - smem_raw);
 	off = (off + 15) & ~(size_t)15;
 	unsigned long long * s_mask = reinterpret_cast<unsigned long long *>(smem_raw + off);
-	ColT * s_col = reinterpret_cast<ColT *>(s_mask + (size_t)kTileV * W);
+	// Wide palettes (W > 2, more than 128 colours): a mask held in W 64-bit registers costs a W-way select per edge (~5 W
+	// instructions), so the masks are accumulated in shared memory instead: per-thread rows of 32-bit words, transposed
+	// (word w of slot s at s_m32[w * kTileV + s]: conflict free), and per-warp accumulators s_wm for the rows a warp or the
+	// whole CTA shares (one shared-memory atomic OR per edge).
+	constexpr bool kWide = W > 2;
+	uint32_t * s_m32 = reinterpret_cast<uint32_t *>(s_mask);
+	uint32_t * s_wm = reinterpret_cast<uint32_t *>(s_mask + (size_t)kTileV * W);
+	ColT * s_col = reinterpret_cast<ColT *>(reinterpret_cast<unsigned char *>(s_mask + (size_t)kTileV * W) + (kWide ? sizeof(uint32_t) * (kThreads / 32) * 2 * W : 0));
+	auto load_wide_mask = [&](uint32_t slot, unsigned long long (&mm)[W]) {
+#pragma unroll
+		for (int w = 0; w < W; ++w)
+			mm[w] = (unsigned long long)s_m32[(2 * w) * kTileV + slot] | ((unsigned long long)s_m32[(2 * w + 1) * kTileV + slot] << 32);
+	};
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState * st = a.st;
@@ -421,27 +434,39 @@ sweep_kernel(const SweepArgs a) {
 				const uint32_t hubSlot = done;
 				const uint32_t hOwn = (uint32_t)cur[a.vBegin + v0 + hubSlot];
 				const uint32_t e0 = base, e1 = s_rp[hubSlot + 1];
-				if (tid < W) s_mask[(size_t)hubSlot * W + tid] = 0ull;
+				if (kWide) { if (tid < 2 * W) s_m32[tid * kTileV + hubSlot] = 0u; if (lane < 2 * W) s_wm[warp * 2 * W + lane] = 0u; }
+				else if (tid < W) s_mask[(size_t)hubSlot * W + tid] = 0ull;
 				if (tid == 0) s_same[hubSlot] = 0u;
 				__syncthreads();
 				for (uint32_t e = e0 + tid; e < e1; e += kThreads) {
 					const uint32_t c = ld_color<ColT>(cur + a.neighs[e], polLast);
 					same += (c == hOwn);
+					if (kWide) atomicOr(&s_wm[warp * 2 * W + (c >> 5)], 1u << (c & 31u));
+					else {
 #pragma unroll
-					for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+					}
 				}
+				if (kWide) {
+					__syncwarp();
+					if (lane < 2 * W) { const uint32_t r = s_wm[warp * 2 * W + lane]; if (r) atomicOr(&s_m32[lane * kTileV + hubSlot], r); }
+				} else {
 #pragma unroll
-				for (int w = 0; w < W; ++w) {
-					const unsigned long long r = warp_reduce_or64(m[w]);
-					if (lane == 0 && r) atomicOr(&s_mask[(size_t)hubSlot * W + w], r);
+					for (int w = 0; w < W; ++w) {
+						const unsigned long long r = warp_reduce_or64(m[w]);
+						if (lane == 0 && r) atomicOr(&s_mask[(size_t)hubSlot * W + w], r);
+					}
 				}
 				same = __reduce_add_sync(0xffffffffu, same);
 				if (lane == 0 && same) atomicAdd(&s_same[hubSlot], same);
 				__syncthreads();
 				mine = (uint32_t)tid == hubSlot;
 				if (mine) {
+					if (kWide) load_wide_mask(hubSlot, m);
+					else {
 #pragma unroll
-					for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)hubSlot * W + w];
+						for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)hubSlot * W + w];
+					}
 					same = s_same[hubSlot];
 				}
 				done += 1;
@@ -495,13 +520,24 @@ sweep_kernel(const SweepArgs a) {
 				const bool heavy = mine && deg > (uint32_t)kLightMaxDeg;
 				if (mine && !heavy) {
 					const ColT * p = s_col + (myBeg - ea);
-					for (uint32_t i = 0; i < deg; ++i) {
-						const uint32_t c = p[i];
-						same += (c == own);
-						if (W == 1) m[0] |= 1ull << c;
-						else {
+					if (kWide) {
 #pragma unroll
-							for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+						for (int w = 0; w < 2 * W; ++w) s_m32[w * kTileV + tid] = 0u;
+						for (uint32_t i = 0; i < deg; ++i) {
+							const uint32_t c = p[i];
+							same += (c == own);
+							s_m32[(c >> 5) * kTileV + tid] |= 1u << (c & 31u);
+						}
+						load_wide_mask((uint32_t)tid, m);
+					} else {
+						for (uint32_t i = 0; i < deg; ++i) {
+							const uint32_t c = p[i];
+							same += (c == own);
+							if (W == 1) m[0] |= 1ull << c;
+							else {
+#pragma unroll
+								for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+							}
 						}
 					}
 				} else if (heavy) {
@@ -516,28 +552,44 @@ sweep_kernel(const SweepArgs a) {
 						const uint32_t hb = s_rp[slot], hd = s_rp[slot + 1] - hb;
 						const uint32_t hOwn = (uint32_t)cur[a.vBegin + v0 + slot];
 						const ColT * p = s_col + (hb - ea);
-						unsigned long long hm[W];
-#pragma unroll
-						for (int w = 0; w < W; ++w) hm[w] = 0ull;
 						uint32_t hs = 0;
-						for (uint32_t i = lane; i < hd; i += 32) {
-							const uint32_t c = p[i];
-							hs += (c == hOwn);
+						if (kWide) {
+							if (lane < 2 * W) s_wm[warp * 2 * W + lane] = 0u;
+							__syncwarp();
+							for (uint32_t i = lane; i < hd; i += 32) {
+								const uint32_t c = p[i];
+								hs += (c == hOwn);
+								atomicOr(&s_wm[warp * 2 * W + (c >> 5)], 1u << (c & 31u));
+							}
+							__syncwarp();
+							if (lane < 2 * W) s_m32[lane * kTileV + slot] = s_wm[warp * 2 * W + lane];
+							__syncwarp();
+						} else {
+							unsigned long long hm[W];
 #pragma unroll
-							for (int w = 0; w < W; ++w) hm[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
-						}
+							for (int w = 0; w < W; ++w) hm[w] = 0ull;
+							for (uint32_t i = lane; i < hd; i += 32) {
+								const uint32_t c = p[i];
+								hs += (c == hOwn);
 #pragma unroll
-						for (int w = 0; w < W; ++w) {
-							const unsigned long long r = warp_reduce_or64(hm[w]);
-							if (lane == 0) s_mask[(size_t)slot * W + w] = r;
+								for (int w = 0; w < W; ++w) hm[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;
+							}
+#pragma unroll
+							for (int w = 0; w < W; ++w) {
+								const unsigned long long r = warp_reduce_or64(hm[w]);
+								if (lane == 0) s_mask[(size_t)slot * W + w] = r;
+							}
 						}
 						hs = __reduce_add_sync(0xffffffffu, hs);
 						if (lane == 0) s_same[slot] = hs;
 					}
 					__syncthreads();
 					if (heavy) {
+						if (kWide) load_wide_mask((uint32_t)tid, m);
+						else {
 #pragma unroll
-						for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)tid * W + w];
+							for (int w = 0; w < W; ++w) m[w] = s_mask[(size_t)tid * W + w];
+						}
 						same = s_same[tid];
 					}
 				}

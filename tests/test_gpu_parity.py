@@ -43,9 +43,11 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
     saved = os.environ.get("MCMCB200_STAGE_CAP_BYTES")
     if kernel in STAGE_CAP:
         os.environ["MCMCB200_STAGE_CAP_BYTES"] = STAGE_CAP[kernel]
+    if kernel == "blocked-serial":
+        os.environ["MCMCB200_NO_OVERLAP"] = "1"
     try:
         ch = mc.Chain(cumul, neighs, prm, device=0, flags=flags)
-        want = {"direct": ("direct",), "blocked": ("blocked-overlapped", "blocked") if nCol > 128 else ("blocked-overlapped",),
+        want = {"direct": ("direct",), "blocked": ("blocked-overlapped", "blocked") if nCol > 64 else ("blocked-overlapped",),
                 "blocked-serial": ("blocked",)}.get(kernel)
         assert want is None or ch.kernel_mode() in want, (kernel, ch.kernel_mode())
         return ch
@@ -55,6 +57,7 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
             pytest.skip("a 256-vertex tile of this graph does not fit the blocked kernel's stage (by design: direct kernel)")
         raise
     finally:
+        os.environ.pop("MCMCB200_NO_OVERLAP", None)
         if saved is None:
             os.environ.pop("MCMCB200_STAGE_CAP_BYTES", None)
         else:
