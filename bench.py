@@ -310,6 +310,7 @@ def main():
                      "traffic": TRAFFIC.get(args.workload), "traffic_source": "profiles/r01g_ncu_blocked_kernels_c3.md (ncu dram__bytes of both kernels of one sweep)" if args.workload in TRAFFIC else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": {"direct": "sweep_kernel (one launch per sweep)",
+                                "direct-binned": "binned_sweep_kernel (one launch per sweep; thread / warp / CTA rows by degree)",
                                 "blocked": "blocked_gather_kernel then blocked_sweep_kernel (two launches per sweep)",
                                 "blocked-overlapped": "blocked_gather_kernel || blocked_sweep_kernel (two launches per sweep, concurrent on two "
                                                       "streams; launch_ms = CUDA events around the pair)"}[ch.kernel_mode()],

@@ -69,6 +69,7 @@ typedef struct mcmcb200_params {
 #define MCMCB200_FLAG_NO_FUSED_FINALIZE 1u  /* caller reduces the sweep counters across ranks itself (multi-GPU) */
 #define MCMCB200_FLAG_FORCE_DIRECT      4u  /* always use the single-pass direct-gather sweep kernel */
 #define MCMCB200_FLAG_FORCE_BLOCKED     8u  /* always use the source-blocked two-pass sweep (EUNSUPPORTED if a row exceeds a tile) */
+#define MCMCB200_FLAG_FORCE_BINNED     16u  /* always use the degree-binned direct sweep (the path of large skewed graphs) */
 #define MCMCB200_FLAG_NO_EARLY_STOP     2u  /* sweeps keep advancing after C_t became proper (tape replay, benchmarking);
                                                mcmcb200_status still reports `converged` for the current colouring */
 
@@ -186,6 +187,7 @@ int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches);
 #define MCMCB200_MODE_DIRECT 0
 #define MCMCB200_MODE_BLOCKED 1
 #define MCMCB200_MODE_BLOCKED_OVERLAPPED 2
+#define MCMCB200_MODE_DIRECT_BINNED 3      /* one launch per sweep, thread / warp / CTA rows by degree (large skewed graphs) */
 int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode);
 
 const char * mcmcb200_strerror(int code);

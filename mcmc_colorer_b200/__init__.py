@@ -6,10 +6,10 @@ Layout:  csrc/  CUDA kernels + the C ABI (include/mcmcb200.h) -> libmcmcb200.so
          graphgen.py            synthetic graph generators (Erdos-Renyi, R-MAT)
          multigpu.py            one-process-per-GPU driver (torch.distributed / NCCL plumbing)
 """
-from .capi import (CONVERGE_EDGES, CONVERGE_VERTICES, FLAG_FORCE_BLOCKED, FLAG_FORCE_DIRECT, FLAG_NO_EARLY_STOP,
+from .capi import (CONVERGE_EDGES, CONVERGE_VERTICES, FLAG_FORCE_BINNED, FLAG_FORCE_BLOCKED, FLAG_FORCE_DIRECT, FLAG_NO_EARLY_STOP,
                    FLAG_NO_FUSED_FINALIZE, PROPOSAL_DYNAMIC, PROPOSAL_UNIFORM,
                    McmcError)
 from .colorer import Chain, ColoringMCMC, ColoringMCMCParams, Graph, color_stats, luby_color, occupancy_bits
 
 __all__ = ["Chain", "ColoringMCMC", "ColoringMCMCParams", "Graph", "McmcError", "color_stats", "occupancy_bits", "luby_color",
-           "PROPOSAL_UNIFORM", "PROPOSAL_DYNAMIC", "CONVERGE_VERTICES", "CONVERGE_EDGES", "FLAG_NO_FUSED_FINALIZE", "FLAG_NO_EARLY_STOP", "FLAG_FORCE_DIRECT", "FLAG_FORCE_BLOCKED"]
+           "PROPOSAL_UNIFORM", "PROPOSAL_DYNAMIC", "CONVERGE_VERTICES", "CONVERGE_EDGES", "FLAG_NO_FUSED_FINALIZE", "FLAG_NO_EARLY_STOP", "FLAG_FORCE_DIRECT", "FLAG_FORCE_BLOCKED", "FLAG_FORCE_BINNED"]

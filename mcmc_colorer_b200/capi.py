@@ -19,6 +19,7 @@ FLAG_NO_FUSED_FINALIZE = 1
 FLAG_NO_EARLY_STOP = 2
 FLAG_FORCE_DIRECT = 4
 FLAG_FORCE_BLOCKED = 8
+FLAG_FORCE_BINNED = 16
 VIEW_COLORS_CUR, VIEW_COLORS_NEXT, VIEW_COUNTERS = 0, 1, 2
 
 # every symbol include/mcmcb200.h declares (tests/test_capi_symbols.py checks the export table against the header)

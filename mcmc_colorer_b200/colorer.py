@@ -228,7 +228,7 @@ class Chain:
         capi.check(self.L.mcmcb200_last_sweep_ms(self.h, C.byref(ms)), "mcmcb200_last_sweep_ms")
         return ms.value
 
-    KERNEL_MODES = ("direct", "blocked", "blocked-overlapped")
+    KERNEL_MODES = ("direct", "blocked", "blocked-overlapped", "direct-binned")
 
     def kernel_mode(self):
         """which sweep implementation the handle runs: 'direct', 'blocked' or 'blocked-overlapped' (mcmcb200_kernel_mode)"""

@@ -3,6 +3,7 @@
 #include "sweep_kernel.cuh"
 #include "tailcut_kernel.cuh"
 #include "blocked_build.cuh"
+#include "binned_sweep.cuh"
 #include "luby_kernel.cuh"
 
 #include <algorithm>
@@ -68,6 +69,7 @@ struct mcmcb200_handle {
 	uint64_t z = 0;
 	int smCount = 0;
 	BlockedLayout bl;                    // source-blocked two-pass layout (valid => the sweeps use it)
+	BinnedLayout bn;                     // degree-binned direct sweep (valid => used when bl is not)
 	void * peerColors[2][kMaxPeers] = {};  // fused multi-GPU exchange: IPC-mapped colour buffers of every rank (own = local)
 	uint32_t nPeers = 0, myPeerIndex = 0;
 };
@@ -98,6 +100,14 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 		if (h->overlap && (e = cudaStreamWaitEvent(h->stream, h->evReset, 0)) != cudaSuccess) return e;
 		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+		return cudaGetLastError();
+	}
+	if (h->bn.valid) {
+		const BinnedArgs b = make_binned_args(h->bn);
+		cudaError_t e = cudaMemsetAsync(h->bn.counters, 0, 4 * sizeof(uint32_t), h->stream);
+		if (e != cudaSuccess) return e;
+		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) binned_sweep_kernel<W, ColT, true><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b);
+		else binned_sweep_kernel<W, ColT, false><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b);
 		return cudaGetLastError();
 	}
 	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) sweep_kernel<W, ColT, true><<<h->gridBlocks, kThreads, h->smemBytes, h->stream>>>(a);
@@ -158,6 +168,31 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	return cudaSuccess;
 }
 
+template <int W, typename ColT>
+cudaError_t configure_binned_t(mcmcb200_handle * h) {
+	BinnedLayout & L = h->bn;
+	L.smem = binned_smem_bytes(h->p.nCol, W);
+	cudaError_t e = cudaFuncSetAttribute(binned_sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(binned_sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	int o0 = 0, o1 = 0;
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, binned_sweep_kernel<W, ColT, false>, kThreadsBin, L.smem);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, binned_sweep_kernel<W, ColT, true>, kThreadsBin, L.smem);
+	if (e != cudaSuccess) return e;
+	const int o = o0 < o1 ? o0 : o1;
+	if (o < 1) { L.valid = false; return cudaSuccess; }
+	L.grid = o * h->smCount;
+	return cudaSuccess;
+}
+
+cudaError_t configure_binned(mcmcb200_handle * h) {
+	switch (h->W) {
+	case 1: return configure_binned_t<1, uint8_t>(h);
+	case 2: return configure_binned_t<2, uint8_t>(h);
+	case 4: return configure_binned_t<4, uint8_t>(h);
+	default: return configure_binned_t<8, uint16_t>(h);
+	}
+}
+
 cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a) {
 	h->launches++;   // (the blocked path counts its first pass itself)
 	switch (h->W) {
@@ -180,7 +215,11 @@ cudaError_t configure_blocked(mcmcb200_handle * h) {
 template <int W, typename ColT>
 cudaError_t occupancy_t(int * blocks, size_t smem) {
 	int a = 0, b = 0;
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sweep_kernel<W, ColT, false>, kThreads, smem);
+	// (more than the 48 KiB default for the wide palettes: mask rows + walk queue)
+	cudaError_t e = cudaFuncSetAttribute(sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sweep_kernel<W, ColT, false>, kThreads, smem);
 	if (e != cudaSuccess) return e;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sweep_kernel<W, ColT, true>, kThreads, smem);
 	*blocks = a < b ? a : b;
@@ -375,7 +414,9 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		// kernel choice: the source-blocked two-pass sweep pays off once the random colour gathers dominate (large sparse
 		// graphs); small graphs keep the single-pass direct kernel.  MCMCB200_FLAG_FORCE_{DIRECT,BLOCKED} override.
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
-		const bool want = forceBlocked || (!forceDirect && nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18));
+		const bool forceBinned = (p->flags & MCMCB200_FLAG_FORCE_BINNED) != 0;
+		const bool large = nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18);
+		const bool want = forceBlocked || (!forceDirect && !forceBinned && large);
 		if (want) {
 			// colour bytes a tile stages in shared memory.  Large partitions: 44 KiB, so that two pass-B CTAs and one pass-A CTA
 			// (64 KiB chunk) share an SM and the two passes overlap; smaller ones (fill/drain of the A->B pipeline would eat the
@@ -388,6 +429,14 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			if (e == cudaSuccess && !h->bl.valid) free_blocked_layout(h->bl);
 			if (e != cudaSuccess) return fail(cuda_fail(e, "build_blocked_layout", __LINE__));
 			if (forceBlocked && !h->bl.valid) return fail(MCMCB200_EUNSUPPORTED);
+		}
+		// large graph whose rows do not fit the blocked layout (hubs): degree-binned direct sweep instead of the tile-synchronous one
+		if (!h->bl.valid && !forceDirect && !forceBlocked && (forceBinned || large)) {
+			cudaError_t e = build_binned_layout(h->bn, h->d_rowptr, h->nLocal, h->stream, &h->launches);
+			if (e == cudaSuccess && h->bn.valid) e = configure_binned(h);
+			if (e != cudaSuccess) return fail(cuda_fail(e, "build_binned_layout", __LINE__));
+			if (!h->bn.valid) free_binned_layout(h->bn);
+			if (forceBinned && !h->bn.valid) return fail(MCMCB200_EUNSUPPORTED);
 		}
 	}
 	rc = reset_state(h);
@@ -455,6 +504,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_tape); cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
 	free_blocked_layout(h->bl);
+	free_binned_layout(h->bn);
 	for (uint32_t q = 0; q < h->nPeers; ++q)
 		if (q != h->myPeerIndex) for (int b = 0; b < 2; ++b) if (h->peerColors[b][q]) cudaIpcCloseMemHandle(h->peerColors[b][q]);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -888,7 +938,8 @@ int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms) {
 
 int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode) {
 	if (!h || !mode) return MCMCB200_EINVAL;
-	*mode = !h->bl.valid ? MCMCB200_MODE_DIRECT : h->overlap ? MCMCB200_MODE_BLOCKED_OVERLAPPED : MCMCB200_MODE_BLOCKED;
+	*mode = h->bl.valid ? (h->overlap ? MCMCB200_MODE_BLOCKED_OVERLAPPED : MCMCB200_MODE_BLOCKED)
+	                    : h->bn.valid ? MCMCB200_MODE_DIRECT_BINNED : MCMCB200_MODE_DIRECT;
 	return MCMCB200_OK;
 }
 

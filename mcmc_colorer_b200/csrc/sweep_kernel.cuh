@@ -93,6 +93,8 @@ __host__ __device__ inline size_t sweep_smem_bytes(uint32_t nCol, int W, int col
 	b += sizeof(unsigned long long) * (size_t)kTileV * W; // s_mask
 	if (W > 2) b += sizeof(uint32_t) * (kThreads / 32) * 2 * W;   // s_wm: per-warp mask accumulators of the wide palettes
 	b += (size_t)colBytes * (kCapEdges + 16);             // s_col
+	b = (b + 15) & ~(size_t)15;
+	b += (size_t)kTileV * (8 * W + 16);                   // deferred CDF walks of one sub-tile (mask, vertex/own, draw/weight)
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -378,6 +380,18 @@ sweep_kernel(const SweepArgs a) {
 			mm[w] = (unsigned long long)s_m32[(2 * w) * kTileV + slot] | ((unsigned long long)s_m32[(2 * w + 1) * kTileV + slot] << 32);
 	};
 
+	// deferred CDF walks: conflicting vertices are parked here in phase 3 and walked by densely packed threads at the end of
+	// the sub-tile (a walk is ~5 instructions per colour; inline it would run with a handful of active lanes per warp)
+	WalkQueue<W> wq{};
+	{
+		size_t qoff = (size_t)(reinterpret_cast<unsigned char *>(s_col + kCapEdges + 16) - smem_raw);
+		qoff = (qoff + 15) & ~(size_t)15;
+		wq.count = s_ctl + 3;
+		wq.cap = kTileV;
+		wq.mask = reinterpret_cast<unsigned long long *>(smem_raw + qoff);
+		wq.lvOwn = reinterpret_cast<uint32_t *>(wq.mask + (size_t)kTileV * W);
+		wq.uw = reinterpret_cast<float *>(wq.lvOwn + 2 * kTileV);
+	}
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState * st = a.st;
 	if (!a.countOnly && st->convergedAt >= 0) return;      // converged earlier in this batch of launches: no-op
@@ -398,6 +412,7 @@ sweep_kernel(const SweepArgs a) {
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); s_S[k + 1] = s; }
 	}
 	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, s_dist, tid, kThreads);
+	if (tid == 0) *wq.count = 0u;
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 
 	// ---- persistent tile loop ----
@@ -599,7 +614,14 @@ sweep_kernel(const SweepArgs a) {
 			// ---------------- PHASE 3: thread-per-vertex proposal, draw, colour write ----------------
 			if (mine)
 				commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + v0 + tid, v0 + tid, own, m, same, s_S, s_dist, s_hist, stayW,
-				                             accDirected, accViol);
+				                             accDirected, accViol, &wq);
+			__syncthreads();
+			{
+				const uint32_t qn = min(*wq.count, wq.cap);
+				if (qn) drain_walk_queue<W, ColT, kDyn>(a, nxt, wq, 0u, qn, s_dist, s_hist, tid);
+				__syncthreads();
+				if (tid == 0) *wq.count = 0u;
+			}
 		} // sub-tiles
 	} // tiles
 

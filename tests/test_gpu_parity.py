@@ -29,7 +29,7 @@ def mc():
 # single-pass direct-gather kernel / source-blocked two-pass kernel with the 44 KiB stage of the large-graph configuration: pass A
 # and pass B overlap on two streams / the same with the largest stage (the default for graphs of this size), which leaves no
 # room for a pass-A CTA next to pass B: the two passes run one after the other
-KERNELS = ["direct", "blocked", "blocked-serial"]
+KERNELS = ["direct", "blocked", "blocked-serial", "binned"]   # binned: degree-binned direct sweep (large skewed graphs)
 STAGE_CAP = {"blocked": "45056", "blocked-serial": "65504"}
 
 
@@ -39,7 +39,7 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
                                 seed=seed, tailcut=tailcut, maxRip=max_rip)
     # replay=True: keep sweeping past convergence, like the oracle's tape harness does
     flags = mc.FLAG_NO_EARLY_STOP if replay else 0
-    flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED, "blocked-serial": mc.FLAG_FORCE_BLOCKED}[kernel]
+    flags |= {None: 0, "direct": mc.FLAG_FORCE_DIRECT, "blocked": mc.FLAG_FORCE_BLOCKED, "blocked-serial": mc.FLAG_FORCE_BLOCKED, "binned": mc.FLAG_FORCE_BINNED}[kernel]
     saved = os.environ.get("MCMCB200_STAGE_CAP_BYTES")
     if kernel in STAGE_CAP:
         os.environ["MCMCB200_STAGE_CAP_BYTES"] = STAGE_CAP[kernel]
@@ -48,7 +48,7 @@ def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence
     try:
         ch = mc.Chain(cumul, neighs, prm, device=0, flags=flags)
         want = {"direct": ("direct",), "blocked": ("blocked-overlapped", "blocked") if nCol > 64 else ("blocked-overlapped",),
-                "blocked-serial": ("blocked",)}.get(kernel)
+                "blocked-serial": ("blocked",), "binned": ("direct-binned",)}.get(kernel)
         assert want is None or ch.kernel_mode() in want, (kernel, ch.kernel_mode())
         return ch
     except mc.McmcError as e:
