@@ -105,7 +105,7 @@ __host__ __device__ inline size_t binned_smem_bytes(uint32_t nCol, int W) {
 }
 
 template <int W, typename ColT, bool kDyn>
-__global__ void __launch_bounds__(kThreadsBin, (W <= 2 ? 4 : 2))
+__global__ void __launch_bounds__(kThreadsBin, (W <= 2 ? 4 : 3))
 binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr bool kWide = W > 2;
@@ -190,11 +190,20 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 #pragma unroll
 		for (int w = 0; w < W; ++w) m[w] = 0ull;
 		uint32_t same = 0;
-		for (uint32_t e = e0 + tid; e < e1; e += kThreadsBin) {
-			const uint32_t c = ld_color<ColT>(cur + a.neighs[e], polLast);
-			same += (c == own);
-			if (kWide) atomicOr(&s_wm[warp * 2 * W + (c >> 5)], 1u << (c & 31u));
-			else set_bit(m, c);
+		for (uint32_t e = e0 + tid; e < e1; e += 4u * kThreadsBin) {   // four coalesced id loads, then four gathers, in flight
+			uint32_t nb[4], c[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) nb[k] = (e + k * kThreadsBin < e1) ? __ldcs(a.neighs + e + k * kThreadsBin) : 0u;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) c[k] = (e + k * kThreadsBin < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				if (e + k * kThreadsBin < e1) {
+					same += (c[k] == own);
+					if (kWide) atomicOr(&s_wm[warp * 2 * W + (c[k] >> 5)], 1u << (c[k] & 31u));
+					else set_bit(m, c[k]);
+				}
+			}
 		}
 		if (kWide) {
 			__syncwarp();
@@ -242,19 +251,19 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 			for (int w = 0; w < W; ++w) mm[w] = 0ull;
 			uint32_t ss = 0;
 			if (kWide) { if (lane < 2 * W) s_wm[warp * 2 * W + lane] = 0u; __syncwarp(); }
-			for (uint32_t e = e0 + lane; e < e1; e += 64u) {            // two coalesced id loads in flight
-				const uint32_t e2 = e + 32u;
-				const uint32_t nbA = a.neighs[e];
-				const uint32_t nbB = (e2 < e1) ? a.neighs[e2] : 0u;
-				const uint32_t cA = ld_color<ColT>(cur + nbA, polLast);
-				const uint32_t cB = (e2 < e1) ? ld_color<ColT>(cur + nbB, polLast) : 0xffffffffu;
-				ss += (cA == ownJ) + (cB == ownJ);
-				if (kWide) {
-					atomicOr(&s_wm[warp * 2 * W + (cA >> 5)], 1u << (cA & 31u));
-					if (e2 < e1) atomicOr(&s_wm[warp * 2 * W + (cB >> 5)], 1u << (cB & 31u));
-				} else {
-					set_bit(mm, cA);
-					if (e2 < e1) set_bit(mm, cB);
+			for (uint32_t e = e0 + lane; e < e1; e += 128u) {           // four coalesced id loads, then four gathers, in flight
+				uint32_t nb[4], c[4];
+#pragma unroll
+				for (int k = 0; k < 4; ++k) nb[k] = (e + 32u * k < e1) ? __ldcs(a.neighs + e + 32u * k) : 0u;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) c[k] = (e + 32u * k < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					if (e + 32u * k < e1) {
+						ss += (c[k] == ownJ);
+						if (kWide) atomicOr(&s_wm[warp * 2 * W + (c[k] >> 5)], 1u << (c[k] & 31u));
+						else set_bit(mm, c[k]);
+					}
 				}
 			}
 			ss = __reduce_add_sync(0xffffffffu, ss);
@@ -303,7 +312,7 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 		for (uint32_t i = 0; i < deg; i += 4u) {
 			uint32_t nb[4], c[4];
 #pragma unroll
-			for (int k = 0; k < 4; ++k) nb[k] = (i + k < deg) ? a.neighs[beg + i + k] : 0u;
+			for (int k = 0; k < 4; ++k) nb[k] = (i + k < deg) ? __ldg(a.neighs + beg + i + k) : 0u;   // (the row's sector serves the next iterations from L1)
 #pragma unroll
 			for (int k = 0; k < 4; ++k) c[k] = (i + k < deg) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
 #pragma unroll
