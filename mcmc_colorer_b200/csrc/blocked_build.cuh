@@ -18,7 +18,7 @@ inline void free_blocked_layout(BlockedLayout & L) {
 
 // Returns cudaSuccess with L.valid == false when the layout does not apply (hub rows larger than a tile, > 2^31 edges...).
 inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_rowptr, const uint32_t * d_neighs, uint32_t nLocal,
-                                        uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes,
+                                        uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes, uint32_t itemEntries,
                                         cudaStream_t stream, uint64_t * launches) {
 	cudaError_t err = cudaSuccess;
 	L = BlockedLayout{};
@@ -172,10 +172,10 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaStreamSynchronize(stream));
 	if (h2[0] + 16u > stageCap) goto done;                             // (cannot happen given the TV choice; keeps the kernel's bound honest)
 	{
-		// about kItemEntries entries per item in the body: K = tiles per body part.  The first and the last K tiles are cut
+		// about itemEntries entries per item in the body: K = tiles per body part.  The first and the last K tiles are cut
 		// into K/4, K/4, K/2 (and mirrored): pass B can start after 1/4 of a part and has only 1/4 of a part left when pass A ends.
 		const uint64_t perBucket = ((uint64_t)L.totalPadded + P - 1) / P;
-		const uint32_t np0 = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (perBucket + kItemEntries - 1) / kItemEntries));
+		const uint32_t np0 = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (perBucket + itemEntries - 1) / itemEntries));
 		const uint32_t K = std::max<uint32_t>(1u, (numTiles + np0 - 1) / np0);
 		std::vector<uint32_t> ps;
 		ps.push_back(0);

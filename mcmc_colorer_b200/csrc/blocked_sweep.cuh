@@ -56,10 +56,6 @@ constexpr int      kThreadsA  = MCMCB200_THREADS_A;
 // palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads, one CTA
 template <int W> struct PassB { static constexpr int threads = (W <= 2) ? MCMCB200_THREADS_B : 512;
                                 static constexpr int maxRegs = (W <= 2) ? 64 : 128; };
-#ifndef MCMCB200_ITEM_BITS
-#define MCMCB200_ITEM_BITS 17
-#endif
-constexpr uint32_t kItemEntries = 1u << MCMCB200_ITEM_BITS;   // pass-A work item: up to this many entries of one bucket
 
 struct BlockedLayout {
 	bool      valid = false;
@@ -332,7 +328,10 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 		}
 		// one 4-entry granule per lane per step: a warp reads 256 contiguous bytes of local ids and 128 of destinations, and
 		// its store covers whole 32-byte sectors wherever a run spans them (full-sector first touches need no fill in L2)
-		constexpr uint32_t kU = 8;
+#ifndef MCMCB200_A_KU
+#define MCMCB200_A_KU 8
+#endif
+		constexpr uint32_t kU = MCMCB200_A_KU;   // granules in flight per thread: 12 bytes of loads each (pass A is bound by bytes in flight)
 		const uint32_t g0 = beg >> 2, g1 = end >> 2;           // runs are padded to 4 entries: items are whole granules
 		for (uint32_t j0 = g0 + tid; j0 < g1; j0 += kThreadsA * kU) {
 			uint2 ids[kU];
