@@ -20,7 +20,9 @@ dev = f"cuda:{lr}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 P = Port()
 ok = True
-for n, deg, proposal, p2p in [(50_001, 12, 0, False), (50_001, 12, 1, False), (300_000, 20, 0, False), (300_000, 20, 1, True), (1_000_003, 16, 0, True)]:
+# (n, mean degree, proposal, fused P2P exchange, stage bytes: 45056 = the large-partition configuration, pass A || pass B)
+for n, deg, proposal, p2p, cap in [(50_001, 12, 0, False, None), (50_001, 12, 1, False, None), (300_000, 20, 0, False, None),
+                                   (300_000, 20, 1, True, None), (1_000_003, 16, 0, True, None), (1_000_003, 16, 1, True, "45056")]:
     cumul, neighs = er_graph_numpy(n, deg, seed=5)
     nCol = int(np.diff(cumul.astype(np.int64)).max())
     parts, chunk = partition(n, world)
@@ -30,7 +32,12 @@ for n, deg, proposal, p2p in [(50_001, 12, 0, False), (50_001, 12, 1, False), (3
     nb = torch.zeros(e1 - e0 + 16, dtype=torch.int32, device=dev)
     nb[: e1 - e0] = torch.from_numpy(neighs[e0:e1].astype(np.int32)).to(dev)
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=proposal, seed=11)
+    if cap:
+        os.environ["MCMCB200_STAGE_CAP_BYTES"] = cap
     eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr)
+    os.environ.pop("MCMCB200_STAGE_CAP_BYTES", None)
+    if rank == 0:
+        print(f"n={n} proposal={proposal}: sweep mode {eng.chain.kernel_mode()}")
     if p2p:
         got_p2p = eng.enable_p2p(rank, world)
         if rank == 0:
