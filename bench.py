@@ -273,16 +273,23 @@ def main():
         ch.sweep(10)
         chain_ms = ch.last_sweep_ms() / 10.0
     st = ch.status()
-    # time to a proper colouring (the other half of BASELINE's metric): a fresh chain swept until no vertex is violated,
-    # counters read back after every sweep (wall clock, includes those host round trips); untimed for `value`
+    # time to a proper colouring (the other half of BASELINE's metric), the reference's --tailcut protocol: sweep until at most
+    # z = max(50, n/2000) vertices are violated (coloringMCMC_main.cu:150-170), then the greedy tail-cutting repair (:271-290).
+    # (At n = 1e8 the epsilon tails alone re-colour ~n*nCol*eps = 45 vertices per sweep, so the plain chain idles at a few
+    # dozen violations: the threshold is part of the algorithm, not a shortcut.)  Counters are read back after every sweep;
+    # wall clock including those host round trips; untimed for `value`.
     ch.init_colors(None)
     torch.cuda.synchronize()
+    z_tail = max(50, n // 2000)
     t_ttc = time.perf_counter()
     ttc_sweeps, st_ttc = 0, ch.status()
-    while st_ttc.violatingVertices > 0 and ttc_sweeps < 250:
+    while st_ttc.violatingVertices > z_tail and ttc_sweeps < 250:
         ch.sweep(1)
         st_ttc = ch.status()
         ttc_sweeps += 1
+    t_sweeps = time.perf_counter() - t_ttc
+    ttc_rounds = ch.tailcut(64) if st_ttc.conflictEdges > 0 else 0
+    st_ttc = ch.status()
     t_ttc = time.perf_counter() - t_ttc
     ms_per_step = float(np.mean(kernel_ms))
     value = n / (ms_per_step * 1e-3)
@@ -332,7 +339,8 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks.summary(),
         "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
-        "time_to_proper_coloring": {"sweeps": ttc_sweeps, "ms": 1e3 * t_ttc, "proper": bool(st_ttc.violatingVertices == 0),
+        "time_to_proper_coloring": {"sweeps": ttc_sweeps, "tailcut_rounds": int(ttc_rounds), "ms": 1e3 * t_ttc, "ms_sweeps": 1e3 * t_sweeps,
+                                    "z": z_tail, "proper": bool(st_ttc.conflictEdges == 0 and st_ttc.violatingVertices == 0),
                                     "usedColors": int(st_ttc.usedColors), "nCol": nCol},
     }
     if not args.no_cpu_baseline:
