@@ -104,6 +104,15 @@ int mcmcb200_create_device_csr(mcmcb200_handle ** out, uint32_t nGlobal, uint32_
                                uint64_t nnzLocal, const uint32_t * d_cumulDegs, const uint32_t * d_neighs,
                                const mcmcb200_params * p);
 
+/* GPU-side CSR construction from an edge list: the device twin of Graph::setupImporterNew (graph/graphCPU.cpp:112-170) for
+ * inputs too large for the host loop -- self-loops dropped, the back-edge of every edge added, duplicates kept, neighbours of a
+ * row in file order: array for array the CSR the reference builds.  src / dst: m entries each, HOST or DEVICE memory, ids < n.
+ * The two result arrays live in device memory (device = CUDA ordinal, -1 = current), are laid out the way
+ * mcmcb200_create_device_csr wants them (d_cumulDegs[0] == 0, d_neighs padded) and are released with mcmcb200_csr_free. */
+int mcmcb200_csr_from_edges(uint32_t n, uint64_t m, const uint32_t * src, const uint32_t * dst, int device,
+                            uint32_t ** d_cumulDegs, uint32_t ** d_neighs, uint64_t * nnz);
+void mcmcb200_csr_free(uint32_t * d_cumulDegs, uint32_t * d_neighs);
+
 void mcmcb200_destroy(mcmcb200_handle * h);
 
 /* Replaces initColoring (coloringMCMC_utils.cu:24-33) / the ctor draw (coloringMCMC_CPU.cpp:54,61).

@@ -9,7 +9,7 @@ Layout:  csrc/  CUDA kernels + the C ABI (include/mcmcb200.h) -> libmcmcb200.so
 from .capi import (CONVERGE_EDGES, CONVERGE_VERTICES, FLAG_FORCE_BINNED, FLAG_FORCE_BLOCKED, FLAG_FORCE_DIRECT, FLAG_NO_EARLY_STOP,
                    FLAG_NO_FUSED_FINALIZE, PROPOSAL_DYNAMIC, PROPOSAL_UNIFORM,
                    McmcError)
-from .colorer import Chain, ColoringMCMC, ColoringMCMCParams, Graph, color_stats, luby_color, occupancy_bits
+from .colorer import Chain, ColoringMCMC, ColoringMCMCParams, DeviceCsr, Graph, color_stats, luby_color, occupancy_bits
 
-__all__ = ["Chain", "ColoringMCMC", "ColoringMCMCParams", "Graph", "McmcError", "color_stats", "occupancy_bits", "luby_color",
+__all__ = ["Chain", "DeviceCsr", "ColoringMCMC", "ColoringMCMCParams", "Graph", "McmcError", "color_stats", "occupancy_bits", "luby_color",
            "PROPOSAL_UNIFORM", "PROPOSAL_DYNAMIC", "CONVERGE_VERTICES", "CONVERGE_EDGES", "FLAG_NO_FUSED_FINALIZE", "FLAG_NO_EARLY_STOP", "FLAG_FORCE_DIRECT", "FLAG_FORCE_BLOCKED", "FLAG_FORCE_BINNED"]

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mcmcb200_init_colors", "mcmcb200_set_tape", "mcmcb200_sweep", "mcmcb200_status", "mcmcb200_get_colors",
     "mcmcb200_get_class_sizes", "mcmcb200_get_history", "mcmcb200_tailcut", "mcmcb200_conflicts_of",
     "mcmcb200_debug_occupancy", "mcmcb200_debug_all_occupancy", "mcmcb200_device_view", "mcmcb200_finalize_sweep",
-    "mcmcb200_stream", "mcmcb200_synchronize", "mcmcb200_last_sweep_ms", "mcmcb200_launch_count", "mcmcb200_kernel_mode",
+    "mcmcb200_stream", "mcmcb200_synchronize", "mcmcb200_last_sweep_ms", "mcmcb200_launch_count", "mcmcb200_kernel_mode", "mcmcb200_csr_from_edges", "mcmcb200_csr_free",
     "mcmcb200_strerror", "mcmcb200_last_cuda_error", "mcmcb200_abi_version", "mcmcb200_luby_color",
     "mcmcb200_ipc_export", "mcmcb200_ipc_attach", "mcmcb200_init_colors_slice", "mcmcb200_init_colors_finish",
     "mcmcb200_get_colors_slice",
@@ -98,6 +98,9 @@ def lib():
     L.mcmcb200_last_sweep_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.mcmcb200_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mcmcb200_kernel_mode.argtypes = [vp, C.POINTER(C.c_int)]
+    L.mcmcb200_csr_from_edges.argtypes = [C.c_uint32, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.mcmcb200_csr_free.argtypes = [vp, vp]
+    L.mcmcb200_csr_free.restype = None
     L.mcmcb200_luby_color.argtypes = [C.c_uint32, C.c_uint64, vp, vp, C.c_uint64, C.c_int32, vp, u32p, u32p]
     L.mcmcb200_strerror.argtypes = [C.c_int]
     L.mcmcb200_strerror.restype = C.c_char_p

@@ -67,6 +67,43 @@ class Graph:
         return int(np.float32(maxDeg) * (np.float32(1.0) / np.float32(numColRatio)))
 
 
+class DeviceCsr:
+    """CSR built on the GPU from an edge list (mcmcb200_csr_from_edges): the device twin of Graph::setupImporterNew
+    (graphCPU.cpp:112-170) -- self-loops dropped, back-edges added, duplicates kept, rows in file order.
+    src / dst: integer arrays on the host (numpy) or raw device pointers (ints) of m entries.
+    Use as Chain(params=..., n_global=n, v_begin=0, v_end=n, device_csr=csr.as_tuple())."""
+
+    def __init__(self, n, src, dst, m=None, device=0):
+        self.L = capi.lib()
+        self.n, self.device = int(n), device
+        keep = []
+        def ptr(x):
+            if isinstance(x, int):
+                return C.c_void_p(x)
+            a = np.ascontiguousarray(x, np.uint32)
+            keep.append(a)
+            return C.c_void_p(a.ctypes.data)
+        m = int(m if m is not None else len(src))
+        self.rowptr, self.neighs, nnz = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        capi.check(self.L.mcmcb200_csr_from_edges(self.n, m, ptr(src), ptr(dst), device, C.byref(self.rowptr), C.byref(self.neighs),
+                                                  C.byref(nnz)), "mcmcb200_csr_from_edges")
+        self.nnz = int(nnz.value)
+
+    def as_tuple(self):
+        return (self.rowptr.value, self.neighs.value, self.nnz)
+
+    def close(self):
+        if self.rowptr is not None:
+            self.L.mcmcb200_csr_free(self.rowptr, self.neighs)
+            self.rowptr = self.neighs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Chain:
     """One Markov chain on one GPU: a mcmcb200_handle."""
 

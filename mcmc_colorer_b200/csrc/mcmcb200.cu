@@ -4,6 +4,7 @@
 #include "tailcut_kernel.cuh"
 #include "blocked_build.cuh"
 #include "binned_sweep.cuh"
+#include "csr_build.cuh"
 #include "luby_kernel.cuh"
 
 #include <algorithm>
@@ -497,6 +498,44 @@ int mcmcb200_create_device_csr(mcmcb200_handle ** out, uint32_t nGlobal, uint32_
                                uint64_t nnzLocal, const uint32_t * d_cumulDegs, const uint32_t * d_neighs,
                                const mcmcb200_params * p) {
 	return create_common(out, nGlobal, vBegin, vEnd, nnzLocal, d_cumulDegs, d_neighs, true, p);
+}
+
+int mcmcb200_csr_from_edges(uint32_t n, uint64_t m, const uint32_t * src, const uint32_t * dst, int device,
+                            uint32_t ** d_cumulDegs, uint32_t ** d_neighs, uint64_t * nnz) {
+	if (!d_cumulDegs || !d_neighs || !nnz || n == 0 || (m && (!src || !dst))) return MCMCB200_EINVAL;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "no CUDA device: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return MCMCB200_ENODEVICE;
+	}
+	if (device >= 0) CU(cudaSetDevice(device));
+	// host arrays are staged in device memory first
+	uint32_t * tmp[2] = {nullptr, nullptr};
+	const uint32_t * in[2] = {src, dst};
+	for (int i = 0; i < 2 && m; ++i) {
+		cudaPointerAttributes at{};
+		e = cudaPointerGetAttributes(&at, in[i]);
+		if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+		if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+			e = cudaMalloc(&tmp[i], sizeof(uint32_t) * m);
+			if (e == cudaSuccess) e = cudaMemcpy(tmp[i], in[i], sizeof(uint32_t) * m, cudaMemcpyHostToDevice);
+			if (e != cudaSuccess) { cudaFree(tmp[0]); cudaFree(tmp[1]); return cuda_fail(e, "edge list upload", __LINE__); }
+			in[i] = tmp[i];
+		}
+	}
+	uint64_t bad = 0;
+	e = build_csr_from_edges(n, m, in[0], in[1], (cudaStream_t)0, d_cumulDegs, d_neighs, nnz, &bad);
+	cudaFree(tmp[0]); cudaFree(tmp[1]);
+	if (e == cudaErrorInvalidValue) { cudaGetLastError(); return bad ? MCMCB200_EINVAL : MCMCB200_EUNSUPPORTED; }   // id >= n / more than 2^32 entries
+	if (e != cudaSuccess) return cuda_fail(e, "build_csr_from_edges", __LINE__);
+	return MCMCB200_OK;
+}
+
+void mcmcb200_csr_free(uint32_t * d_cumulDegs, uint32_t * d_neighs) {
+	cudaFree(d_cumulDegs); cudaFree(d_neighs);
+	cudaGetLastError();
 }
 
 void mcmcb200_destroy(mcmcb200_handle * h) {

@@ -294,3 +294,27 @@ class Ref:
         hit = C.c_int()
         viol = self.L.ref_mcmc_run_native(h, C.byref(sweeps), C.byref(hit))
         return viol, sweeps.value, bool(hit.value)
+
+
+def importer_csr(n, src, dst):
+    """Plain restatement of Graph::setupImporterNew (graph/graphCPU.cpp:112-170) on vertex-id pairs: first pass counts
+    (self-loops skipped, one slot for the edge and one for its back-edge, :121-132), prefix sum (:135-137), second pass fills
+    the rows in file order (:150-165).  Duplicate edges are kept.  Python loops: small inputs only.  Pin: the loops are the
+    reference's, statement for statement; tests/test_host_layer.py checks the C++ host importer built the same way against
+    the reference's own CSR (oracle/_ref) on a file."""
+    cumul = np.zeros(n + 1, np.int64)
+    for s_, d_ in zip(src, dst):
+        if s_ != d_:
+            cumul[s_ + 1] += 1
+            cumul[d_ + 1] += 1
+    for i in range(1, n + 1):
+        cumul[i] += cumul[i - 1]
+    neighs = np.zeros(int(cumul[n]), np.uint32)
+    temp = np.zeros(n, np.int64)
+    for s_, d_ in zip(src, dst):
+        if s_ != d_:
+            neighs[cumul[s_] + temp[s_]] = d_
+            temp[s_] += 1
+            neighs[cumul[d_] + temp[d_]] = s_
+            temp[d_] += 1
+    return cumul.astype(np.uint32), neighs
