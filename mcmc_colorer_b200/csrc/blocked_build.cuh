@@ -10,7 +10,7 @@ namespace mcmcb200 {
 
 inline void free_blocked_layout(BlockedLayout & L) {
 	cudaFree(L.srcLocal); cudaFree(L.ecol); cudaFree(L.gidx); cudaFree(L.gidxS); cudaFree(L.order); cudaFree(L.slotInfo); cudaFree(L.sliceOff);
-	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items); cudaFree(L.sync); cudaFree(L.tilePart);
+	cudaFree(L.granDst); cudaFree(L.tileBase); cudaFree(L.items); cudaFree(L.sync); cudaFree(L.tilePart); cudaFree(L.dbgTimes);
 	L = BlockedLayout{};
 }
 
@@ -205,6 +205,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 		}
 		cudaFree(d_ps);
 		if (err != cudaSuccess) goto done;
+		BLK_CU(cudaMalloc(&L.dbgTimes, 8 * sizeof(unsigned long long)));
 		BLK_CU(cudaMalloc(&L.sync, sizeof(uint32_t) * (2 + (size_t)L.numParts)));
 		BLK_CU(cudaMemsetAsync(L.sync, 0, sizeof(uint32_t) * (2 + (size_t)L.numParts), stream));
 		BLK_CU(cudaStreamSynchronize(stream));
@@ -227,7 +228,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granDst = L.granDst; b.tileBase = L.tileBase;
-	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilePart = L.tilePart; b.sync = L.sync;
+	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilePart = L.tilePart; b.sync = L.sync; b.dbgTimes = L.dbgTimes;
 	return b;
 }
 

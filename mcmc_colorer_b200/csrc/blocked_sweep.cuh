@@ -33,6 +33,10 @@
 
 namespace mcmcb200 {
 
+#ifndef MCMCB200_TIMING
+#define MCMCB200_TIMING 0     /* 1: kernels record start/end/wait times (experiments; host prints them after every sweep) */
+#endif
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 constexpr uint32_t kChunkBits = 16;
 constexpr uint32_t kChunkV    = 1u << kChunkBits;    // source chunk: 65536 vertices, u16 local ids
 #ifndef MCMCB200_THREADS_A
@@ -78,6 +82,7 @@ struct BlockedLayout {
 	uint32_t  numParts = 0;          // pass A works through the tiles in numParts stretches (short ones first and last) ...
 	uint8_t * tilePart = nullptr;    // [numTiles] part of each tile
 	uint32_t * sync = nullptr;       // [2 + numParts]: next item, next tile, buckets finished per part  (... and pass B follows behind)
+	unsigned long long * dbgTimes = nullptr;
 	size_t    smemA = 0, smemB = 0;
 	int       gridA = 0, gridB = 0;
 };
@@ -95,6 +100,7 @@ struct BlockedArgs {
 	const uint32_t * items;
 	uint32_t numItems, numParts;
 	const uint8_t * tilePart;
+	unsigned long long * dbgTimes;   // (MCMCB200_TIMING builds only) [0] A first start [1] A last end [2] B first start [3] B last end [4] B wait ns
 	uint32_t * sync;
 };
 
@@ -310,12 +316,13 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	if (MCMCB200_ST_LAST) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	__shared__ uint32_t s_item;
 	uint32_t have = 0xffffffffu;
+	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 0, global_ns());
 	for (;;) {
 		__syncthreads();                                      // everybody is done with the previous item (and its chunk)
 		if (tid == 0) s_item = atomicAdd(bl.sync + 0, 1u);
 		__syncthreads();
 		const uint32_t it = s_item;
-		if (it >= bl.numItems) break;
+		if (it >= bl.numItems) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 1, global_ns()); break; }
 		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
 		if (b != have && beg < end) {
 			// the colour buffers are padded by 64 Ki entries, so a whole chunk is always readable
@@ -660,17 +667,19 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	if (tid < 16) sm.stage2[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
 	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, sm.dist, tid, kT);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
+	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 2, global_ns());
 	__syncthreads();
 
 	for (;;) {
 		if (tid == 0) {                                       // tiles in ascending order: the order pass A completes them in
 			const uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
-			if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
+			if (MCMCB200_TIMING) { const unsigned long long w0 = global_ns(); if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st); atomicAdd(bl.dbgTimes + 4, global_ns() - w0); }
+			else if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
 			sm.ctl[4] = Tn;
 		}
 		__syncthreads();
 		const uint32_t T = sm.ctl[4];
-		if (T >= bl.numTiles) break;
+		if (T >= bl.numTiles) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 3, global_ns()); break; }
 		const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
 		stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, (uint32_t)tid, (uint32_t)kT);
 		cp_async_commit_wait_all();

@@ -93,6 +93,9 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 			if (e == cudaSuccess) e = cudaStreamWaitEvent(sA, h->evFork, 0);
 		}
 		if (e == cudaSuccess) e = cudaMemsetAsync(h->bl.sync, 0, syncBytes, sA);
+#if MCMCB200_TIMING
+		{ const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, 0, 0, 0, 0}; cudaMemcpyAsync(h->bl.dbgTimes, init, sizeof(init), cudaMemcpyHostToDevice, sA); }
+#endif
 		if (e == cudaSuccess && h->overlap) e = cudaEventRecord(h->evReset, sA);   // B may start as soon as the counters are clean
 		if (e != cudaSuccess) return e;
 		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b);
@@ -101,6 +104,11 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 		if (h->overlap && (e = cudaStreamWaitEvent(h->stream, h->evReset, 0)) != cudaSuccess) return e;
 		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+#if MCMCB200_TIMING
+		{ unsigned long long tm[8]; cudaStreamSynchronize(h->stream); cudaStreamSynchronize(sA); cudaMemcpy(tm, h->bl.dbgTimes, sizeof(tm), cudaMemcpyDeviceToHost);
+		  fprintf(stderr, "[timing] A %.3f ms (start +0) | B start +%.3f ms, end +%.3f ms | A end +%.3f ms | B waited %.3f ms summed over %d CTAs\n", (tm[1] - tm[0]) * 1e-6,
+		          ((double)tm[2] - (double)tm[0]) * 1e-6, ((double)tm[3] - (double)tm[0]) * 1e-6, ((double)tm[1] - (double)tm[0]) * 1e-6, tm[4] * 1e-6, h->bl.gridB); }
+#endif
 		return cudaGetLastError();
 	}
 	if (h->bn.valid) {
