@@ -429,15 +429,15 @@ __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 // shared-memory views of one pass-B CTA
 template <int W, typename ColT>
 struct PassBShared {
-	uint32_t * slot2; uint32_t * soff2; float * S; float * dist; int * hist; uint32_t * ctl; unsigned long long * red;
-	uint32_t * qcnt; uint16_t * heavy; unsigned char * queues; ColT * stage2; ColT * new2; ColT * own2;
+	uint32_t * slotTab; uint32_t * sliceTab; float * S; float * dist; int * hist; uint32_t * ctl; unsigned long long * red;
+	uint32_t * qcnt; uint16_t * heavy; unsigned char * queues; ColT * stageBuf; ColT * newCol; ColT * ownCol;
 	uint32_t stageStride, tvStride, soffStride;
 	__device__ __forceinline__ PassBShared(unsigned char * raw, uint32_t nCol, uint32_t TV, uint32_t stageCap) {
 		const uint32_t spt = TV >> 5;
-		slot2 = reinterpret_cast<uint32_t *>(raw);
-		soff2 = slot2 + TV;
+		slotTab = reinterpret_cast<uint32_t *>(raw);
+		sliceTab = slotTab + TV;
 		soffStride = spt + 4;
-		S = reinterpret_cast<float *>(soff2 + soffStride);
+		S = reinterpret_cast<float *>(sliceTab + soffStride);
 		dist = S + ((nCol + 1 + 3) & ~3u);
 		hist = reinterpret_cast<int *>(dist + ((nCol + 3) & ~3u));
 		ctl = reinterpret_cast<uint32_t *>(hist + ((nCol + 3) & ~3u));
@@ -448,11 +448,11 @@ struct PassBShared {
 		off = (off + 15) & ~(size_t)15;
 		queues = raw + off;
 		if (W <= 2) off += (size_t)(PassB<W>::threads / 32) * warp_queue_cap(W) * (8 * W + 16);
-		stage2 = reinterpret_cast<ColT *>(raw + off);
+		stageBuf = reinterpret_cast<ColT *>(raw + off);
 		stageStride = stageCap + 16;
 		tvStride = TV + 16;
-		new2 = stage2 + stageStride;
-		own2 = new2 + tvStride;
+		newCol = stageBuf + stageStride;
+		ownCol = newCol + tvStride;
 	}
 };
 
@@ -463,12 +463,12 @@ __device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArg
                                            uint32_t T, uint32_t tb, uint32_t te, uint32_t thr, uint32_t nThr) {
 	const uint32_t TV = bl.TV, spt = TV >> 5;
 	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
-	uint32_t * sl = sm.slot2;
+	uint32_t * sl = sm.slotTab;
 	const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
 	for (uint32_t i = thr; i < (TV >> 2); i += nThr) cp_async_16(sl + 4u * i, gsl + i);
-	uint32_t * so = sm.soff2;
+	uint32_t * so = sm.sliceTab;
 	for (uint32_t i = thr; i <= spt; i += nThr) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
-	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.own2);
+	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.ownCol);
 	const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
 	const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;          // (colour arrays are padded; tiles start 256-aligned)
 	for (uint32_t i = thr; i < n16; i += nThr) cp_async_16(ow + 16u * i, cb + 16u * i);
@@ -478,7 +478,7 @@ __device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArg
 	const uint32_t a0 = tb & ~(alignE - 1u);
 	const uint32_t nC = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) >> 4;
 	const unsigned char * eb = reinterpret_cast<const unsigned char *>(static_cast<const ColT *>(bl.ecol) + a0);
-	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stage2);
+	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stageBuf);
 	for (uint32_t i = thr; i < nC; i += nThr) cp_async_16(stg + 16u * i, eb + 16u * i);
 }
 
@@ -664,7 +664,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); sm.S[k + 1] = s; }
 		sm.ctl[1] = 0u;                                       // heavy-list counter
 	}
-	if (tid < 16) sm.stage2[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
+	if (tid < 16) sm.stageBuf[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
 	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, sm.dist, tid, kT);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 2, global_ns());
@@ -686,7 +686,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		__syncthreads();                                      // the tile is staged
 		TileView<W, ColT> tv;
 		tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
-		tv.slot = sm.slot2; tv.soff = sm.soff2; tv.own = sm.own2; tv.stage = sm.stage2; tv.snew = sm.new2; tv.heavyCount = sm.ctl + 1;
+		tv.slot = sm.slotTab; tv.soff = sm.sliceTab; tv.own = sm.ownCol; tv.stage = sm.stageBuf; tv.snew = sm.newCol; tv.heavyCount = sm.ctl + 1;
 		if (useQueue && lane == 0) *wq.count = 0u;
 		__syncwarp();
 		for (uint32_t g = 0; g < tv.nv; g += kT)
