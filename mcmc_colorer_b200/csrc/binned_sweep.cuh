@@ -23,6 +23,10 @@ constexpr int      kThreadsBin   = 256;
 constexpr uint32_t kBinThreadMax = 32;      // thread rows: degree <= 32
 constexpr uint32_t kBinWarpMax   = 4096;    // warp rows: degree <= 4096; longer rows take the whole CTA
 constexpr uint32_t kBinQueueCap  = 48;
+#ifndef MCMCB200_BIN_UNROLL
+#define MCMCB200_BIN_UNROLL 4
+#endif
+constexpr int      kBinUnroll    = MCMCB200_BIN_UNROLL;   // coalesced id loads (then colour gathers) in flight per lane in warp / CTA rows
 
 struct BinnedLayout {
 	bool       valid = false;
@@ -190,14 +194,14 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 #pragma unroll
 		for (int w = 0; w < W; ++w) m[w] = 0ull;
 		uint32_t same = 0;
-		for (uint32_t e = e0 + tid; e < e1; e += 4u * kThreadsBin) {   // four coalesced id loads, then four gathers, in flight
-			uint32_t nb[4], c[4];
+		for (uint32_t e = e0 + tid; e < e1; e += (uint32_t)kBinUnroll * kThreadsBin) {   // kBinUnroll coalesced id loads, then as many gathers, in flight
+			uint32_t nb[kBinUnroll], c[kBinUnroll];
 #pragma unroll
-			for (int k = 0; k < 4; ++k) nb[k] = (e + k * kThreadsBin < e1) ? __ldcs(a.neighs + e + k * kThreadsBin) : 0u;
+			for (int k = 0; k < kBinUnroll; ++k) nb[k] = (e + k * kThreadsBin < e1) ? __ldcs(a.neighs + e + k * kThreadsBin) : 0u;
 #pragma unroll
-			for (int k = 0; k < 4; ++k) c[k] = (e + k * kThreadsBin < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
+			for (int k = 0; k < kBinUnroll; ++k) c[k] = (e + k * kThreadsBin < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
 #pragma unroll
-			for (int k = 0; k < 4; ++k) {
+			for (int k = 0; k < kBinUnroll; ++k) {
 				if (e + k * kThreadsBin < e1) {
 					same += (c[k] == own);
 					if (kWide) atomicOr(&s_wm[warp * 2 * W + (c[k] >> 5)], 1u << (c[k] & 31u));
@@ -251,14 +255,14 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 			for (int w = 0; w < W; ++w) mm[w] = 0ull;
 			uint32_t ss = 0;
 			if (kWide) { if (lane < 2 * W) s_wm[warp * 2 * W + lane] = 0u; __syncwarp(); }
-			for (uint32_t e = e0 + lane; e < e1; e += 128u) {           // four coalesced id loads, then four gathers, in flight
-				uint32_t nb[4], c[4];
+			for (uint32_t e = e0 + lane; e < e1; e += 32u * kBinUnroll) {   // kBinUnroll coalesced id loads, then as many gathers, in flight
+				uint32_t nb[kBinUnroll], c[kBinUnroll];
 #pragma unroll
-				for (int k = 0; k < 4; ++k) nb[k] = (e + 32u * k < e1) ? __ldcs(a.neighs + e + 32u * k) : 0u;
+				for (int k = 0; k < kBinUnroll; ++k) nb[k] = (e + 32u * k < e1) ? __ldcs(a.neighs + e + 32u * k) : 0u;
 #pragma unroll
-				for (int k = 0; k < 4; ++k) c[k] = (e + 32u * k < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
+				for (int k = 0; k < kBinUnroll; ++k) c[k] = (e + 32u * k < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
 #pragma unroll
-				for (int k = 0; k < 4; ++k) {
+				for (int k = 0; k < kBinUnroll; ++k) {
 					if (e + 32u * k < e1) {
 						ss += (c[k] == ownJ);
 						if (kWide) atomicOr(&s_wm[warp * 2 * W + (c[k] >> 5)], 1u << (c[k] & 31u));
