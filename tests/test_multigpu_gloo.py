@@ -58,6 +58,19 @@ class OracleEngine:
     def next_colors(self):
         return self.bufs[(self.t + 1) & 1]
 
+    def cur_colors(self):
+        return self.bufs[self.t & 1]
+
+    def init_colors_slice(self, own, sweeper):
+        """sliced host interface (GpuEngine.init_colors_slice): this rank provides only the colours it owns"""
+        import torch
+        self.bufs[0].zero_()
+        self.bufs[0][self.vb:self.ve] = torch.from_numpy(own.astype(np.uint8))
+        self.t, self.counts_sweep = 0, None
+        self._counters.zero_()
+        sweeper.gather_current()
+        self.hist = self.P.class_sizes(self._cur(), self.nCol).astype(np.int64)
+
     def counters(self):
         return self._counters
 
@@ -99,7 +112,16 @@ def _worker(rank, world, port_file, result_dir, proposal):
         hist.append((st.sweep, st.conflictEdges, st.violatingVertices))
         sw.sweep(1)
     final = eng.bufs[eng.t & 1][:n].numpy().astype(np.uint32)
-    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), final=final, hist=np.array(hist), class_sizes=eng.hist)
+    class_sizes = eng.hist.copy()                     # maintained from the all-reduced deltas over the 6 sweeps
+    # sliced host interface: restart from a colouring of which every rank holds only its own part
+    c0 = P.init_colors(77, n, nCol)
+    eng.init_colors_slice(c0[vb:ve], sw)
+    st = sw.status()
+    sliced = eng.bufs[0][:n].numpy().astype(np.uint32)
+    sw.sweep(1)
+    after = eng.bufs[eng.t & 1][:n].numpy().astype(np.uint32)
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), final=final, hist=np.array(hist), class_sizes=class_sizes,
+             sliced=sliced, sliced_counts=np.array([st.conflictEdges, st.violatingVertices]), after=after)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -125,6 +147,13 @@ def test_two_rank_driver_matches_single_process_oracle(port, tmp_path, proposal)
         assert np.array_equal(z["final"], c), r                       # same trajectory as one process, on every rank
         assert z["hist"].tolist() == [list(x) for x in want_hist]
         assert np.array_equal(z["class_sizes"], port.class_sizes(c, nCol).astype(np.int64))
+    c0 = port.init_colors(77, n, nCol)
+    c1, _ = port.sweep(cumul, neighs, nCol, 1e-8, c0, port.tape(11, 1, n, proposal), proposal)
+    for r in range(world):
+        z = np.load(str(tmp_path / f"rank{r}.npz"))
+        assert np.array_equal(z["sliced"], c0), r                     # every rank ends up with the whole colouring
+        assert z["sliced_counts"].tolist() == [port.conflict_edges(cumul, neighs, c0), port.violation_count(cumul, neighs, c0)]
+        assert np.array_equal(z["after"], c1), r
     parts, chunk = partition(n, world)
     assert parts[0][0] == 0 and parts[-1][1] == n and chunk % 256 == 0 and parts[0][1] == parts[1][0]
 
