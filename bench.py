@@ -214,6 +214,11 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the vertex count (debugging)")
     ap.add_argument("--proposal", default="uniform", choices=["uniform", "dynamic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-cap-bytes", type=int, default=0, help="tuning experiments: mcmcb200_params.stageCapBytes (0 = automatic)")
+    ap.add_argument("--item-bits", type=int, default=0, help="tuning experiments: mcmcb200_params.itemBits (0 = automatic)")
+    ap.add_argument("--stage-buffers", type=int, default=0, help="tuning experiments: mcmcb200_params.stageBuffers (0 = automatic)")
+    ap.add_argument("--no-overlap", action="store_true", help="tuning experiments: the two passes of the blocked sweep back to back")
+    ap.add_argument("--quick", action="store_true", help="tuning experiments: kernel timing only (no e2e, no time-to-colouring, no CPU baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -247,8 +252,28 @@ def main():
     prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal,
                                 convergence=mc.CONVERGE_VERTICES if proposal == mc.PROPOSAL_UNIFORM else mc.CONVERGE_EDGES,
                                 seed=CHAIN_SEED)
-    ch = mc.Chain(params=prm, device=local_rank, flags=mc.FLAG_NO_EARLY_STOP, n_global=n, v_begin=0, v_end=n,
-                  device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz))
+    torch.cuda.synchronize()
+    t_create = time.perf_counter()
+    ch = mc.Chain(params=prm, device=local_rank, flags=mc.FLAG_NO_EARLY_STOP | (mc.FLAG_NO_OVERLAP if args.no_overlap else 0),
+                  n_global=n, v_begin=0, v_end=n, device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz),
+                  stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers)
+    ch.synchronize()
+    create_ms = 1e3 * (time.perf_counter() - t_create)   # mcmcb200_create: allocations + (blocked path) the layout build on the device
+    if args.quick:
+        for _ in range(args.warmup):
+            ch.init_colors(None); ch.sweep(1); ch.synchronize()
+        ms = []
+        for _ in range(args.steps):
+            ch.init_colors(None); torch.cuda.synchronize(); ch.sweep(1); ms.append(ch.last_sweep_ms())
+        ch.init_colors(None); ch.sweep(10); chain_ms = ch.last_sweep_ms() / 10.0
+        st = ch.status()
+        t = float(np.mean(ms))
+        print(json.dumps({"quick": True, "workload": args.workload, "ms_per_step": t, "min_ms": float(np.min(ms)), "frac": (8 * nnz + 12 * n + 4) / (t * 1e-3) / 1e9 / measured_peak()[0],
+                          "chain_ms_per_sweep": chain_ms, "kernel_mode": ch.kernel_mode(), "create_ms": create_ms, "nCol": nCol,
+                          "after_10": [int(st.conflictEdges), int(st.violatingVertices)],
+                          "tuning": [args.stage_cap_bytes, args.item_bits, args.stage_buffers, bool(args.no_overlap)], "lib": os.environ.get("MCMCB200_LIB", "")}))
+        ch.close()
+        return 0
 
     # ---- device-resident timing: `value` ----
     for _ in range(args.warmup):
@@ -324,7 +349,7 @@ def main():
         "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "maxDeg": max_deg, "proposal": args.proposal,
                    "step": "one sweep from the uniform random colouring (all vertices active)",
                    "l2": "inputs (CSR %.1f GB) larger than L2; no flush needed" % ((4 * nnz + 4 * n) / 1e9),
-                   "graph_gen_s": round(t_gen, 2)},
+                   "graph_gen_s": round(t_gen, 2), "create_ms": round(create_ms, 1)},
         "edges_per_sec": value * nnz / n,
         "chain_ms_per_sweep": chain_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -15,13 +15,17 @@
  *   - there is NO CPU fallback: without a CUDA device every entry point that needs one fails with
  *     MCMCB200_ENODEVICE.
  *
- * RNG contract (replaces GPURand/curandState, GPUutils/GPURandomizer.cu:8-13,85-96, and
- * std::default_random_engine, graph_coloring/coloringMCMC_CPU.cpp:53-55): stateless Philox4x32-10,
- *   counter = (global vertex id, purpose, sweep, 0), key = (seed & 0xffffffff, seed >> 32), draw = word 0;
+ * RNG contract, version 2 (replaces GPURand/curandState, GPUutils/GPURandomizer.cu:8-13,85-96, and
+ * std::default_random_engine, graph_coloring/coloringMCMC_CPU.cpp:53-55): stateless Philox4x32-10, ONE call per FOUR
+ * consecutive vertices:
+ *   counter = (global vertex id >> 2, purpose, sweep, 0), key = (seed & 0xffffffff, seed >> 32),
+ *   x = output word (global vertex id & 3);
  *   purpose 0: sweep draw, sweep = 1,2,...   UNIFORM: u = (x >> 8) * 2^-24 in [0,1)
  *                                           DYNAMIC: u = ((x >> 8) + 1) * 2^-24 in (0,1]
  *   purpose 1: initial colour, sweep = 0    colour = (x * nCol) >> 32
- * so trajectories do not depend on the GPU count or on the launch shape.
+ *   purpose 2: Luby cross-check, sweep = round
+ * so trajectories do not depend on the GPU count or on the launch shape.  (Version 1 spent a whole call per vertex and
+ * threw three of the four words away.)
  */
 #ifndef MCMCB200_H
 #define MCMCB200_H
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MCMCB200_ABI_VERSION 1
+#define MCMCB200_ABI_VERSION 2
 
 enum {
 	MCMCB200_OK          =  0,
@@ -64,12 +68,19 @@ typedef struct mcmcb200_params {
 	uint64_t seed;
 	int32_t  device;          /* CUDA device ordinal; -1 = current device */
 	uint32_t flags;           /* MCMCB200_FLAG_* */
+	/* tuning of the source-blocked sweep; 0 = chosen from the graph size (what every production caller passes) */
+	uint32_t stageCapBytes;   /* bytes of gathered neighbour colours a destination tile stages in shared memory */
+	uint32_t itemBits;        /* log2 of the entries of one pass-A work item */
+	uint32_t stageBuffers;    /* 1 or 2 stage buffers per pass-B CTA (2: the next tile is copied in while this one is computed) */
+	uint32_t reserved;        /* must be 0 */
 } mcmcb200_params;
 
 #define MCMCB200_FLAG_NO_FUSED_FINALIZE 1u  /* caller reduces the sweep counters across ranks itself (multi-GPU) */
 #define MCMCB200_FLAG_FORCE_DIRECT      4u  /* always use the single-pass direct-gather sweep kernel */
 #define MCMCB200_FLAG_FORCE_BLOCKED     8u  /* always use the source-blocked two-pass sweep (EUNSUPPORTED if a row exceeds a tile) */
 #define MCMCB200_FLAG_FORCE_BINNED     16u  /* always use the degree-binned direct sweep (the path of large skewed graphs) */
+#define MCMCB200_FLAG_NO_OVERLAP       32u  /* source-blocked sweep: run the two passes back to back even where they could overlap
+                                               (a device shared with other work; see mcmcb200_kernel_mode) */
 #define MCMCB200_FLAG_NO_EARLY_STOP     2u  /* sweeps keep advancing after C_t became proper (tape replay, benchmarking);
                                                mcmcb200_status still reports `converged` for the current colouring */
 
@@ -93,7 +104,8 @@ int mcmcb200_create(mcmcb200_handle ** out, uint32_t n, uint64_t nnz, const uint
 
 /* Vertex-partitioned variant (one handle per GPU/rank): this handle owns global vertices [vBegin, vEnd) of an
  * nGlobal-vertex graph.  cumulDegs holds vEnd-vBegin+1 entries (any base; differences are used), neighs the
- * owned rows only, with GLOBAL neighbour ids.  The colour array is replicated (nGlobal entries). */
+ * owned rows only, with GLOBAL neighbour ids.  The colour array is replicated (nGlobal entries).
+ * vBegin must be a multiple of 256 (the sweep moves the owned colours with 16-byte vector and bulk copies): EINVAL otherwise. */
 int mcmcb200_create_partition(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd,
                               const uint32_t * cumulDegs, const uint32_t * neighs, const mcmcb200_params * p);
 

@@ -20,6 +20,7 @@ FLAG_NO_EARLY_STOP = 2
 FLAG_FORCE_DIRECT = 4
 FLAG_FORCE_BLOCKED = 8
 FLAG_FORCE_BINNED = 16
+FLAG_NO_OVERLAP = 32
 VIEW_COLORS_CUR, VIEW_COLORS_NEXT, VIEW_COUNTERS = 0, 1, 2
 
 # every symbol include/mcmcb200.h declares (tests/test_capi_symbols.py checks the export table against the header)
@@ -40,7 +41,8 @@ class Params(C.Structure):
     _fields_ = [("nCol", C.c_uint32), ("epsilon", C.c_float), ("lambda_", C.c_float), ("numColorRatio", C.c_float),
                 ("ratioFreezed", C.c_float), ("tabooIteration", C.c_uint32), ("maxRip", C.c_uint32),
                 ("tailcut", C.c_uint32), ("proposal", C.c_uint32), ("convergence", C.c_uint32),
-                ("seed", C.c_uint64), ("device", C.c_int32), ("flags", C.c_uint32)]
+                ("seed", C.c_uint64), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("stageCapBytes", C.c_uint32), ("itemBits", C.c_uint32), ("stageBuffers", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Status(C.Structure):

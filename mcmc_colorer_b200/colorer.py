@@ -108,14 +108,15 @@ class Chain:
     """One Markov chain on one GPU: a mcmcb200_handle."""
 
     def __init__(self, cumulDegs=None, neighs=None, params: ColoringMCMCParams = None, device=-1, flags=0,
-                 n_global=None, v_begin=0, v_end=None, device_csr=None):
+                 n_global=None, v_begin=0, v_end=None, device_csr=None, stage_cap_bytes=0, item_bits=0, stage_buffers=0):
+        """stage_cap_bytes / item_bits / stage_buffers: tuning of the source-blocked sweep (mcmcb200_params), 0 = automatic."""
         self.L = capi.lib()
         self.params = params
         p = capi.Params(nCol=params.nCol, epsilon=params.epsilon, lambda_=params.lambda_,
                         numColorRatio=params.numColorRatio, ratioFreezed=params.ratioFreezed,
                         tabooIteration=params.tabooIteration, maxRip=params.maxRip, tailcut=int(params.tailcut),
                         proposal=params.proposal, convergence=params.convergence, seed=params.seed, device=device,
-                        flags=flags)
+                        flags=flags, stageCapBytes=stage_cap_bytes, itemBits=item_bits, stageBuffers=stage_buffers, reserved=0)
         self.h = C.c_void_p()
         if device_csr is not None:
             d_rowptr, d_neighs, nnz_local = device_csr

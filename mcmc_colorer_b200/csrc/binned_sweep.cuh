@@ -146,7 +146,7 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
 	const float eps = a.eps;
-	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
+	const float stayW = stay_weight<kDyn>(nCol, eps);
 	const uint64_t polLast = make_policy_evict_last();
 
 	for (uint32_t k = tid; k < nCol; k += kThreadsBin) s_hist[k] = 0;

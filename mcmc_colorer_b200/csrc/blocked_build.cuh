@@ -150,7 +150,8 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&d_words, sizeof(uint32_t) * ((size_t)numSlices + 1)));
 	BLK_CU(cudaMemsetAsync(d_words, 0, sizeof(uint32_t) * ((size_t)numSlices + 1), stream));
 	blk_sell_width_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, TV, numSlices, d_words); (*launches)++;
-	BLK_CU(cudaMalloc(&L.sliceOff, sizeof(uint32_t) * ((size_t)numSlices + 1)));
+	BLK_CU(cudaMalloc(&L.sliceOff, sizeof(uint32_t) * ((size_t)numSlices + 8)));    // (+ slack: pass B copies spt + 4 entries per tile)
+	BLK_CU(cudaMemsetAsync(L.sliceOff, 0, sizeof(uint32_t) * ((size_t)numSlices + 8), stream));
 	{
 		size_t need = 0;
 		cudaFree(d_cub); d_cub = nullptr;
@@ -164,7 +165,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&L.gidxS, sizeof(uint2) * ((size_t)sellTotal + 64)));
 	BLK_CU(cudaMemsetAsync(L.gidxS, 0, sizeof(uint2) * ((size_t)sellTotal + 64), stream));
 	blk_sell_fill_kernel<<<(numSlices * 32 + 255) / 256, 256, 0, stream>>>(d_rowptr, L.order, L.gidx, TV, numSlices, L.sliceOff, stageCap, L.gidxS); (*launches)++;
-	BLK_CU(cudaMalloc(&L.slotInfo, sizeof(uint32_t) * (size_t)numTiles * TV));
+	BLK_CU(cudaMalloc(&L.slotInfo, sizeof(uint16_t) * (size_t)numTiles * TV));
 	blk_sell_slotinfo_kernel<<<(unsigned)(((size_t)numTiles * TV + 255) / 256), 256, 0, stream>>>(d_rowptr, L.order, TV, numTiles, L.slotInfo); (*launches)++;
 	// ---- pass-A work items: (part, bucket) -> entry range; parts are stretches of tiles so that "part p finished" means the
 	//      stage images of its tiles are complete (pass B follows pass A part by part) ----
@@ -228,7 +229,7 @@ inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granDst = L.granDst; b.tileBase = L.tileBase;
-	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.tilePart = L.tilePart; b.sync = L.sync; b.dbgTimes = L.dbgTimes;
+	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.nbuf = L.nbuf; b.tilePart = L.tilePart; b.sync = L.sync; b.dbgTimes = L.dbgTimes;
 	return b;
 }
 

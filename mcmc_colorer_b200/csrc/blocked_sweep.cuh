@@ -73,7 +73,7 @@ struct BlockedLayout {
 	uint16_t * gidx = nullptr;       // [nnzLocal (+16)], CSR order (heavy rows and layout construction)
 	uint2 *    gidxS = nullptr;      // SELL-32-sigma copy of gidx for the light rows: slice-interleaved 4-entry words
 	uint16_t * order = nullptr;      // (construction only) [numTiles*TV] slot -> vertex (local to the tile), degree-descending inside each tile
-	uint32_t * slotInfo = nullptr;   // [numTiles*TV] slot -> (local vertex | degree << 16); 0xffff = empty slot.  Staged per tile by cp.async
+	uint16_t * slotInfo = nullptr;   // [numTiles*TV] slot -> local vertex (bits 0-12) | kSlotHeavy for rows longer than kLightMaxDeg; 0xffff = empty slot.  Staged per tile (TMA)
 	uint32_t * sliceOff = nullptr;   // [numTiles*TV/32 + 1] start of each 32-slot slice in gidxS (uint2 units)
 	uint32_t * granDst = nullptr;    // [totalPadded/4]  chunk-major granule (4 entries of srcLocal) -> its granule in the tile-major ecol
 	uint32_t * tileBase = nullptr;   // [numTiles+1]     first entry of each tile's stage image in ecol
@@ -83,6 +83,7 @@ struct BlockedLayout {
 	uint8_t * tilePart = nullptr;    // [numTiles] part of each tile
 	uint32_t * sync = nullptr;       // [2 + numParts]: next item, next tile, buckets finished per part  (... and pass B follows behind)
 	unsigned long long * dbgTimes = nullptr;
+	uint32_t  nbuf = 1;              // stage buffers per pass-B CTA: 2 = tile T+1 is copied in (TMA) while tile T is computed
 	size_t    smemA = 0, smemB = 0;
 	int       gridA = 0, gridB = 0;
 };
@@ -93,12 +94,12 @@ struct BlockedArgs {
 	void * ecol;
 	const uint16_t * gidx;
 	const uint2 * gidxS;
-	const uint32_t * slotInfo;
+	const uint16_t * slotInfo;
 	const uint32_t * sliceOff;
 	const uint32_t * granDst;
 	const uint32_t * tileBase;
 	const uint32_t * items;
-	uint32_t numItems, numParts;
+	uint32_t numItems, numParts, nbuf;
 	const uint8_t * tilePart;
 	unsigned long long * dbgTimes;   // (MCMCB200_TIMING builds only) [0] A first start [1] A last end [2] B first start [3] B last end [4] B wait ns
 	uint32_t * sync;
@@ -249,14 +250,15 @@ __global__ void blk_sell_width_kernel(const uint32_t * rowptr, const uint16_t * 
 	if (lane == 0) words[sl] = 32u * ((deg + 3u) >> 2);
 }
 
-// slotInfo[T*TV + s] = local vertex | degree << 16 (a tile's rows never exceed the stage, so the degree fits 16 bits)
-__global__ void blk_sell_slotinfo_kernel(const uint32_t * rowptr, const uint16_t * order, uint32_t TV, uint32_t numTiles, uint32_t * slotInfo) {
+// slotInfo[T*TV + s] = local vertex (TV <= 8192: 13 bits) | kSlotHeavy when the row is longer than kLightMaxDeg; 0xffff = empty
+constexpr uint32_t kSlotHeavy = 0x8000u, kSlotVertexMask = 0x1fffu;
+__global__ void blk_sell_slotinfo_kernel(const uint32_t * rowptr, const uint16_t * order, uint32_t TV, uint32_t numTiles, uint16_t * slotInfo) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= (size_t)numTiles * TV) return;
 	const uint32_t T = (uint32_t)(i / TV), o = order[i];
 	uint32_t info = 0xffffu;
-	if (o != 0xffffu) { const uint32_t v = T * TV + o; info = o | ((rowptr[v + 1] - rowptr[v]) << 16); }
-	slotInfo[i] = info;
+	if (o != 0xffffu) { const uint32_t v = T * TV + o; info = o | ((rowptr[v + 1] - rowptr[v] > (uint32_t)kLightMaxDeg) ? kSlotHeavy : 0u); }
+	slotInfo[i] = (uint16_t)info;
 }
 
 // Every row of a slice is filled to the slice's width: positions past the row's degree (and the whole row of an empty
@@ -315,7 +317,9 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	unsigned long long pol = 0ull;
 	if (MCMCB200_ST_LAST) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	__shared__ uint32_t s_item;
-	uint32_t have = 0xffffffffu;
+	__shared__ __align__(8) unsigned long long s_bar;           // mbarrier of the chunk copy
+	if (tid == 0) { mbar_init(&s_bar, 1u); mbar_fence_init(); }
+	uint32_t have = 0xffffffffu, loads = 0u;
 	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 0, global_ns());
 	for (;;) {
 		__syncthreads();                                      // everybody is done with the previous item (and its chunk)
@@ -325,13 +329,17 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 		if (it >= bl.numItems) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 1, global_ns()); break; }
 		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
 		if (b != have && beg < end) {
+			// the chunk's 64 Ki colours: ONE bulk copy issued by one thread (TMA engine, no LDG/STS through the LSU pipe);
 			// the colour buffers are padded by 64 Ki entries, so a whole chunk is always readable
-			const uint4 * src = reinterpret_cast<const uint4 *>(cur + (size_t)b * kChunkV);
-			uint4 * dst = reinterpret_cast<uint4 *>(chunk);
-			constexpr uint32_t nVec = kChunkV * sizeof(ColT) / 16;
-			for (uint32_t i = tid; i < nVec; i += kThreadsA) dst[i] = __ldg(src + i);
+			if (tid == 0) {
+				fence_proxy_async();                              // the previous chunk's shared-memory reads precede the async-proxy write
+				constexpr uint32_t bytes = kChunkV * (uint32_t)sizeof(ColT);
+				mbar_arrive_expect_tx(&s_bar, bytes);
+				tma_bulk_g2s(chunk, cur + (size_t)b * kChunkV, bytes, &s_bar);
+			}
+			mbar_wait(&s_bar, loads & 1u);
+			loads++;
 			have = b;
-			__syncthreads();
 		}
 		// one 4-entry granule per lane per step: a warp reads 256 contiguous bytes of local ids and 128 of destinations, and
 		// its store covers whole 32-byte sectors wherever a run spans them (full-sector first touches need no fill in L2)
@@ -366,56 +374,59 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// pass B: per destination tile -- stage the runs, permute to CSR order, then phases 2-3 of the direct kernel
+// pass B: per destination tile -- stage the tile (TMA), occupancy masks through the SELL index words, then phases 2-3 of the
+// direct kernel
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kWarpQueueCap = MCMCB200_QUEUE_CAP;     // deferred CDF walks parked per warp (drained 32 at a time, no CTA barrier; overflow walks inline)
 __host__ __device__ constexpr uint32_t warp_queue_cap(int W) { return W == 1 ? kWarpQueueCap : (kWarpQueueCap * 5u) / 6u; }   // 24- vs 32-byte entries
 constexpr uint32_t kHeavyCap = MCMCB200_HEAVY_CAP;        // warp-per-vertex work list per tile (overflow is handled by the owning thread)
 
-__host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t P, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
-	(void)P;
+// bytes of one stage buffer set (everything the TMA copies bring in for one tile); every part is a multiple of 16 bytes
+__host__ __device__ inline size_t blocked_buf_bytes(uint32_t TV, uint32_t stageCap, int colBytes) {
+	size_t b = 0;
+	b += sizeof(uint16_t) * (size_t)TV;                    // slotTab: slot -> vertex | heavy flag
+	b += sizeof(uint32_t) * (size_t)((TV >> 5) + 4);       // sliceTab: SELL slice starts of the tile
+	b += (size_t)colBytes * (size_t)(TV + 16);             // ownCol: the tile's current colours
+	b += (size_t)colBytes * (size_t)(stageCap + 16);       // stage; [stageCap, +16) = dummy colour
+	return (b + 15) & ~(size_t)15;
+}
+
+__host__ __device__ inline size_t blocked_smem_bytes_B(uint32_t nCol, uint32_t nbuf, uint32_t TV, uint32_t stageCap, int colBytes, int W) {
 	const int warps = ((W <= 2) ? MCMCB200_THREADS_B : 512) >> 5;
 	size_t b = 0;
-	b += sizeof(uint32_t) * (size_t)TV;            // s_slot: slot -> vertex | degree << 16
-	b += sizeof(uint32_t) * (size_t)((TV >> 5) + 4); // s_soff: SELL slice starts of the tile
 	b += sizeof(float) * (size_t)((nCol + 1 + 3) & ~3u);   // s_S
 	b += sizeof(float) * (size_t)((nCol + 3) & ~3u);       // s_dist (DYNAMIC) / free-colour weight table (UNIFORM)
 	b += sizeof(int) * (size_t)((nCol + 3) & ~3u);         // s_hist
 	b += sizeof(uint32_t) * 8;                             // s_ctl
+	b += sizeof(unsigned long long) * 4;                   // mbarriers (one per stage buffer) + tile ids
 	b += sizeof(uint32_t) * 128;                           // s_red (64 x u64)
 	b += sizeof(uint32_t) * 32;                            // per-warp queue counters
 	b += sizeof(uint16_t) * (size_t)kHeavyCap;             // s_heavy
 	b = (b + 15) & ~(size_t)15;
 	if (W <= 2) b += (size_t)warps * warp_queue_cap(W) * (8 * W + 16);   // per-warp walk queues (mask, lv/own, u/w)
-	b += (size_t)colBytes * (stageCap + 16);               // stage; [stageCap, +16) = dummy colour
-	b += (size_t)colBytes * (size_t)(TV + 16);             // s_new: the tile's new colours, written out coalesced (local + peers)
-	b += (size_t)colBytes * (size_t)(TV + 16);             // s_own: the tile's current colours
-	return (b + 15) & ~(size_t)15;
+	b = (b + 15) & ~(size_t)15;
+	b += sizeof(uint32_t) * (size_t)TV;                    // s_draw: the tile's Philox words (one call per 4 vertices)
+	b += (size_t)nbuf * (((size_t)colBytes * (TV + 16) + 15) & ~(size_t)15);   // s_new: the tile's new colours, written out coalesced (local + peers)
+	b += (size_t)nbuf * blocked_buf_bytes(TV, stageCap, colBytes);
+	return (b + 127) & ~(size_t)127;
 }
 
-__device__ __forceinline__ void cp_async_4(void * smem, const void * gmem) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_8(void * smem, const void * gmem) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_16(void * smem, const void * gmem) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-// pass B waits until pass A has delivered all P buckets of the tile's part.  Bounded: if the producer kernel never shows up
-// (launch failure) the sweep flags an error instead of hanging the device.
-__device__ __forceinline__ void wait_part_ready(const BlockedArgs & bl, uint32_t T, DevState * st) {
+// pass B waits until pass A has delivered all P buckets of the tile's part.  Bounded: if the producer never shows up (it was
+// not co-scheduled: another tenant on the device, a profiler serialising kernels the wrong way round) the sweep is ABORTED --
+// errorFlag 2, no tile of this CTA is processed or written, the finalize step does not advance, and every host call that
+// reads results returns MCMCB200_ECUDA (mcmcb200_sweep then retries the sweep with the two passes back to back).
+__device__ __forceinline__ bool wait_part_ready(const BlockedArgs & bl, uint32_t T, DevState * st) {
 	const uint32_t * flag = bl.sync + 2 + bl.tilePart[T];
 	uint32_t v;
 	long long t0 = 0;
 	for (uint32_t spins = 0;; ++spins) {
 		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-		if (v >= bl.P) return;
+		if (v >= bl.P) return true;
 		if (spins == 0) t0 = clock64();
-		else if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000ll) { st->errorFlag = 2; return; }   // ~3 s
+		else if ((spins & 255u) == 0) {
+			if (*reinterpret_cast<volatile uint32_t *>(&st->errorFlag) == 2u) return false;      // another CTA gave up already
+			if (clock64() - t0 > 4000000000ll) { st->errorFlag = 2u; __threadfence(); return false; }   // ~2 s
+		}
 		__nanosleep(100);
 	}
 }
@@ -429,63 +440,67 @@ __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 // shared-memory views of one pass-B CTA
 template <int W, typename ColT>
 struct PassBShared {
-	uint32_t * slotTab; uint32_t * sliceTab; float * S; float * dist; int * hist; uint32_t * ctl; unsigned long long * red;
-	uint32_t * qcnt; uint16_t * heavy; unsigned char * queues; ColT * stageBuf; ColT * newCol; ColT * ownCol;
-	uint32_t stageStride, tvStride, soffStride;
-	__device__ __forceinline__ PassBShared(unsigned char * raw, uint32_t nCol, uint32_t TV, uint32_t stageCap) {
-		const uint32_t spt = TV >> 5;
-		slotTab = reinterpret_cast<uint32_t *>(raw);
-		sliceTab = slotTab + TV;
-		soffStride = spt + 4;
-		S = reinterpret_cast<float *>(sliceTab + soffStride);
+	float * S; float * dist; int * hist; uint32_t * ctl; unsigned long long * bars; uint32_t * tileOf; unsigned long long * red;
+	uint32_t * qcnt; uint16_t * heavy; unsigned char * queues; uint32_t * draw; unsigned char * newBase; unsigned char * bufBase;
+	uint32_t newBytes, bufBytes, TV, stageCap, soffStride;
+	__device__ __forceinline__ PassBShared(unsigned char * raw, uint32_t nCol, uint32_t nbuf, uint32_t TV_, uint32_t stageCap_) {
+		TV = TV_; stageCap = stageCap_;
+		soffStride = (TV >> 5) + 4;
+		S = reinterpret_cast<float *>(raw);
 		dist = S + ((nCol + 1 + 3) & ~3u);
 		hist = reinterpret_cast<int *>(dist + ((nCol + 3) & ~3u));
 		ctl = reinterpret_cast<uint32_t *>(hist + ((nCol + 3) & ~3u));
-		red = reinterpret_cast<unsigned long long *>(ctl + 8);
-		qcnt = ctl + 8 + 128;
-		heavy = reinterpret_cast<uint16_t *>(ctl + 8 + 160);
+		bars = reinterpret_cast<unsigned long long *>(ctl + 8);
+		tileOf = reinterpret_cast<uint32_t *>(bars + 2);
+		red = bars + 4;
+		qcnt = reinterpret_cast<uint32_t *>(red + 64);
+		heavy = reinterpret_cast<uint16_t *>(qcnt + 32);
 		size_t off = (size_t)(reinterpret_cast<unsigned char *>(heavy + kHeavyCap) - raw);
 		off = (off + 15) & ~(size_t)15;
 		queues = raw + off;
 		if (W <= 2) off += (size_t)(PassB<W>::threads / 32) * warp_queue_cap(W) * (8 * W + 16);
-		stageBuf = reinterpret_cast<ColT *>(raw + off);
-		stageStride = stageCap + 16;
-		tvStride = TV + 16;
-		newCol = stageBuf + stageStride;
-		ownCol = newCol + tvStride;
+		off = (off + 15) & ~(size_t)15;
+		draw = reinterpret_cast<uint32_t *>(raw + off);
+		off += sizeof(uint32_t) * (size_t)TV;
+		newBytes = (uint32_t)((sizeof(ColT) * (size_t)(TV + 16) + 15) & ~(size_t)15);
+		newBase = raw + off;
+		off += (size_t)nbuf * newBytes;
+		bufBytes = (uint32_t)blocked_buf_bytes(TV, stageCap, (int)sizeof(ColT));
+		bufBase = raw + off;
 	}
+	__device__ __forceinline__ uint16_t * slotTab(uint32_t buf) const { return reinterpret_cast<uint16_t *>(bufBase + (size_t)buf * bufBytes); }
+	__device__ __forceinline__ uint32_t * sliceTab(uint32_t buf) const { return reinterpret_cast<uint32_t *>(slotTab(buf) + TV); }
+	__device__ __forceinline__ ColT * ownCol(uint32_t buf) const { return reinterpret_cast<ColT *>(sliceTab(buf) + soffStride); }
+	__device__ __forceinline__ ColT * stageBuf(uint32_t buf) const { return ownCol(buf) + (TV + 16); }
+	__device__ __forceinline__ ColT * newCol(uint32_t buf) const { return reinterpret_cast<ColT *>(newBase + (size_t)buf * newBytes); }
 };
 
-// cp.async copies of everything tile T needs, spread over nThr threads (this thread = thr).
-// tb, te = the tile's entry range in ecol (bl.tileBase[T], bl.tileBase[T+1]).
+// ONE thread: four bulk copies (TMA engine) bring in everything tile T needs -- slot table, slice starts, current colours and
+// the gathered neighbour colours (pass A left the tile's whole stage image contiguous in ecol) -- and complete on `bar`.
 template <int W, typename ColT>
-__device__ __forceinline__ void stage_tile(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const ColT * cur,
-                                           uint32_t T, uint32_t tb, uint32_t te, uint32_t thr, uint32_t nThr) {
+__device__ __forceinline__ void stage_tile_tma(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const ColT * cur,
+                                               uint32_t T, uint32_t buf, unsigned long long * bar, uint64_t polFirst) {
 	const uint32_t TV = bl.TV, spt = TV >> 5;
 	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
-	uint32_t * sl = sm.slotTab;
-	const uint4 * gsl = reinterpret_cast<const uint4 *>(bl.slotInfo + (size_t)T * TV);
-	for (uint32_t i = thr; i < (TV >> 2); i += nThr) cp_async_16(sl + 4u * i, gsl + i);
-	uint32_t * so = sm.sliceTab;
-	for (uint32_t i = thr; i <= spt; i += nThr) cp_async_4(so + i, bl.sliceOff + (size_t)T * spt + i);
-	unsigned char * ow = reinterpret_cast<unsigned char *>(sm.ownCol);
-	const unsigned char * cb = reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT);
-	const uint32_t n16 = (nv * (uint32_t)sizeof(ColT) + 15u) >> 4;          // (colour arrays are padded; tiles start 256-aligned)
-	for (uint32_t i = thr; i < n16; i += nThr) cp_async_16(ow + 16u * i, cb + 16u * i);
-	// the gathered neighbour colours: pass A left the tile's whole stage image contiguous in ecol; copy it from the 16-byte
-	// boundary below its first entry (the static indices in gidx / gidxS include that offset)
+	const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
+	const uint32_t bytesSlot = TV * (uint32_t)sizeof(uint16_t);
+	const uint32_t bytesSoff = (spt + 4u) * (uint32_t)sizeof(uint32_t);     // spt + 1 used; the table has slack behind its end
+	const uint32_t bytesOwn = (nv * (uint32_t)sizeof(ColT) + 15u) & ~15u;   // (colour arrays are padded; tiles start 256-aligned)
+	// copy the stage image from the 16-byte boundary below its first entry (the static indices in gidx / gidxS include that offset)
 	constexpr uint32_t alignE = 16u / (uint32_t)sizeof(ColT);
 	const uint32_t a0 = tb & ~(alignE - 1u);
-	const uint32_t nC = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) >> 4;
-	const unsigned char * eb = reinterpret_cast<const unsigned char *>(static_cast<const ColT *>(bl.ecol) + a0);
-	unsigned char * stg = reinterpret_cast<unsigned char *>(sm.stageBuf);
-	for (uint32_t i = thr; i < nC; i += nThr) cp_async_16(stg + 16u * i, eb + 16u * i);
+	const uint32_t bytesStage = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) & ~15u;
+	mbar_arrive_expect_tx(bar, bytesSlot + bytesSoff + bytesOwn + bytesStage);
+	tma_bulk_g2s(sm.slotTab(buf), bl.slotInfo + (size_t)T * TV, bytesSlot, bar);
+	tma_bulk_g2s(sm.sliceTab(buf), bl.sliceOff + (size_t)T * spt, bytesSoff, bar);
+	tma_bulk_g2s(sm.ownCol(buf), reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT), bytesOwn, bar);
+	if (bytesStage) tma_bulk_g2s_hint(sm.stageBuf(buf), static_cast<const ColT *>(bl.ecol) + a0, bytesStage, bar, polFirst);   // read once: evict_first
 }
 
 // per-tile views handed to the slot / heavy-list routines
 template <int W, typename ColT>
 struct TileView {
-	const uint32_t * slot; const uint32_t * soff; const ColT * own; const ColT * stage; ColT * snew; uint32_t * heavyCount;
+	const uint16_t * slot; const uint32_t * soff; const ColT * own; const ColT * stage; ColT * snew; uint32_t * heavyCount; const uint32_t * draw;
 	uint32_t v0, nv;
 };
 
@@ -502,10 +517,10 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 	const uint32_t TV = bl.TV;
 	const ColT * stage = tv.stage;
 	const bool inTile = slot < TV;                            // warp-uniform (TV is a multiple of 32)
-	const uint32_t info = inTile ? tv.slot[slot] : 0xffffu;
-	const uint32_t lv = info & 0xffffu, deg = info >> 16;
-	const bool valid = lv != 0xffffu;
-	bool light = valid && deg <= (uint32_t)kLightMaxDeg;
+	const uint32_t info = inTile ? (uint32_t)tv.slot[slot] : 0xffffu;
+	const bool valid = info != 0xffffu;
+	const uint32_t lv = info & kSlotVertexMask;
+	bool light = valid && !(info & kSlotHeavy);
 	bool inlineHeavy = false;
 	if (valid && !light) {                                    // warp-per-vertex list; if it is full the thread does the row itself
 		const uint32_t hi = atomicAdd(tv.heavyCount, 1u);
@@ -529,7 +544,8 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 		// SELL slice: word j of the 32 rows is one contiguous 256-byte load for the warp
 		const uint32_t so0 = tv.soff[slot >> 5], nW = (tv.soff[(slot >> 5) + 1] - so0) >> 5;
 		const uint2 * gq = bl.gidxS + so0 + lane;
-		const uint32_t degL = light ? deg : 0u;               // (only the kPad == false instance tests it)
+		uint32_t degL = 0u;                                   // (only the kPad == false instance tests it)
+		if (!kPad && light) degL = a.rowptr[tv.v0 + lv + 1] - a.rowptr[tv.v0 + lv];
 #ifndef MCMCB200_MASK_PF
 #define MCMCB200_MASK_PF 6
 #endif
@@ -564,13 +580,13 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 		}
 	}
 	if (inlineHeavy) {                                        // overflow of the heavy list: plain CSR-order indices
-		const uint32_t myBeg = a.rowptr[tv.v0 + lv];
+		const uint32_t myBeg = a.rowptr[tv.v0 + lv], deg = a.rowptr[tv.v0 + lv + 1] - myBeg;
 		for (uint32_t i = 0; i < deg; ++i) addc(__ldg(bl.gidx + myBeg + i));
 		light = true;
 	}
 	if (light)
 		commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + tv.v0 + lv, tv.v0 + lv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
-		                             wq, tv.snew, tv.v0);
+		                             wq, tv.snew, tv.v0, tv.draw);
 	if (wq != nullptr) {                                      // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
 		__syncwarp();
 		const uint32_t qn = min(*wq->count, wq->cap);
@@ -608,7 +624,7 @@ __device__ __forceinline__ void sweep_heavy_list(const SweepArgs & a, const Bloc
 		same = __reduce_add_sync(0xffffffffu, same);
 		if (lane == 0)
 			commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, tv.v0 + hv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
-			                             nullptr, tv.snew, tv.v0);
+			                             nullptr, tv.snew, tv.v0, tv.draw);
 	}
 }
 
@@ -634,8 +650,8 @@ __global__ void __launch_bounds__(PassB<W>::threads) __maxnreg__(PassB<W>::maxRe
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int kT = PassB<W>::threads;
-	const uint32_t nCol = a.nCol, TV = bl.TV;
-	const PassBShared<W, ColT> sm(smem_raw, nCol, TV, bl.stageCap);
+	const uint32_t nCol = a.nCol, TV = bl.TV, nbuf = bl.nbuf;
+	const PassBShared<W, ColT> sm(smem_raw, nCol, nbuf, TV, bl.stageCap);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr bool useQueue = W <= 2;
 	WalkQueue<W> wq{};
@@ -656,39 +672,59 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	                                                 : static_cast<const ColT *>(a.colors[t & 1]);
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
 	const float eps = a.eps;
-	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
+	const float stayW = stay_weight<kDyn>(nCol, eps);
+	const uint64_t polFirst = make_policy_evict_first();
 
 	for (uint32_t k = tid; k < nCol; k += kT) sm.hist[k] = 0;
 	if (tid == 0) {
 		float s = 0.0f; sm.S[0] = 0.0f;
 		for (uint32_t k = 0; k < nCol; ++k) { s = __fadd_rn(s, eps); sm.S[k + 1] = s; }
 		sm.ctl[1] = 0u;                                       // heavy-list counter
+		for (uint32_t b = 0; b < nbuf; ++b) mbar_init(sm.bars + b, 1u);
+		mbar_fence_init();
 	}
-	if (tid < 16) sm.stageBuf[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
+	if (tid < 16) for (uint32_t b = 0; b < nbuf; ++b) sm.stageBuf(b)[bl.stageCap + tid] = (ColT)~(ColT)0;   // the dummy colour of the padded SELL rows
 	if (!a.countOnly) fill_proposal_table<kDyn>(a, t, sm.dist, tid, kT);
 	unsigned long long accDirected = 0ull, accViol = 0ull;
 	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 2, global_ns());
 	__syncthreads();
 
-	for (;;) {
-		if (tid == 0) {                                       // tiles in ascending order: the order pass A completes them in
-			const uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
-			if (MCMCB200_TIMING) { const unsigned long long w0 = global_ns(); if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st); atomicAdd(bl.dbgTimes + 4, global_ns() - w0); }
-			else if (Tn < bl.numTiles) wait_part_ready(bl, Tn, st);
-			sm.ctl[4] = Tn;
+	// thread 0 is the producer: it takes the next tile (ascending order: the order pass A completes them in), waits until pass A
+	// has delivered the tile's part and issues the bulk copies into stage buffer `buf`; the CTA consumes the buffers in turn.
+	auto produce = [&](uint32_t buf) {
+		uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
+		if (Tn < bl.numTiles) {
+			bool ok;
+			if (MCMCB200_TIMING) { const unsigned long long w0 = global_ns(); ok = wait_part_ready(bl, Tn, st); atomicAdd(bl.dbgTimes + 4, global_ns() - w0); }
+			else ok = wait_part_ready(bl, Tn, st);
+			if (!ok) Tn = 0xffffffffu;                            // producer missing: abort (see wait_part_ready)
 		}
-		__syncthreads();
-		const uint32_t T = sm.ctl[4];
+		sm.tileOf[buf] = Tn;
+		if (Tn < bl.numTiles) {
+			fence_proxy_async();                                  // pass A's stores (acquired above) and this CTA's reads of the buffer precede the copies
+			stage_tile_tma<W, ColT>(a, bl, sm, cur, Tn, buf, sm.bars + buf, polFirst);
+		} else mbar_arrive(sm.bars + buf);                        // nothing to copy: complete the phase so that the consumers see tileOf
+	};
+	if (tid == 0) for (uint32_t b = 0; b < nbuf; ++b) produce(b);
+
+	for (uint32_t it = 0;; ++it) {
+		const uint32_t buf = (nbuf == 2u) ? (it & 1u) : 0u;
+		mbar_wait(sm.bars + buf, ((nbuf == 2u) ? (it >> 1) : it) & 1u);      // the tile is staged
+		const uint32_t T = sm.tileOf[buf];
 		if (T >= bl.numTiles) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 3, global_ns()); break; }
-		const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
-		stage_tile<W, ColT>(a, bl, sm, cur, T, tb, te, (uint32_t)tid, (uint32_t)kT);
-		cp_async_commit_wait_all();
-		__syncthreads();                                      // the tile is staged
 		TileView<W, ColT> tv;
 		tv.v0 = T * TV; tv.nv = min(TV, a.nLocal - tv.v0);
-		tv.slot = sm.slotTab; tv.soff = sm.sliceTab; tv.own = sm.ownCol; tv.stage = sm.stageBuf; tv.snew = sm.newCol; tv.heavyCount = sm.ctl + 1;
+		tv.slot = sm.slotTab(buf); tv.soff = sm.sliceTab(buf); tv.own = sm.ownCol(buf); tv.stage = sm.stageBuf(buf); tv.snew = sm.newCol(buf);
+		tv.heavyCount = sm.ctl + 1;
+		tv.draw = (a.tape || a.countOnly) ? nullptr : sm.draw;
+		// the tile's draws: one Philox4x32-10 call per 4 consecutive vertices (tiles start 256-aligned), parked in shared memory
+		if (tv.draw) {
+			const uint32_t g0 = (a.vBegin + tv.v0) >> 2;
+			uint4 * d4 = reinterpret_cast<uint4 *>(sm.draw);
+			for (uint32_t i = tid; i < ((tv.nv + 3u) >> 2); i += kT) d4[i] = philox4(a.seed, t + 1u, g0 + i, 0u);
+		}
 		if (useQueue && lane == 0) *wq.count = 0u;
-		__syncwarp();
+		__syncthreads();                                      // draws are in; the previous tile's write-out has left s_new (nbuf == 1)
 		for (uint32_t g = 0; g < tv.nv; g += kT)
 			sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
 		if (useQueue) {
@@ -700,8 +736,8 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		__syncthreads();
 		const uint32_t nHeavy = min(sm.ctl[1], kHeavyCap);
 		sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
-		__syncthreads();                                      // the tile is finished: everybody has read the heavy list, s_new is complete
-		if (tid == 0) sm.ctl[1] = 0u;
+		__syncthreads();                                      // the tile is finished: everybody has read the heavy list and the stage buffer, s_new is complete
+		if (tid == 0) { sm.ctl[1] = 0u; produce(buf); }       // refill this buffer (nbuf == 2: the other one is already in flight)
 		if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kT);
 	}
 

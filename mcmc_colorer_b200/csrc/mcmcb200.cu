@@ -15,7 +15,7 @@
 
 using namespace mcmcb200;
 
-static_assert(sizeof(mcmcb200_params) == 56, "ABI: mcmcb200_params layout (mirrored by capi.Params)");
+static_assert(sizeof(mcmcb200_params) == 72, "ABI: mcmcb200_params layout (mirrored by capi.Params)");
 static_assert(sizeof(mcmcb200_status_t) == 40, "ABI: mcmcb200_status_t layout (mirrored by capi.Status)");
 
 namespace {
@@ -129,7 +129,7 @@ template <int W, typename ColT>
 cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	BlockedLayout & L = h->bl;
 	L.smemA = (size_t)kChunkV * sizeof(ColT);
-	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.P, L.TV, L.stageCap, (int)sizeof(ColT), W);
+	L.smemB = blocked_smem_bytes_B(h->p.nCol, L.nbuf, L.TV, L.stageCap, (int)sizeof(ColT), W);
 	int dev = 0, optin = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -146,8 +146,6 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	if (e != cudaSuccess) return e;
 	int ob = ob0 < ob1 ? ob0 : ob1;
 	if (oa < 1 || ob < 1) { L.valid = false; return cudaSuccess; }
-	if (const char * env = getenv("MCMCB200_B_PER_SM")) ob = std::max(1, std::min(ob, atoi(env)));   // experiments
-	if (const char * env = getenv("MCMCB200_A_PER_SM")) oa = std::max(1, std::min(oa, atoi(env)));
 	L.gridB = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numTiles, (uint32_t)(ob * h->smCount)));
 	// Overlap: pass A is DRAM bound, pass B issue bound.  With `ob` pass-B CTAs resident an SM must still have room
 	// (shared memory, registers, threads) for at least one pass-A CTA -- otherwise a grid of waiting B CTAs could keep A out.
@@ -164,7 +162,7 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	const long freeRegs = (long)regsSM - (long)ob * regsOf(fb.numRegs, PassB<W>::threads);
 	const long freeThr = (long)thrSM - (long)ob * PassB<W>::threads;
 	long aFit = std::min<long>(freeSmem / (long)(L.smemA + 1024), std::min<long>(freeRegs / regsOf(fa.numRegs, kThreadsA), freeThr / kThreadsA));
-	h->overlap = aFit >= 1 && getenv("MCMCB200_NO_OVERLAP") == nullptr;
+	h->overlap = aFit >= 1 && !(h->p.flags & MCMCB200_FLAG_NO_OVERLAP);
 	if (h->overlap) {
 		L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(std::min<long>(aFit, oa) * h->smCount)));
 		if (!h->streamA) e = cudaStreamCreateWithFlags(&h->streamA, cudaStreamNonBlocking);
@@ -272,6 +270,7 @@ int check_params(const mcmcb200_params * p, uint32_t nGlobal) {
 	if (p->nCol > 64u * kMaxColWords) return MCMCB200_EUNSUPPORTED;   // wide-palette path: not in this build
 	if (p->tabooIteration > 65535u) return MCMCB200_EUNSUPPORTED;
 	if (p->proposal == MCMCB200_PROPOSAL_DYNAMIC && p->nCol < 2) return MCMCB200_EINVAL;
+	if (p->reserved != 0u || p->stageBuffers > 2u || (p->itemBits && (p->itemBits < 12u || p->itemBits > 24u))) return MCMCB200_EINVAL;
 	return MCMCB200_OK;
 }
 
@@ -370,9 +369,40 @@ int compute_class_sizes(mcmcb200_handle * h, const void * colors, unsigned long 
 	return MCMCB200_OK;
 }
 
-int read_state(mcmcb200_handle * h, DevState * s) {
+int read_state_raw(mcmcb200_handle * h, DevState * s) {
 	CU(cudaMemcpyAsync(s, h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a);
+SweepArgs make_args(mcmcb200_handle * h);
+
+// Every host call that reads results goes through here.  If an overlapped blocked sweep was aborted on the device (pass B timed
+// out waiting for pass A: the two kernels were not co-scheduled -- another tenant on the GPU, MPS, a tool serialising launches)
+// nothing of it was committed; the handle drops to the back-to-back mode for good and the lost sweeps are run again.
+int read_state(mcmcb200_handle * h, DevState * s) {
+	int rc = read_state_raw(h, s); if (rc) return rc;
+	if (s->errorFlag != 2u) return MCMCB200_OK;
+	if (!h->overlap) {
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "blocked sweep aborted on the device (sweep %u)", s->sweep);
+		return MCMCB200_ECUDA;
+	}
+	h->overlap = false;
+	if (h->streamA) CU(cudaStreamSynchronize(h->streamA));
+	if (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) {       // multi-GPU: the caller drives the exchange, it has to redo the sweep itself
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "overlapped blocked sweep aborted on the device (sweep %u); handle switched to back-to-back passes", s->sweep);
+		return MCMCB200_ECUDA;
+	}
+	const uint32_t zero = 0;
+	CU(cudaMemcpyAsync(&h->d_state->errorFlag, &zero, sizeof(zero), cudaMemcpyHostToDevice, h->stream));
+	const uint32_t lost = (s->convergedAt < 0 && h->hostSweepUpper > s->sweep) ? h->hostSweepUpper - s->sweep : 0u;
+	for (uint32_t i = 0; i < lost; ++i) { SweepArgs a = make_args(h); CU(launch_sweep(h, a)); }
+	rc = read_state_raw(h, s); if (rc) return rc;
+	if (s->errorFlag == 2u) {
+		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "blocked sweep aborted on the device (sweep %u)", s->sweep);
+		return MCMCB200_ECUDA;
+	}
 	return MCMCB200_OK;
 }
 
@@ -384,6 +414,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 	int rc = check_params(p, nGlobal); if (rc) return rc;
 	if (vBegin > vEnd || vEnd > nGlobal || !cumulDegs || (nnzLocal && !neighs)) return MCMCB200_EINVAL;
 	if (nnzLocal >= 0xfffffff0ull) return MCMCB200_EUNSUPPORTED;   // 32-bit CSR offsets, like the reference (graph.h:19-20)
+	if (vBegin & 255u) return MCMCB200_EINVAL;                      // owned colours move as 16-byte vectors / bulk copies (mcmcb200.h)
 	int dev = 0, sms = 0;
 	rc = select_device(p, &dev, &sms); if (rc) return rc;
 	mcmcb200_handle * h = new (std::nothrow) mcmcb200_handle;
@@ -431,13 +462,16 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			// (64 KiB chunk) share an SM and the two passes overlap; smaller ones (fill/drain of the A->B pipeline would eat the
 			// gain; measured on config 5): the largest stage the 16-bit positions allow, passes back to back
 			uint32_t capBytes = nnzLocal >= (1ull << 29) ? 45056u : 65504u;
+			uint32_t nbuf = 1u;
 			// pass-A work item: ~2^18 entries of one bucket when the passes overlap (fewer reloads of the 64 KiB chunk; measured
 			// 4.20 vs 4.28 ms on config 3), 2^17 back to back (pass A alone: 2.03 vs 2.23 ms at 2^19)
 			uint32_t itemEntries = nnzLocal >= (1ull << 29) ? (1u << 18) : (1u << 17);
-			if (const char * env = getenv("MCMCB200_ITEM_BITS")) itemEntries = 1u << std::max(12, std::min(24, atoi(env)));
-			if (const char * env = getenv("MCMCB200_STAGE_CAP_BYTES")) capBytes = (uint32_t)strtoul(env, nullptr, 10);
+			if (p->itemBits) itemEntries = 1u << p->itemBits;
+			if (p->stageCapBytes) capBytes = p->stageCapBytes;
+			if (p->stageBuffers) nbuf = p->stageBuffers;
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes, itemEntries,
 			                                     h->stream, &h->launches);
+			h->bl.nbuf = nbuf;
 			if (e == cudaSuccess && h->bl.valid) e = configure_blocked(h);
 			if (e == cudaSuccess && !h->bl.valid) free_blocked_layout(h->bl);
 			if (e != cudaSuccess) return fail(cuda_fail(e, "build_blocked_layout", __LINE__));
@@ -576,7 +610,7 @@ int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors) {
 	if (colors) {
 		rc = narrow_into(h, colors, h->d_colors[0]); if (rc) return rc;
 	} else {
-		const uint32_t n = h->nGlobal, blocks = (n + 255) / 256;
+		const uint32_t n = h->nGlobal, blocks = ((n + 3) / 4 + 255) / 256;
 		if (h->colBytes == 1) init_colors_philox_kernel<uint8_t><<<blocks, 256, 0, h->stream>>>((uint8_t *)h->d_colors[0], n, h->p.nCol, h->p.seed);
 		else init_colors_philox_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>((uint16_t *)h->d_colors[0], n, h->p.nCol, h->p.seed);
 		h->launches++;
@@ -692,10 +726,6 @@ int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
 	CU(cudaSetDevice(h->device));
 	DevState s;
 	int rc = read_state(h, &s); if (rc) return rc;
-	if (s.errorFlag == 2u) {                                  // wait_part_ready gave up: pass B never saw pass A's output
-		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "blocked sweep: pass B timed out waiting for pass A (sweep %u)", s.sweep);
-		return MCMCB200_ECUDA;
-	}
 	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
 	if (s.countsSweep != s.sweep) {
 		if (split) {

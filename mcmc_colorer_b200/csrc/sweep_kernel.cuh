@@ -105,7 +105,12 @@ __device__ __forceinline__ void finalize_sweep_device(const SweepArgs & a) {
 	const unsigned long long directed = __ldcg(a.scratch + 0);
 	const unsigned long long viol = __ldcg(a.scratch + 1);
 	const uint32_t t = st->sweep;
-	if (a.countOut != nullptr) {                       // count-only on an arbitrary colouring
+	// errorFlag 2: the blocked sweep was aborted (pass B never saw pass A's output, blocked_sweep.cuh wait_part_ready) -- nothing
+	// of this launch counts: no history entry, no class sizes, the sweep index does not advance.  The host retries (read_state).
+	const bool aborted = *reinterpret_cast<volatile uint32_t *>(&st->errorFlag) == 2u;
+	if (aborted) {
+		// fall through to the scratch reset only
+	} else if (a.countOut != nullptr) {                // count-only on an arbitrary colouring
 		if (threadIdx.x == 0) { a.countOut[0] = directed; a.countOut[1] = viol; }
 	} else {
 		const unsigned long long metric = (st->convergence == 0) ? viol : (directed >> 1);
@@ -155,6 +160,17 @@ __device__ __forceinline__ void fill_proposal_table(const SweepArgs & a, uint32_
 		for (uint32_t k = tid; k < nCol; k += nThreads)     // Zn = k occupied, Zp = nCol - k >= 1 free
 			s_dist[k] = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(a.eps, __uint2float_rn(k))), __uint2float_rn(nCol - k));
 	}
+}
+
+// weight of the own colour in the "stay" distribution, 1 - (nCol-1)*eps.
+//   UNIFORM follows the CPU colourer's x86-64 build: product and difference are two roundings (coloringMCMC_CPU.cpp:406,474);
+//   DYNAMIC follows the reference GPU kernel as nvcc compiles it (default -fmad=true): ONE fused multiply-add,
+//   `FFMA R, -(float)(nCol-1), eps, 1` in the SASS of selectStarColoringBalanceDynamic (coloringMCMC_balance.cu:88,132) built
+//   for sm_100a with the reference's flags; the GPU test suite replays that kernel against this one.  The two differ for 17 palettes >= 9499 colours at eps = 1e-8 and from 89 colours on at eps = 1e-4.
+template <bool kDyn>
+__device__ __forceinline__ float stay_weight(uint32_t nCol, float eps) {
+	const float k = __uint2float_rn(nCol - 1u);
+	return kDyn ? __fmaf_rn(-k, eps, 1.0f) : __fsub_rn(1.0f, __fmul_rn(k, eps));
 }
 
 // "stay" distribution (all colours eps, own colour 1-(nCol-1)eps) when the draw fell into an epsilon tail:
@@ -253,7 +269,8 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
                                               uint32_t myOwn, const unsigned long long (&m)[W], uint32_t same,
                                               const float * s_S, const float * s_dist, int * s_hist, float stayW,
                                               unsigned long long & accDirected, unsigned long long & accViol,
-                                              const WalkQueue<W> * queue = nullptr, ColT * nxtTile = nullptr, uint32_t tileV0 = 0) {
+                                              const WalkQueue<W> * queue = nullptr, ColT * nxtTile = nullptr, uint32_t tileV0 = 0,
+                                              const uint32_t * drawTab = nullptr) {
 	constexpr bool isDyn = kDyn;
 	const uint32_t nCol = a.nCol;
 	const float eps = a.eps;
@@ -282,6 +299,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 		} else {
 			float u;
 			if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
+			else if (drawTab) u = draw_to_uniform(drawTab[lv - tileV0], isDyn);      // the tile's Philox words, one call per 4 vertices
 			else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
 			const bool stay = !viol || Zp == 0u;              // :472-478 / :402-411
 			if (stay) {
@@ -402,7 +420,7 @@ sweep_kernel(const SweepArgs a) {
 	ColT * __restrict__ nxt = static_cast<ColT *>(a.colors[(t + 1) & 1]);
 	const float eps = a.eps;
 	// "stay" weight 1 - (nCol-1)*eps, two roundings like the reference's x86 build (coloringMCMC_CPU.cpp:406,474)
-	const float stayW = __fsub_rn(1.0f, __fmul_rn(__uint2float_rn(nCol - 1u), eps));
+	const float stayW = stay_weight<kDyn>(nCol, eps);
 	const uint64_t polLast = make_policy_evict_last();
 
 	// ---- prologue: per-CTA tables ----
@@ -661,10 +679,15 @@ sweep_kernel(const SweepArgs a) {
 // ---------------------------------------------------------------------------------------------
 template <typename ColT>
 __global__ void init_colors_philox_kernel(ColT * colors, uint32_t n, uint32_t nCol, uint64_t seed) {
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;      // one Philox call = the colours of vertices 4g .. 4g+3
+	const uint32_t v = 4u * g;
 	if (v >= n) return;
 	// uniform colour in [0,nCol) -- replaces initColoring (coloringMCMC_utils.cu:24-33) without its nCol overshoot
-	colors[v] = (ColT)__umulhi(philox_draw(seed, 0u, v, 1u), nCol);
+	const uint4 w = philox4(seed, 0u, g, 1u);
+	colors[v] = (ColT)__umulhi(w.x, nCol);
+	if (v + 1u < n) colors[v + 1u] = (ColT)__umulhi(w.y, nCol);
+	if (v + 2u < n) colors[v + 2u] = (ColT)__umulhi(w.z, nCol);
+	if (v + 3u < n) colors[v + 3u] = (ColT)__umulhi(w.w, nCol);
 }
 
 template <typename ColT>

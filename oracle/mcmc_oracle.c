@@ -35,14 +35,15 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* RNG contract (include/mcmcb200.h): counter = (vertex, purpose, sweep, 0), key = (seed_lo, seed_hi);
- * the first output word is the draw.  purpose 0 = sweep draw, 1 = initial colour. */
+/* RNG contract v2 (include/mcmcb200.h): one Philox call serves four consecutive vertices --
+ * counter = (vertex >> 2, purpose, sweep, 0), key = (seed_lo, seed_hi); the draw of vertex v is output word v & 3.
+ * purpose 0 = sweep draw, 1 = initial colour, 2 = Luby cross-check. */
 uint32_t orc_draw_bits(uint64_t seed, uint32_t sweep, uint32_t vertex, uint32_t purpose) {
-	uint32_t ctr[4] = { vertex, purpose, sweep, 0u };
+	uint32_t ctr[4] = { vertex >> 2, purpose, sweep, 0u };
 	uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
 	uint32_t out[4];
 	orc_philox4x32_10(ctr, key, out);
-	return out[0];
+	return out[vertex & 3u];
 }
 
 /* UNIFORM proposal: u in [0,1) like std::uniform_real_distribution<float>(0,1) (coloringMCMC_CPU.cpp:55,139);
@@ -225,8 +226,12 @@ uint64_t orc_sweep(uint32_t n, const uint32_t * cumulDegs, const uint32_t * neig
 					i++;
 				} while (threshold < randnum && i < nCol);
 			} else {                                                       /* :130-136 */
+				/* the reference GPU kernel as nvcc builds it (default -fmad=true) evaluates 1.0f - (nCol-1)*epsilon with ONE
+				 * rounding: `FFMA R, -R(nCol-1), R(eps), 1` in the SASS of selectStarColoringBalanceDynamic (oracle/_ref_gpu);
+				 * tests/test_gpu_refgpu.py pins this against the real kernel at eps = 1e-4, nCol = 89, where the two differ */
+				const float stayW = fmaf(-(float)(nCol - 1), eps, 1.0f);
 				do {
-					q = (own == i) ? (1.0f - (nCol - 1) * eps) : eps;
+					q = (own == i) ? stayW : eps;
 					threshold += q;
 					i++;
 				} while (threshold < randnum && i < nCol);

@@ -318,3 +318,78 @@ def importer_csr(n, src, dst):
             neighs[cumul[d_] + temp[d_]] = s_
             temp[d_] += 1
     return cumul.astype(np.uint32), neighs
+
+
+REFGPU_SO = os.path.join(HERE, "_ref_gpu", "libmcmc_refgpu.so")
+
+
+class RefGpu:
+    """oracle/refgpu_harness.cu over the UNMODIFIED reference GPU colourer compiled for sm_100a (oracle/_ref_gpu, built by
+    `make -C oracle refgpu` where /root/reference exists; the binary travels to the GPU box).  GPU tests only."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REFGPU_SO)
+
+    def __init__(self):
+        L = self.L = C.CDLL(REFGPU_SO)
+        vp = C.c_void_p
+        L.refgpu_create.restype = vp
+        L.refgpu_create.argtypes = [C.c_uint32, C.c_uint32, _u32p, _u32p, C.c_float, C.c_uint32, C.c_float, C.c_float,
+                                    C.c_uint32, C.c_int, C.c_uint32, C.c_float, C.c_long]
+        L.refgpu_destroy.argtypes = [vp]
+        for name in ("refgpu_set_colors", "refgpu_get_colors", "refgpu_set_taboo", "refgpu_get_taboo"):
+            getattr(L, name).argtypes = [vp, _u32p]
+        L.refgpu_peek_draws.argtypes = [vp, _f32p]
+        L.refgpu_step_dynamic.argtypes = [vp, C.c_int]
+        L.refgpu_conflicts.argtypes = [vp]
+        L.refgpu_tailcut.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.refgpu_run.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+
+    def create(self, cumul, neighs, nCol, prob=0.0, eps=1e-8, taboo_iter=0, tailcut=False, max_rip=250, ratio=1.0, curand_seed=1234):
+        n = len(cumul) - 1
+        h = self.L.refgpu_create(n, len(neighs), np.ascontiguousarray(cumul, np.uint32), np.ascontiguousarray(neighs, np.uint32),
+                                 prob, nCol, eps, 1.0, taboo_iter, int(tailcut), max_rip, 1.0 / ratio, curand_seed)
+        assert h, "refgpu_create failed"
+        return h
+
+    def destroy(self, h):
+        self.L.refgpu_destroy(h)
+
+    def set_colors(self, h, c):
+        assert self.L.refgpu_set_colors(h, np.ascontiguousarray(c, np.uint32)) == 0
+
+    def get_colors(self, h, n):
+        out = np.zeros(n, np.uint32)
+        assert self.L.refgpu_get_colors(h, out) == 0
+        return out
+
+    def set_taboo(self, h, t):
+        assert self.L.refgpu_set_taboo(h, np.ascontiguousarray(t, np.uint32)) == 0
+
+    def get_taboo(self, h, n):
+        out = np.zeros(n, np.uint32)
+        assert self.L.refgpu_get_taboo(h, out) == 0
+        return out
+
+    def peek_draws(self, h, n):
+        out = np.zeros(n, np.float32)
+        assert self.L.refgpu_peek_draws(h, out) == 0
+        return out
+
+    def step_dynamic(self, h, prefill=True):
+        assert self.L.refgpu_step_dynamic(h, int(prefill)) == 0
+
+    def conflicts(self, h):
+        return self.L.refgpu_conflicts(h)
+
+    def tailcut(self, h, max_rounds=64):
+        r = C.c_int()
+        left = self.L.refgpu_tailcut(h, max_rounds, C.byref(r))
+        return left, r.value
+
+    def run(self, h, iteration, directory):
+        """The reference's own ColoringMCMC::run(iteration): writes <directory>.log and <directory>-colors.txt."""
+        mx = C.c_int()
+        rip = self.L.refgpu_run(h, iteration, directory.encode(), C.byref(mx))
+        return rip, bool(mx.value)

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(capi):
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (mcmcb200_\w+)", out))
     assert exported == set(header_symbols())
-    assert L.mcmcb200_abi_version() == 1
+    assert L.mcmcb200_abi_version() == 2
     assert b"invalid" in L.mcmcb200_strerror(-1)
 
 
@@ -48,8 +48,8 @@ def test_library_holds_sm100a_sass_only(capi):
 
 
 def test_struct_layouts_match_header(capi):
-    # mcmcb200_params: 10 x 4 bytes, u64 seed, i32 device, u32 flags = 56; mcmcb200_status_t = 40
-    assert ctypes.sizeof(capi.Params) == 56
+    # mcmcb200_params: 10 x 4 bytes, u64 seed, i32 device, u32 flags, 4 x u32 tuning = 72; mcmcb200_status_t = 40
+    assert ctypes.sizeof(capi.Params) == 72
     assert ctypes.sizeof(capi.Status) == 40
 
 
