@@ -301,24 +301,35 @@ def main():
     # time to a proper colouring (the other half of BASELINE's metric), the reference's --tailcut protocol: sweep until at most
     # z = max(50, n/2000) vertices are violated (coloringMCMC_main.cu:150-170), then the greedy tail-cutting repair (:271-290).
     # (At n = 1e8 the epsilon tails alone re-colour ~n*nCol*eps = 45 vertices per sweep, so the plain chain idles at a few
-    # dozen violations: the threshold is part of the algorithm, not a shortcut.)  Counters are read back after every sweep;
-    # wall clock including those host round trips; untimed for `value`.
-    ch.init_colors(None)
+    # dozen violations: the threshold is part of the algorithm, not a shortcut.)  A second handle with params.tailcut = 1 (its
+    # mcmcb200_create is timed too: `setup_ms` is the layout build a user pays once per graph); the chain stops ON THE DEVICE at
+    # the threshold -- the host only polls every 4 sweeps -- and the repair works from the violator list the last sweep emitted.
+    prm_tc = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=prm.convergence, seed=CHAIN_SEED, tailcut=True)
     torch.cuda.synchronize()
+    t_setup = time.perf_counter()
+    ch_tc = mc.Chain(params=prm_tc, device=local_rank, flags=(mc.FLAG_NO_OVERLAP if args.no_overlap else 0), n_global=n, v_begin=0, v_end=n,
+                     device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz),
+                     stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers)
+    ch_tc.synchronize()
+    setup_ms = 1e3 * (time.perf_counter() - t_setup)
+    ch_tc.init_colors(None)
+    ch_tc.synchronize()
     z_tail = max(50, n // 2000)
     t_ttc = time.perf_counter()
-    ttc_sweeps, st_ttc = 0, ch.status()
-    while st_ttc.violatingVertices > z_tail and ttc_sweeps < 250 and time.perf_counter() - t_ttc < 5.0:
-        ch.sweep(1)
-        st_ttc = ch.status()
-        ttc_sweeps += 1
+    while True:
+        ch_tc.sweep(4)
+        st_ttc = ch_tc.status()
+        if st_ttc.converged or st_ttc.sweep >= 250 or time.perf_counter() - t_ttc > 5.0:
+            break
+    ttc_sweeps = int(st_ttc.sweep)
     t_sweeps = time.perf_counter() - t_ttc
     # the repair pass only once the chain is below the threshold (a palette that cannot get there -- config 4 at nCol = 512 --
     # is reported as not proper; the greedy repair is not meant for hundreds of thousands of conflicts on hub rows)
-    reached = st_ttc.violatingVertices <= z_tail
-    ttc_rounds = ch.tailcut(64) if (reached and st_ttc.conflictEdges > 0) else 0
-    st_ttc = ch.status()
+    reached = bool(st_ttc.converged)
+    ttc_rounds = ch_tc.tailcut(64) if (reached and st_ttc.conflictEdges > 0) else 0
+    st_ttc = ch_tc.status()
     t_ttc = time.perf_counter() - t_ttc
+    ch_tc.close()
     ms_per_step = float(np.mean(kernel_ms))
     value = n / (ms_per_step * 1e-3)
     alg_bytes = 8 * nnz + 12 * n + 4
@@ -368,6 +379,7 @@ def main():
         "clocks": clocks.summary(),
         "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
         "time_to_proper_coloring": {"sweeps": ttc_sweeps, "tailcut_rounds": int(ttc_rounds), "ms": 1e3 * t_ttc, "ms_sweeps": 1e3 * t_sweeps,
+                                    "setup_ms": setup_ms, "total_ms_with_setup": setup_ms + 1e3 * t_ttc,
                                     "z": z_tail, "reached_z": bool(reached), "proper": bool(st_ttc.conflictEdges == 0 and st_ttc.violatingVertices == 0),
                                     "usedColors": int(st_ttc.usedColors), "nCol": nCol},
     }

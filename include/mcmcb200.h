@@ -188,13 +188,19 @@ int mcmcb200_init_colors_slice(mcmcb200_handle * h, const uint32_t * ownedColors
 int mcmcb200_init_colors_finish(mcmcb200_handle * h);
 int mcmcb200_get_colors_slice(mcmcb200_handle * h, uint32_t * out /* [vEnd - vBegin] */);
 
-/* Fused exchange (one box, NVLink/NVSwitch): instead of an all-gather after the sweep, the sweep kernel itself stores
- * every finished tile's new colours into ALL ranks' colour replicas through peer pointers.  Each rank exports the two
- * cudaIpcMemHandle_t (64 bytes each) of its colour buffers, the caller exchanges them (any transport) and attaches the
- * full table [nRanks][2][64]; afterwards only the counter all-reduce (which doubles as the inter-rank barrier) remains.
- * Needs MCMCB200_FLAG_NO_FUSED_FINALIZE and the source-blocked sweep; nRanks <= 8. */
-int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [2][64] */);
+/* Fused exchange (one box, NVLink/NVSwitch): no collective library call and no host in the sweep loop.  The sweep kernel
+ * itself stores every finished tile's new colours into ALL ranks' colour replicas through peer pointers, and the last CTA of
+ * every rank's sweep all-reduces the counters {conflicts, violations, class-size deltas} into all ranks' exchange blocks with
+ * system-scope reductions over NVLink, waits for all ranks to arrive (the inter-rank barrier) and finalizes the sweep on the
+ * device.  After attach, mcmcb200_sweep(h, k) runs k sweeps on N GPUs as 2k launches per rank; the ranks must issue the same
+ * sequence of mcmcb200_init_colors* / mcmcb200_sweep / mcmcb200_status calls (SPMD: each of them is a collective).
+ * Each rank exports three cudaIpcMemHandle_t (64 bytes each: two colour buffers, the exchange block), the caller exchanges
+ * them (any transport) and attaches the full table [nRanks][3][64].  Needs the source-blocked sweep on every rank
+ * (MCMCB200_EUNSUPPORTED otherwise: agree on eligibility BEFORE attaching anywhere); nRanks <= 8.  mcmcb200_ipc_detach closes
+ * the mappings again (back to MCMCB200_FLAG_NO_FUSED_FINALIZE semantics: the caller exchanges). */
+int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [3][64] */);
 int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles);
+int mcmcb200_ipc_detach(mcmcb200_handle * h);
 int mcmcb200_stream(mcmcb200_handle * h, void ** cudaStream);
 int mcmcb200_synchronize(mcmcb200_handle * h);
 /* elapsed milliseconds (CUDA events on the handle's stream) of the kernels launched by the last mcmcb200_sweep */

@@ -244,8 +244,11 @@ class Chain:
     def get_colors_slice_ptr(self, host_ptr):
         capi.check(self.L.mcmcb200_get_colors_slice(self.h, C.c_void_p(host_ptr)), "mcmcb200_get_colors_slice")
 
+    def ipc_detach(self):
+        capi.check(self.L.mcmcb200_ipc_detach(self.h), "mcmcb200_ipc_detach")
+
     def ipc_export(self):
-        buf = (C.c_ubyte * 128)()
+        buf = (C.c_ubyte * 192)()
         capi.check(self.L.mcmcb200_ipc_export(self.h, C.cast(buf, C.c_void_p)), "mcmcb200_ipc_export")
         return bytes(buf)
 

@@ -81,6 +81,7 @@ inline cudaError_t build_binned_layout(BinnedLayout & L, const uint32_t * d_rowp
 done:
 	cudaFree(d_num); cudaFree(scratch); cudaFree(d_tmp);
 	if (err != cudaSuccess || !L.valid) { cudaError_t keep = err; free_binned_layout(L); err = keep; }
+	if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); err = cudaSuccess; }   // no room for the lists: the tile-synchronous kernel needs none
 	return err;
 }
 

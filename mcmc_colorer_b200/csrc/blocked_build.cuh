@@ -18,7 +18,7 @@ inline void free_blocked_layout(BlockedLayout & L) {
 
 // Returns cudaSuccess with L.valid == false when the layout does not apply (hub rows larger than a tile, > 2^31 edges...).
 inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_rowptr, const uint32_t * d_neighs, uint32_t nLocal,
-                                        uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes, uint32_t itemEntries,
+                                        uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes, uint32_t itemEntries, uint32_t roundV,
                                         cudaStream_t stream, uint64_t * launches) {
 	cudaError_t err = cudaSuccess;
 	L = BlockedLayout{};
@@ -42,15 +42,38 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	uint32_t numSlices = 0, sellTotal = 0;
 
 	BLK_CU(cudaMalloc(&d_tmp, 2 * sizeof(uint32_t)));
-	// ---- tile size: the largest multiple of 256 vertices whose worst tile (edges + run padding) fits the stage ----
-	for (uint32_t j = std::min<uint32_t>(32u, (nLocal + 255u) / 256u); j >= 1; --j) {
-		const uint32_t tv = 256u * j, nt = (nLocal + tv - 1) / tv;
-		BLK_CU(cudaMemsetAsync(d_tmp, 0, sizeof(uint32_t), stream));
-		blk_max_tile_edges_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, tv, nt, d_tmp); (*launches)++;
-		BLK_CU(cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-		BLK_CU(cudaStreamSynchronize(stream));
-		const uint64_t worst = (uint64_t)h2[0] + 3ull * std::min<uint64_t>(P, h2[0]) + 16ull;   // + run padding + start misalignment
-		if (worst <= stageCap) { TV = tv; numTiles = nt; break; }
+	// ---- tile size: a multiple of 128 vertices whose worst tile (edges + run padding) fits the stage.  Pass B walks a tile in
+	//      rounds of one vertex per thread, so a tile of k * threads vertices leaves no lane idle in the last round (measured on
+	//      config 3: 1536 = 4 x 384 vertices 3.81 ms, 1792 vertices 4.35 ms): take the largest multiple of `roundV` that fits, or,
+	//      for small stages / graphs, the largest multiple of 128 ----
+	{
+		auto fits = [&](uint32_t tv, bool & ok) -> cudaError_t {
+			const uint32_t nt = (nLocal + tv - 1) / tv;
+			cudaError_t e = cudaMemsetAsync(d_tmp, 0, sizeof(uint32_t), stream);
+			if (e != cudaSuccess) return e;
+			blk_max_tile_edges_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, tv, nt, d_tmp); (*launches)++;
+			e = cudaMemcpyAsync(h2, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+			const uint64_t worst = (uint64_t)h2[0] + 3ull * std::min<uint64_t>(P, h2[0]) + 16ull;   // + run padding + start misalignment
+			ok = worst <= stageCap;
+			return e;
+		};
+		const uint32_t maxTv = std::min<uint32_t>(8192u, ((nLocal + 127u) / 128u) * 128u);      // (13-bit local vertex ids in the slot table)
+		bool ok = false;
+		uint32_t lo = 0, hi = maxTv / 128u;                        // binary search on the multiple of 128 (worst-tile size grows with tv)
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi + 1) / 2;
+			BLK_CU(fits(mid * 128u, ok));
+			if (ok) lo = mid; else hi = mid - 1;
+		}
+		uint32_t tv = lo * 128u;
+		if (tv >= roundV && tv % roundV != 0) {
+			const uint32_t tr = (tv / roundV) * roundV;
+			BLK_CU(fits(tr, ok));
+			if (ok) tv = tr;
+		}
+		if (tv) { BLK_CU(fits(tv, ok)); if (!ok) tv = 0; }        // (re-check: the search assumes monotonicity)
+		if (tv) { TV = tv; numTiles = (nLocal + tv - 1) / tv; }
 	}
 	if (TV == 0) goto done;                                     // a row (or 256 of them) exceeds the stage: direct kernel only
 	cells = (size_t)P * numTiles;

@@ -128,12 +128,25 @@ __global__ void blk_edge_keys_kernel(const uint32_t * neighs, uint32_t nnz, uint
 	vals[e] = e;
 }
 
-// tile of a CSR edge position: tileE is ascending, tileE[T] <= e < tileE[T+1] (empty tiles are skipped by upper_bound)
-__device__ __forceinline__ uint32_t blk_tile_of_edge(const uint32_t * tileE, uint32_t numTiles, uint32_t e) {
-	uint32_t lo = 0, hi = numTiles;          // first index with tileE[idx] > e, minus one
+// tile of a CSR edge position: tileE is ascending, tileE[T] <= e < tileE[T+1] (empty tiles are skipped).  Interpolation first --
+// tiles of a graph that fits this layout hold similar numbers of edges, so the guess e * numTiles / nnz is almost always within
+// a step or two (the plain 16-step binary search per edge made blk_fill_entries_kernel the longest kernel of the layout build:
+// 108 ms on config 3) -- then a bounded walk, then binary search on what is left.
+__device__ __forceinline__ uint32_t blk_tile_of_edge(const uint32_t * __restrict__ tileE, uint32_t numTiles, uint32_t e) {
+	const uint32_t nnz = __ldg(tileE + numTiles);
+	uint32_t T = (uint32_t)(((unsigned long long)e * numTiles) / (nnz ? nnz : 1u));
+	if (T >= numTiles) T = numTiles - 1u;
+	uint32_t lo = 0, hi = numTiles;                         // answer in [lo, hi)
+	for (int step = 0; step < 6; ++step) {
+		if (__ldg(tileE + T) > e) { hi = T; if (T == 0) break; --T; }
+		else if (__ldg(tileE + T + 1) <= e) { lo = T + 1; ++T; if (T >= numTiles) { T = numTiles - 1u; break; } }
+		else return T;
+	}
+	if (lo >= hi) return min(lo, numTiles - 1u);
+	hi = hi - 1;                                            // first index with tileE[idx + 1] > e in [lo, hi]
 	while (lo < hi) {
 		const uint32_t mid = (lo + hi) >> 1;
-		if (tileE[mid + 1] > e) hi = mid; else lo = mid + 1;
+		if (__ldg(tileE + mid + 1) > e) hi = mid; else lo = mid + 1;
 	}
 	return lo;
 }
@@ -760,12 +773,13 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		}
 	}
 	if (a.fuseFinalize) {
-		__threadfence();
+		if (a.nPeers) __threadfence_system(); else __threadfence();   // (peer colour stores of this CTA: visible system-wide before the ticket)
 		__syncthreads();
 		if (tid == 0) sm.ctl[3] = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
 		__syncthreads();
 		if (sm.ctl[3]) {
 			__threadfence();
+			if (a.nPeers) cross_rank_reduce(a);               // all-reduce + inter-rank barrier over NVLink, inside the kernel
 			finalize_sweep_device(a);
 		}
 	}

@@ -28,6 +28,7 @@ inline cudaError_t build_csr_from_edges(uint32_t n, uint64_t m, const uint32_t *
                                         uint32_t ** rowptrOut, uint32_t ** neighsOut, uint64_t * nnzOut, uint64_t * badOut) {
 	*rowptrOut = nullptr; *neighsOut = nullptr; *nnzOut = 0; *badOut = 0;
 	if (2 * m >= 0xfffffff0ull) return cudaErrorInvalidValue;          // 32-bit CSR offsets, like the reference (graph.h:19-20)
+	if (n >= 0x7ffffff0u) return cudaErrorInvalidValue;                 // cub::DeviceScan item counts are int
 	cudaError_t err = cudaSuccess;
 	const uint64_t pairs = 2 * m;
 	uint32_t * d_keys[2] = {nullptr, nullptr}, * d_vals[2] = {nullptr, nullptr}, * d_deg = nullptr, * d_rowptr = nullptr, * d_neighs = nullptr;

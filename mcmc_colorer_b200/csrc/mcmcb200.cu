@@ -72,7 +72,15 @@ struct mcmcb200_handle {
 	BlockedLayout bl;                    // source-blocked two-pass layout (valid => the sweeps use it)
 	BinnedLayout bn;                     // degree-binned direct sweep (valid => used when bl is not)
 	void * peerColors[2][kMaxPeers] = {};  // fused multi-GPU exchange: IPC-mapped colour buffers of every rank (own = local)
+	uint32_t * d_violList[2] = {nullptr, nullptr};   // tail cutting: violating vertices emitted by the sweeps / left by the last repair pass
+	uint32_t * d_violCount = nullptr; uint32_t violCap = 0;
+	uint8_t * d_pending = nullptr;         // tail cutting: per-vertex flags (all zero between calls)
+	uint32_t * d_flist = nullptr;
+	TailcutCounters * d_tcCnt = nullptr;
+	unsigned long long * d_xchg = nullptr; // this rank's counter-exchange block (sweep_kernel.cuh: cross_rank_reduce)
+	unsigned long long * peerXchg[kMaxPeers] = {};
 	uint32_t nPeers = 0, myPeerIndex = 0;
+	bool split() const { return (p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0 && nPeers == 0; }   // caller reduces the counters (NCCL path)
 };
 
 namespace {
@@ -255,11 +263,15 @@ SweepArgs make_args(mcmcb200_handle * h) {
 	a.st = h->d_state; a.scratch = h->d_scratch; a.hist[0] = h->d_hist[0]; a.hist[1] = h->d_hist[1];
 	a.history = h->d_history; a.historyCap = h->historyCap;
 	a.countOnly = 0; a.countOut = nullptr;
-	a.fuseFinalize = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) ? 0u : 1u;
+	a.fuseFinalize = h->split() ? 0u : 1u;
 	a.noEarlyStop = (h->p.flags & MCMCB200_FLAG_NO_EARLY_STOP) ? 1u : 0u;
 	a.nPeers = h->bl.valid ? h->nPeers : 0u;
 	for (int b = 0; b < 2; ++b) for (uint32_t q = 0; q < kMaxPeers; ++q) a.peerColors[b][q] = h->peerColors[b][q];
+	for (uint32_t q = 0; q < kMaxPeers; ++q) a.peerXchg[q] = h->peerXchg[q];
+	a.myRank = h->myPeerIndex;
 	a.dbgMasks = nullptr; a.dbgSame = nullptr;
+	a.violList = h->d_violList[0]; a.violCount = h->d_violCount; a.violCap = h->violCap; a.forceEmit = 0;
+	a.emitThreshold = h->violCap ? (unsigned long long)h->violCap : 0ull;
 	return a;
 }
 
@@ -318,6 +330,19 @@ int alloc_chain_state(mcmcb200_handle * h) {
 	CU(cudaMalloc(&h->d_hist[1], sizeof(unsigned long long) * nCol));
 	CU(cudaMalloc(&h->d_history, sizeof(unsigned long long) * 2 * h->historyCap));
 	CU(cudaMalloc(&h->d_countOut, sizeof(unsigned long long) * 2));
+	if (h->p.tailcut && h->vBegin == 0 && h->vEnd == h->nGlobal) {
+		// room for the violators of a colouring up to 32 z away from the threshold (sweep_kernel.cuh: emitThreshold)
+		h->violCap = (uint32_t)std::min<uint64_t>(h->nGlobal, 32ull * h->z + 4096ull);
+		for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_violList[i], sizeof(uint32_t) * (size_t)h->violCap));
+		CU(cudaMalloc(&h->d_flist, sizeof(uint32_t) * (size_t)h->violCap));
+		CU(cudaMalloc(&h->d_violCount, sizeof(uint32_t)));
+		CU(cudaMemsetAsync(h->d_violCount, 0, sizeof(uint32_t), h->stream));
+		CU(cudaMalloc(&h->d_tcCnt, sizeof(TailcutCounters)));
+		CU(cudaMalloc(&h->d_pending, std::max<size_t>(h->nGlobal, 1)));
+		CU(cudaMemsetAsync(h->d_pending, 0, std::max<size_t>(h->nGlobal, 1), h->stream));
+	}
+	CU(cudaMalloc(&h->d_xchg, sizeof(unsigned long long) * xchg_words(nCol)));
+	CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(unsigned long long) * xchg_words(nCol), h->stream));
 	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (nCol + 2), h->stream));
 	CU(cudaMemsetAsync(h->d_history, 0, sizeof(unsigned long long) * 2 * h->historyCap, h->stream));
 	h->smemBytes = sweep_smem_bytes(nCol, h->W, h->colBytes);
@@ -334,8 +359,11 @@ int reset_state(mcmcb200_handle * h) {
 	DevState s{};
 	s.sweep = 0; s.convergedAt = -1; s.ticket = 0; s.tileCounter = 0;
 	s.convergence = h->p.convergence; s.countsSweep = 0xffffffffu; s.z = h->z;
-	s.lastDirected = 0; s.lastViol = 0; s.errorFlag = 0;
+	s.lastDirected = 0; s.lastViol = 0; s.errorFlag = 0; s.xseq = 0;
+	s.emitNow = 0; s.violListSweep = 0xffffffffu; s.violListCount = 0;
+	if (h->d_violCount) CU(cudaMemsetAsync(h->d_violCount, 0, sizeof(uint32_t), h->stream));
 	CU(cudaMemcpyAsync(h->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(unsigned long long) * xchg_words(h->p.nCol), h->stream));   // (all ranks reset together: init_colors is collective)
 	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (h->p.nCol + 2), h->stream));
 	if (h->d_taboo) CU(cudaMemsetAsync(h->d_taboo, 0, sizeof(uint16_t) * std::max<size_t>(h->nLocal, 1), h->stream));
 	h->hostSweepUpper = 0; h->tapeBase = 0; h->pendingCountOnly = false;
@@ -390,7 +418,7 @@ int read_state(mcmcb200_handle * h, DevState * s) {
 	}
 	h->overlap = false;
 	if (h->streamA) CU(cudaStreamSynchronize(h->streamA));
-	if (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) {       // multi-GPU: the caller drives the exchange, it has to redo the sweep itself
+	if (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) {       // multi-GPU: the ranks run in lock step, one of them cannot redo a sweep alone
 		snprintf(g_lastCudaError, sizeof(g_lastCudaError), "overlapped blocked sweep aborted on the device (sweep %u); handle switched to back-to-back passes", s->sweep);
 		return MCMCB200_ECUDA;
 	}
@@ -470,7 +498,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			if (p->stageCapBytes) capBytes = p->stageCapBytes;
 			if (p->stageBuffers) nbuf = p->stageBuffers;
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes, itemEntries,
-			                                     h->stream, &h->launches);
+			                                     (uint32_t)(h->W <= 2 ? PassB<1>::threads : PassB<4>::threads), h->stream, &h->launches);
 			h->bl.nbuf = nbuf;
 			if (e == cudaSuccess && h->bl.valid) e = configure_blocked(h);
 			if (e == cudaSuccess && !h->bl.valid) free_blocked_layout(h->bl);
@@ -497,8 +525,73 @@ int run_count_pass(mcmcb200_handle * h, const void * overrideColors, unsigned lo
 	SweepArgs a = make_args(h);
 	a.countOnly = 1; a.colorsOverride = overrideColors; a.countOut = countOut;
 	a.dbgMasks = dbgMasks; a.dbgSame = dbgSame; a.fuseFinalize = 1; a.tape = nullptr;
+	if (overrideColors || countOut || dbgMasks) { a.nPeers = 0; a.violList = nullptr; }   // a pure function of a colouring: this rank's rows only, no collective, no list
 	CU(launch_sweep(h, a));
 	return MCMCB200_OK;
+}
+
+// List-driven tail cutting (tailcut_kernel.cuh).  Returns MCMCB200_OK / an error, or 1 when the violator list cannot be had
+// (more violators than the list holds): the caller then uses the full-scan path.
+template <typename ColT>
+int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned long long * hist, const std::vector<uint32_t> & order,
+                        uint32_t maxRounds, uint32_t * rounds) {
+	ColT * cur = static_cast<ColT *>(curV);
+	const uint32_t nCol = h->p.nCol;
+	if (s.violListSweep != s.sweep || s.violListCount > h->violCap) {
+		// no list for this colouring (chain stopped by maxRip, colours set by the caller, ...): one count-only pass emits it
+		SweepArgs a = make_args(h);
+		a.countOnly = 1; a.fuseFinalize = 1; a.tape = nullptr; a.forceEmit = 1; a.nPeers = 0;
+		CU(cudaMemsetAsync(h->d_violCount, 0, sizeof(uint32_t), h->stream));
+		CU(launch_sweep(h, a));
+		int rc = read_state(h, &s); if (rc) return rc;
+		if (s.violListSweep != s.sweep || s.violListCount > h->violCap) return 1;
+	}
+	uint32_t * d_order = nullptr;
+	CU(cudaMalloc(&d_order, sizeof(uint32_t) * nCol));
+	cudaError_t e = cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * nCol, cudaMemcpyHostToDevice, h->stream);
+	uint32_t listCount = s.violListCount, used = 0;
+	int src = 0;
+	TailcutCounters c{};
+	for (; e == cudaSuccess && used < maxRounds; ++used) {                 // while (conflictCounter > 0), _main.cu:279
+		if (listCount == 0) break;
+		if ((e = cudaMemsetAsync(h->d_tcCnt, 0, sizeof(TailcutCounters), h->stream)) != cudaSuccess) break;
+		const uint32_t lb = (listCount + 255) / 256;
+		tc_filter_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_flist, h->d_tcCnt);
+		tc_rounds_kernel<ColT><<<1, 1024, 0, h->stream>>>(h->d_rowptr, h->d_neighs, nCol, cur, h->d_pending, h->d_flist, h->d_tcCnt, d_order, hist);
+		tc_recount_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_violList[src ^ 1], h->d_tcCnt);
+		h->launches += 3;
+		if ((e = cudaMemcpyAsync(&c, h->d_tcCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) break;
+		if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+		src ^= 1;
+		listCount = c.nextCount;
+		if (c.flagged == 0) break;                                         // the pass found nothing to repair
+		if (c.inexact) break;
+		if (c.nextFlagged == 0) { ++used; break; }
+	}
+	if (e == cudaSuccess && src == 1) e = cudaMemcpyAsync(h->d_violList[0], h->d_violList[1], sizeof(uint32_t) * (size_t)listCount, cudaMemcpyDeviceToDevice, h->stream);
+	if (e == cudaSuccess) {
+		if (c.inexact) {                                                   // a repaired vertex found every colour taken: recount with a full pass at the next status
+			const uint32_t stale = 0xffffffffu; const int32_t notConv = -1;
+			e = cudaMemcpyAsync(&h->d_state->countsSweep, &stale, sizeof(stale), cudaMemcpyHostToDevice, h->stream);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(&h->d_state->convergedAt, &notConv, sizeof(notConv), cudaMemcpyHostToDevice, h->stream);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(&h->d_state->violListSweep, &stale, sizeof(stale), cudaMemcpyHostToDevice, h->stream);
+		} else if (used > 0 || s.violListCount > 0) {
+			tc_commit_kernel<<<1, 1, 0, h->stream>>>(h->d_state, h->d_tcCnt);
+			h->launches++;
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+	cudaFree(d_order);
+	if (e != cudaSuccess) return cuda_fail(e, "tailcut (list)", __LINE__);
+	if (rounds) *rounds = used;
+	return MCMCB200_OK;
+}
+
+int tailcut_from_list(mcmcb200_handle * h, DevState & s, void * cur, unsigned long long * hist, const std::vector<uint32_t> & order,
+                      uint32_t maxRounds, uint32_t * rounds) {
+	return h->colBytes == 1 ? tailcut_from_list_t<uint8_t>(h, s, cur, hist, order, maxRounds, rounds)
+	                        : tailcut_from_list_t<uint16_t>(h, s, cur, hist, order, maxRounds, rounds);
 }
 
 } // namespace
@@ -590,8 +683,9 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
 	free_blocked_layout(h->bl);
 	free_binned_layout(h->bn);
-	for (uint32_t q = 0; q < h->nPeers; ++q)
-		if (q != h->myPeerIndex) for (int b = 0; b < 2; ++b) if (h->peerColors[b][q]) cudaIpcCloseMemHandle(h->peerColors[b][q]);
+	mcmcb200_ipc_detach(h);
+	cudaFree(h->d_xchg);
+	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcCnt);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
 	if (h->streamA) { cudaStreamSynchronize(h->streamA); cudaStreamDestroy(h->streamA); }
 	if (h->evFork) cudaEventDestroy(h->evFork);
@@ -689,7 +783,7 @@ int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps) {
 int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k) {
 	if (!h) return MCMCB200_EINVAL;
 	if (!h->colorsInit) return MCMCB200_ESTATE;
-	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
+	const bool split = h->split();
 	if (split && k != 1) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));
 	CU(cudaEventRecord(h->ev0, h->stream));
@@ -726,7 +820,7 @@ int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
 	CU(cudaSetDevice(h->device));
 	DevState s;
 	int rc = read_state(h, &s); if (rc) return rc;
-	const bool split = (h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE) != 0;
+	const bool split = h->split();
 	if (s.countsSweep != s.sweep) {
 		if (split) {
 			// multi-GPU: launch the local counting pass; the caller all-reduces COUNTERS, calls finalize_sweep and asks again
@@ -872,6 +966,12 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	std::vector<uint32_t> order(nCol);
 	for (uint32_t i = 0; i < nCol; ++i) order[i] = i;
 	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hh[a] < hh[b]; });
+	if (h->d_violList[0]) {
+		// ---- list-driven path (params.tailcut): the sweeps emitted the violating vertices; no rescan of the graph, no host
+		//      round trip per round.  Falls through to the full-scan path below when the list is not available. ----
+		int lrc = tailcut_from_list(h, s, cur, hist, order, maxRounds, rounds);
+		if (lrc != 1) return lrc;                                  // 1 = list unavailable / overflowed
+	}
 	uint32_t * d_order = nullptr, * d_list = nullptr, * d_counters = nullptr; uint8_t * d_pending = nullptr, * d_ready = nullptr;
 	auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_list); cudaFree(d_counters); cudaFree(d_pending); cudaFree(d_ready); };
 	cudaError_t e = cudaMalloc(&d_order, sizeof(uint32_t) * nCol);
@@ -902,12 +1002,18 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 int mcmcb200_luby_color(uint32_t n, uint64_t nnz, const uint32_t * cumulDegs, const uint32_t * neighs, uint64_t seed, int32_t device,
                         uint32_t * colorsOut, uint32_t * numColors, uint32_t * rounds) {
 	if (!cumulDegs || (nnz && !neighs) || !colorsOut || n == 0) return MCMCB200_EINVAL;
+	// the same host-side CSR validation as mcmcb200_create: monotone offsets starting at 0, nnz consistent, ids < n
+	if (cumulDegs[0] != 0 || cumulDegs[n] != nnz || nnz >= 0xfffffff0ull) return MCMCB200_EINVAL;
+	for (uint32_t i = 0; i < n; ++i) if (cumulDegs[i + 1] < cumulDegs[i]) return MCMCB200_EINVAL;
+	for (uint64_t e2 = 0; e2 < nnz; ++e2) if (neighs[e2] >= n) return MCMCB200_EINVAL;
 	mcmcb200_params p{}; p.device = device;
 	int dev = 0, sms = 0;
 	int rc = select_device(&p, &dev, &sms); if (rc) return rc;
 	uint32_t * d_rp = nullptr, * d_nb = nullptr, * d_col = nullptr, * d_flag = nullptr;
 	uint8_t * d_c = nullptr, * d_is = nullptr, * d_ch = nullptr, * d_keep = nullptr;
-	auto cleanup = [&]() { cudaFree(d_rp); cudaFree(d_nb); cudaFree(d_col); cudaFree(d_flag); cudaFree(d_c); cudaFree(d_is); cudaFree(d_ch); cudaFree(d_keep); };
+	cudaStream_t st = nullptr;
+	CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	auto cleanup = [&]() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; } cudaFree(d_rp); cudaFree(d_nb); cudaFree(d_col); cudaFree(d_flag); cudaFree(d_c); cudaFree(d_is); cudaFree(d_ch); cudaFree(d_keep); };
 	cudaError_t e = cudaMalloc(&d_rp, sizeof(uint32_t) * ((size_t)n + 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_nb, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_col, sizeof(uint32_t) * (size_t)n);
@@ -918,30 +1024,33 @@ int mcmcb200_luby_color(uint32_t n, uint64_t nnz, const uint32_t * cumulDegs, co
 	if (e == cudaSuccess) e = cudaMalloc(&d_keep, n);
 	if (e == cudaSuccess) e = cudaMemcpy(d_rp, cumulDegs, sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess && nnz) e = cudaMemcpy(d_nb, neighs, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = cudaMemset(d_col, 0, sizeof(uint32_t) * (size_t)n);
+	if (e == cudaSuccess) e = cudaMemsetAsync(d_col, 0, sizeof(uint32_t) * (size_t)n, st);
 	if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby setup", __LINE__); }
 	const uint32_t blocks = (n + 127) / 128;                      // block 128 like the reference (coloringLuby.cu)
 	uint32_t color = 0, round = 0, flag = 1;
 	while (flag) {                                                // CICLO_1: one colour per iteration (coloringLuby.cu:389-470)
 		color++;
-		luby_prune_kernel<<<blocks, 128>>>(n, d_col, d_c, d_is);
+		luby_prune_kernel<<<blocks, 128, 0, st>>>(n, d_col, d_c, d_is);
 		uint32_t left = 1;
 		while (left) {                                            // CICLO_2: grow the independent set until no candidate is left
 			round++;
-			luby_choose_kernel<<<blocks, 128>>>(n, seed, round, d_c, d_ch);
-			luby_resolve_kernel<<<blocks, 128>>>(n, d_rp, d_nb, d_ch, d_keep);
-			luby_update_kernel<<<blocks, 128>>>(n, d_rp, d_nb, d_keep, d_c, d_is, d_flag);
-			cudaMemsetAsync(d_flag, 0, sizeof(uint32_t));
-			luby_left_kernel<<<blocks, 128>>>(n, d_c, d_flag);
-			e = cudaMemcpy(&left, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+			luby_choose_kernel<<<blocks, 128, 0, st>>>(n, seed, round, d_c, d_ch);
+			luby_resolve_kernel<<<blocks, 128, 0, st>>>(n, d_rp, d_nb, d_ch, d_keep);
+			luby_update_kernel<<<blocks, 128, 0, st>>>(n, d_rp, d_nb, d_keep, d_c, d_is, d_flag);
+			cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), st);
+			luby_left_kernel<<<blocks, 128, 0, st>>>(n, d_c, d_flag);
+			e = cudaMemcpyAsync(&left, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 			if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby round", __LINE__); }
 		}
-		cudaMemsetAsync(d_flag, 0, sizeof(uint32_t));
-		luby_color_kernel<<<blocks, 128>>>(n, color, d_is, d_col, d_flag);
-		e = cudaMemcpy(&flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+		cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), st);
+		luby_color_kernel<<<blocks, 128, 0, st>>>(n, color, d_is, d_col, d_flag);
+		e = cudaMemcpyAsync(&flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 		if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "luby colour", __LINE__); }
 	}
-	e = cudaMemcpy(colorsOut, d_col, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost);
+	e = cudaStreamSynchronize(st);
+	if (e == cudaSuccess) e = cudaMemcpy(colorsOut, d_col, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost);
 	cleanup();
 	if (e != cudaSuccess) return cuda_fail(e, "luby copy", __LINE__);
 	if (numColors) *numColors = color;
@@ -964,34 +1073,62 @@ int mcmcb200_device_view(mcmcb200_handle * h, int which, void ** devPtr, uint64_
 	return MCMCB200_OK;
 }
 
-int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [2][64] */) {
+int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [3][64] */) {
 	if (!h || !handles) return MCMCB200_EINVAL;
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	if (!h->bl.valid) return MCMCB200_EUNSUPPORTED;          // the fused exchange lives in the source-blocked sweep
 	CU(cudaSetDevice(h->device));
-	for (int b = 0; b < 2; ++b) {
+	void * ptrs[3] = {h->d_colors[0], h->d_colors[1], h->d_xchg};
+	for (int b = 0; b < 3; ++b) {
 		cudaIpcMemHandle_t mh;
-		CU(cudaIpcGetMemHandle(&mh, h->d_colors[b]));
+		CU(cudaIpcGetMemHandle(&mh, ptrs[b]));
 		memcpy(handles + 64 * b, &mh, 64);
 	}
 	return MCMCB200_OK;
 }
 
-int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles /* [nRanks][2][64] */) {
+int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles /* [nRanks][3][64] */) {
 	if (!h || !handles || nRanks < 2 || nRanks > (uint32_t)kMaxPeers || myRank >= nRanks) return MCMCB200_EINVAL;
-	if (!(h->p.flags & MCMCB200_FLAG_NO_FUSED_FINALIZE)) return MCMCB200_ESTATE;
-	if (!h->bl.valid) return MCMCB200_EUNSUPPORTED;          // the fused exchange lives in the source-blocked sweep
+	if (!h->bl.valid) return MCMCB200_EUNSUPPORTED;
 	if (h->nPeers) return MCMCB200_ESTATE;
 	CU(cudaSetDevice(h->device));
-	for (uint32_t q = 0; q < nRanks; ++q)
-		for (int b = 0; b < 2; ++b) {
-			if (q == myRank) { h->peerColors[b][q] = h->d_colors[b]; continue; }
+	CU(cudaStreamSynchronize(h->stream));
+	void * opened[kMaxPeers][3] = {};
+	for (uint32_t q = 0; q < nRanks; ++q) {
+		if (q == myRank) { opened[q][0] = h->d_colors[0]; opened[q][1] = h->d_colors[1]; opened[q][2] = h->d_xchg; continue; }
+		for (int b = 0; b < 3; ++b) {
 			cudaIpcMemHandle_t mh;
-			memcpy(&mh, handles + ((size_t)q * 2 + b) * 64, 64);
-			void * ptr = nullptr;
-			CU(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
-			h->peerColors[b][q] = ptr;
+			memcpy(&mh, handles + ((size_t)q * 3 + b) * 64, 64);
+			cudaError_t e = cudaIpcOpenMemHandle(&opened[q][b], mh, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) {                               // close what was opened so far: nothing half attached
+				for (uint32_t q2 = 0; q2 <= q; ++q2)
+					if (q2 != myRank) for (int b2 = 0; b2 < 3; ++b2) if (opened[q2][b2] && !(q2 == q && b2 >= b)) cudaIpcCloseMemHandle(opened[q2][b2]);
+				return cuda_fail(e, "cudaIpcOpenMemHandle", __LINE__);
+			}
 		}
+	}
+	for (uint32_t q = 0; q < nRanks; ++q) {
+		h->peerColors[0][q] = opened[q][0]; h->peerColors[1][q] = opened[q][1];
+		h->peerXchg[q] = static_cast<unsigned long long *>(opened[q][2]);
+	}
 	h->nPeers = nRanks; h->myPeerIndex = myRank;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_ipc_detach(mcmcb200_handle * h) {
+	if (!h) return MCMCB200_EINVAL;
+	if (!h->nPeers) return MCMCB200_OK;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	for (uint32_t q = 0; q < h->nPeers; ++q) {
+		if (q != h->myPeerIndex) {
+			for (int b = 0; b < 2; ++b) if (h->peerColors[b][q]) cudaIpcCloseMemHandle(h->peerColors[b][q]);
+			if (h->peerXchg[q]) cudaIpcCloseMemHandle(h->peerXchg[q]);
+		}
+		h->peerColors[0][q] = h->peerColors[1][q] = nullptr; h->peerXchg[q] = nullptr;
+	}
+	h->nPeers = 0;
+	cudaGetLastError();
 	return MCMCB200_OK;
 }
 

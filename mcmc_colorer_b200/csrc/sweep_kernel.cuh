@@ -47,8 +47,12 @@ struct DevState {
 	uint64_t z;              // threshold
 	uint64_t lastDirected;   // sum_v #{u in N(v): C[u]==C[v]}  == 2 * conflicting edges
 	uint64_t lastViol;       // violating vertices
-	uint32_t errorFlag;      // sticky device-side error (colour out of range, ...)
-	uint32_t pad;
+	uint32_t errorFlag;      // sticky device-side error: 1 colour out of range, 2 blocked sweep aborted (producer missing), 3 a peer GPU never arrived
+	uint32_t xseq;           // multi-GPU: collective finalize steps performed so far (parity selects the exchange slot)
+	uint32_t emitNow;        // tail cutting: the running sweep appends its violating vertices to SweepArgs::violList
+	uint32_t violListSweep;  // colouring index that list describes (0xffffffff: none / overflowed)
+	uint32_t violListCount;  // entries of the list
+	uint32_t pad2;
 };
 
 struct SweepArgs {
@@ -75,9 +79,18 @@ struct SweepArgs {
 	uint32_t fuseFinalize;       // last CTA runs finalize_sweep
 	uint32_t noEarlyStop;        // keep sweeping even when C_t is already proper (replay / benchmarking)
 	void *   peerColors[2][kMaxPeers]; // fused exchange: every rank's two colour buffers (IPC-mapped; own entries = local)
+	unsigned long long * peerXchg[kMaxPeers]; // fused exchange: every rank's counter-exchange block (layout: xchg_* below)
 	uint32_t nPeers;             // 0: no fused exchange (single GPU, or NCCL all-gather by the caller)
+	uint32_t myRank;             // index of this handle in the peer tables
 	unsigned long long * dbgMasks; // optional [nLocal][W]
 	uint32_t * dbgSame;          // optional [nLocal]
+	// tail cutting (params.tailcut): when the chain gets close to the threshold z the sweeps emit the violating vertices of the
+	// colouring they evaluate, so that the repair never has to rescan the graph (tailcut_kernel.cuh)
+	uint32_t * violList;         // [violCap] global vertex ids, or nullptr
+	uint32_t * violCount;        // entries appended by the running launch
+	uint32_t violCap;
+	uint32_t forceEmit;          // emit regardless of DevState::emitNow (the count-only pass mcmcb200_tailcut falls back to)
+	unsigned long long emitThreshold; // finalize: the NEXT sweep emits iff this colouring has at most so many violating vertices
 };
 
 __host__ __device__ inline size_t sweep_smem_bytes(uint32_t nCol, int W, int colBytes) {
@@ -96,6 +109,53 @@ __host__ __device__ inline size_t sweep_smem_bytes(uint32_t nCol, int W, int col
 	b = (b + 15) & ~(size_t)15;
 	b += (size_t)kTileV * (8 * W + 16);                   // deferred CDF walks of one sub-tile (mask, vertex/own, draw/weight)
 	return (b + 15) & ~(size_t)15;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU, fused exchange: the per-sweep all-reduce of {directed conflicts, violating vertices, class-size deltas} and the
+// inter-rank barrier, done by the sweep kernel itself over NVLink -- no NCCL call, no host in the loop.
+// Every rank owns an exchange block (IPC-mapped by all peers):  [0..1] arrival counters, then two slots of 2 + nCol sums.
+// The LAST CTA of a rank's sweep adds its local counters into the current slot of EVERY rank (system-scope reductions on peer
+// memory), fences, bumps every rank's arrival counter, waits until all nPeers ranks have arrived at its own block, and only then
+// runs finalize_sweep_device on the global sums.  Because nobody passes this point before everybody's last CTA got here, it is
+// also the barrier that orders sweep t+1 after every peer's colour stores of sweep t.  Slots alternate with st->xseq; a slot is
+// re-used two collectives later, which a rank can only reach after all ranks finished the collective in between.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t xchg_words(uint32_t nCol) { return 2 + 2 * (size_t)(nCol + 2); }
+__device__ __forceinline__ unsigned long long * xchg_slot(unsigned long long * block, uint32_t nCol, uint32_t par) { return block + 2 + (size_t)par * (nCol + 2); }
+
+__device__ __forceinline__ void cross_rank_reduce(const SweepArgs & a) {
+	DevState * st = a.st;
+	const uint32_t par = st->xseq & 1u, nw = a.nCol + 2u;
+	for (uint32_t k = threadIdx.x; k < nw; k += blockDim.x) {
+		const unsigned long long v = __ldcg(a.scratch + k);
+		if (v) for (uint32_t r = 0; r < a.nPeers; ++r) atomicAdd_system(xchg_slot(a.peerXchg[r], a.nCol, par) + k, v);
+	}
+	__threadfence_system();                               // my sums (and, through the ticket chain, every CTA's colour stores) before my arrival
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (uint32_t r = 0; r < a.nPeers; ++r) atomicAdd_system(a.peerXchg[r] + par, 1ull);
+		unsigned long long * mine = a.peerXchg[a.myRank] + par;
+		unsigned long long v;
+		long long t0 = clock64();
+		for (uint32_t spins = 0;; ++spins) {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+			if (v >= (unsigned long long)a.nPeers) break;
+			if ((spins & 1023u) == 1023u && clock64() - t0 > 20000000000ll) { st->errorFlag = 3u; break; }   // ~10 s: a peer never launched
+			__nanosleep(200);
+		}
+	}
+	__syncthreads();
+	unsigned long long * slot = xchg_slot(a.peerXchg[a.myRank], a.nCol, par);
+	for (uint32_t k = threadIdx.x; k < nw; k += blockDim.x) {
+		unsigned long long v;
+		asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot + k) : "memory");
+		a.scratch[k] = v;                                 // the global sums take the place of the local ones
+		slot[k] = 0ull;                                   // slot is clean for the collective after the next
+	}
+	if (threadIdx.x == 0) { a.peerXchg[a.myRank][par] = 0ull; st->xseq = st->xseq + 1u; }
+	__threadfence();
+	__syncthreads();
 }
 
 // finalize: executed by ONE CTA after all counters of the sweep are in `scratch` (fused: the last CTA of the
@@ -124,6 +184,18 @@ __device__ __forceinline__ void finalize_sweep_device(const SweepArgs & a) {
 		if (threadIdx.x == 0) {
 			if (t < a.historyCap) { a.history[2 * (size_t)t] = directed >> 1; a.history[2 * (size_t)t + 1] = viol; }
 			st->lastDirected = directed; st->lastViol = viol; st->countsSweep = t;
+			if (a.violList != nullptr) {                   // the violating vertices of C_t, if this launch emitted them
+				const uint32_t cnt = __ldcg(a.violCount);
+				const bool emitted = a.forceEmit || st->emitNow;
+				if (a.countOnly || conv) {                 // C_t stays the current colouring: keep the list for the repair
+					st->violListSweep = (emitted && cnt <= a.violCap) ? t : 0xffffffffu;
+					st->violListCount = cnt;
+				} else {
+					st->violListSweep = 0xffffffffu;
+					st->emitNow = (viol <= a.emitThreshold) ? 1u : 0u;
+				}
+				*a.violCount = 0u;
+			}
 			if (!a.countOnly) {
 				if (conv) st->convergedAt = (int32_t)t;
 				else st->sweep = t + 1;
@@ -281,6 +353,17 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 #pragma unroll
 		for (int w = 0; w < W; ++w) a.dbgMasks[(size_t)lv * W + w] = m[w];
 		a.dbgSame[lv] = same;
+	}
+	if (viol && a.violList != nullptr) {                      // tail cutting: remember who violates (one atomic per group of lanes)
+		if (a.forceEmit || __ldcg(&a.st->emitNow)) {
+			const unsigned act = __activemask();
+			const int leader = __ffs((int)act) - 1;
+			uint32_t base = 0;
+			if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(a.violCount, (uint32_t)__popc(act));
+			base = __shfl_sync(act, base, leader);
+			const uint32_t idx = base + (uint32_t)__popc(act & ((1u << (threadIdx.x & 31)) - 1u));
+			if (idx < a.violCap) a.violList[idx] = v;
+		}
 	}
 	if (a.countOnly) return;
 	uint32_t newc = myOwn;

@@ -29,6 +29,27 @@ def partition(n, world, align=256):
     return [(min(n, r * chunk), min(n, (r + 1) * chunk)) for r in range(world)], chunk
 
 
+def partition_by_nnz(rowptr, world, align=256):
+    """Contiguous vertex ranges balanced by the number of directed edges (prefix of cumulDegs): cut r is the first
+    vertex whose offset reaches r/world of nnz, rounded to a multiple of `align` (the kernels move owned colours as 16-byte
+    vectors / bulk copies; mcmcb200_create_partition insists on 256).  rowptr: numpy array or torch tensor of n+1 offsets.
+    Returns [(vBegin, vEnd)] -- ranges may be empty at the end of a very skewed graph."""
+    n = len(rowptr) - 1
+    nnz = int(rowptr[n])
+    cuts = [0]
+    for r in range(1, world):
+        target = nnz * r // world
+        if hasattr(rowptr, "cpu"):                       # torch tensor (device or host)
+            import torch
+            v = int(torch.searchsorted(rowptr, torch.tensor([target], dtype=rowptr.dtype, device=rowptr.device)).item())
+        else:
+            v = int(np.searchsorted(rowptr, target))
+        v = min(n, (v + align // 2) // align * align)
+        cuts.append(max(v, cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class _DevPtr:
     """zero-copy torch view of raw device memory (no ownership)"""
 
@@ -58,16 +79,20 @@ class GpuEngine:
         self.p2p = False
 
     def enable_p2p(self, rank, world, group=None):
-        """Fused exchange: map every rank's colour replicas (CUDA IPC) so that the sweep kernel stores each finished tile's
-        new colours straight into all of them over NVLink; the NCCL all-gather disappears, the counter all-reduce stays
-        (it is also the inter-rank barrier).  Returns False (and keeps the all-gather) where it does not apply."""
+        """Fused exchange: map every rank's colour replicas and counter-exchange block (CUDA IPC) so that the sweep kernel stores
+        each finished tile's new colours straight into all replicas over NVLink and all-reduces the counters itself -- no NCCL
+        call and no host in the sweep loop.  Returns False (and keeps all-gather + all-reduce) where it does not apply.
+        Protocol: (1) every rank says whether it is eligible (source-blocked sweep, export works) and NOBODY attaches unless all
+        are; (2) attach; (3) if any rank failed to map a peer, everybody detaches again."""
         import torch.distributed as dist
         if world < 2 or world > 8:
             return False
-        try:
-            mine = self.chain.ipc_export()
-        except Exception:
-            mine = None
+        mine = None
+        if self.chain.kernel_mode() in ("blocked", "blocked-overlapped"):
+            try:
+                mine = self.chain.ipc_export()
+            except Exception:
+                mine = None
         table = [None] * world
         dist.all_gather_object(table, mine, group=group)
         if any(t is None for t in table):
@@ -80,7 +105,8 @@ class GpuEngine:
         flags = [None] * world
         dist.all_gather_object(flags, ok, group=group)
         self.p2p = all(flags)
-        assert self.p2p or not ok, "fused exchange attached on some ranks only"
+        if not self.p2p and ok:
+            self.chain.ipc_detach()
         return self.p2p
 
     def _views(self):
@@ -98,6 +124,15 @@ class GpuEngine:
         self.t = 0
         self._bufs = None
         self._views()
+        self._fence_ranks()
+
+    def _fence_ranks(self):
+        """fused exchange: (re)initialisation clears this rank's exchange block; no peer may start the next collective (and add
+        into that block) before every rank is through it"""
+        if self.p2p:
+            import torch.distributed as dist
+            self.chain.synchronize()
+            dist.barrier()
 
     def init_colors_slice(self, host_ptr, sweeper):
         """Host interface at N GPUs: every rank uploads only the colours it owns; the slices are all-gathered on the device."""
@@ -106,6 +141,7 @@ class GpuEngine:
         self._views()
         sweeper.gather_current()
         self.chain.init_colors_finish()
+        self._fence_ranks()
 
     def local_sweep(self):
         self.chain.sweep(1)
@@ -139,10 +175,13 @@ class GpuEngine:
 
 
 class DistributedSweeper:
-    """Sweep driver of one rank.  All collectives are issued on the engine's stream so they order with its kernels."""
+    """Sweep driver of one rank.  All collectives are issued on the engine's stream so they order with its kernels.
+    parts: [(vBegin, vEnd)] of every rank (equal chunks -> one in-place all-gather; nnz-balanced ranges -> one broadcast per rank)."""
 
-    def __init__(self, engine, rank, world, chunk, group=None):
+    def __init__(self, engine, rank, world, chunk, group=None, parts=None):
         self.e, self.rank, self.world, self.chunk, self.group = engine, rank, world, chunk, group
+        self.parts = parts
+        self.uniform = parts is None or all(vb == r * chunk for r, (vb, ve) in enumerate(parts))
 
     def _on_stream(self):
         import contextlib
@@ -150,33 +189,47 @@ class DistributedSweeper:
         s = getattr(self.e, "stream", None)
         return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
 
+    def _gather(self, buf):
+        import torch.distributed as dist
+        eb = self.e.elem_bytes
+        if self.uniform:
+            cb = self.chunk * eb
+            full = buf[: cb * self.world]
+            dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb], group=self.group)
+        else:
+            for r, (vb, ve) in enumerate(self.parts):
+                if ve > vb:
+                    dist.broadcast(buf[vb * eb: ve * eb], src=r, group=self.group)
+
     def _exchange(self, colours):
         import torch.distributed as dist
         with self._on_stream():
             if colours:
-                cb = self.chunk * self.e.elem_bytes
-                full = self.e.next_colors()[: cb * self.world]
-                mine = full[self.rank * cb:(self.rank + 1) * cb]
-                dist.all_gather_into_tensor(full, mine, group=self.group)            # owned slices of C_{t+1}
+                self._gather(self.e.next_colors())                                   # owned slices of C_{t+1}
             dist.all_reduce(self.e.counters(), op=dist.ReduceOp.SUM, group=self.group)  # conflicts, violations, class deltas
 
     def gather_current(self):
         """all-gather the owned slices of the CURRENT colouring (sliced init)"""
-        import torch.distributed as dist
         with self._on_stream():
-            cb = self.chunk * self.e.elem_bytes
-            full = self.e.cur_colors()[: cb * self.world]
-            dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb], group=self.group)
+            self._gather(self.e.cur_colors())
 
     def sweep(self, k=1):
+        if getattr(self.e, "p2p", False):
+            # fused exchange: colours, counters and the inter-rank barrier all happen inside the sweep kernels -- k sweeps are
+            # 2k launches per rank, nothing else
+            self.e.chain.sweep(k)
+            self.e.t += k
+            return
         for _ in range(k):
             self.e.local_sweep()
-            self._exchange(colours=not getattr(self.e, "p2p", False))   # fused exchange: the kernel already stored into the peers
+            self._exchange(colours=True)
             self.e.finalize(advanced=True)
 
     def status(self):
         """Global counters of the current colouring (runs a distributed counting pass if they are stale)."""
         st = self.e.status()
+        if getattr(self.e, "p2p", False):
+            return st                                   # the counting pass (if one was needed) reduced across the ranks on the device
         if st.countsSweep != st.sweep:
             self._exchange(colours=False)
             self.e.finalize(advanced=False)
@@ -199,7 +252,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     import json
     import torch
     import torch.distributed as dist
-    from .graphgen import er_graph_torch
+    from .graphgen import er_graph_torch, rmat_graph_torch
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = f"cuda:{local_rank}"
@@ -208,19 +261,27 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     if args.n:
         n = args.n
     # every rank generates the same graph on its own GPU (deterministic), keeps its rows and frees the rest
-    rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=dev)
+    skewed = args.workload.startswith("c4")
+    if skewed:
+        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(max(1, (n - 1).bit_length()), deg, GRAPH_SEED, n_keep=n, device=dev)
+    else:
+        rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=dev)
+    # contiguous vertex ranges: equal vertex counts on Erdos-Renyi (they are nnz-balanced to a fraction of a percent and keep the
+    # NCCL fallback a single in-place all-gather), balanced by directed edges on skewed graphs
     parts, chunk = partition(n, world)
+    if skewed:
+        parts = partition_by_nnz(rowptr64, world)
     vb, ve = parts[rank]
     rp, nb, nnz_local = slice_csr_torch(rowptr64, neighs, vb, ve)
     del rowptr64, neighs
     torch.cuda.empty_cache()
-    nCol = max_deg
+    nCol = min(max_deg, 512) if skewed else max_deg      # (bench.py palette_for: R-MAT hubs have degree ~1e6)
     proposal = capi.PROPOSAL_UNIFORM if args.proposal == "uniform" else capi.PROPOSAL_DYNAMIC
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, seed=CHAIN_SEED,
                              convergence=capi.CONVERGE_VERTICES if proposal == capi.PROPOSAL_UNIFORM else capi.CONVERGE_EDGES)
     eng = GpuEngine(rp, nb, nnz_local, n, vb, ve, prm, local_rank)
     fused = eng.enable_p2p(rank, world) if os.environ.get("MCMCB200_NO_P2P") is None else False
-    sw = DistributedSweeper(eng, rank, world, chunk)
+    sw = DistributedSweeper(eng, rank, world, chunk, parts=parts)
 
     def timed_step():
         eng.init_colors(None)
@@ -277,7 +338,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8 colours / u32 ids / f32 CDF", "data": "synthetic",
             "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": args.proposal,
-                       "parallelism": f"vertex partition x{world}; colour exchange: " + ("fused into the sweep kernel (peer stores over NVLink)" if fused else "NCCL all-gather of u8 slices") + "; counters: one NCCL all-reduce per sweep",
+                       "parallelism": f"vertex partition x{world} ({'nnz-balanced' if skewed else 'equal vertex counts'}); " + ("colour exchange AND counter all-reduce + inter-rank barrier fused into the sweep kernels (peer stores / system-scope reductions over NVLink): no NCCL call, no host in the sweep loop" if fused else "NCCL all-gather of the narrow colour slices + one NCCL all-reduce of the counters per sweep"),
                        "step": "one sweep from the uniform random colouring incl. the colour exchange (max over ranks)",
                        "l2": "inputs larger than L2; no flush needed"},
             "edges_per_sec": value * nnz / n,

@@ -31,7 +31,7 @@ def mc():
 # this size), the two passes one after the other.  blocked-2buf: two half-size stage buffers per pass-B CTA, tile T+1 is
 # copied in (TMA) while tile T is computed.  binned: degree-binned direct sweep (large skewed graphs).
 KERNELS = ["direct", "blocked", "blocked-serial", "blocked-2buf", "binned"]
-TUNING = {"blocked": dict(stage_cap_bytes=45056), "blocked-serial": dict(stage_cap_bytes=65504), "blocked-2buf": dict(stage_cap_bytes=22528, stage_buffers=2)}
+TUNING = {"blocked": dict(stage_cap_bytes=32768), "blocked-serial": dict(stage_cap_bytes=65504), "blocked-2buf": dict(stage_cap_bytes=22528, stage_buffers=2)}
 
 
 def make_chain(mc, cumul, neighs, nCol, proposal=0, taboo=0, seed=0, convergence=0, tailcut=False, max_rip=250,
@@ -556,3 +556,42 @@ def test_statistical_gate_config5_vs_reference_pins(mc, golden_dir):
         assert all(u == r["usedColors"] for u, r in zip(used, recs))
         assert abs(np.mean(stds) - ref_std) <= 0.20 * ref_std, (ratio, stds, ref_std)
         assert abs(np.mean(sweeps) - ref_sw) <= 0.25 * ref_sw + 1.0, (ratio, sweeps, ref_sw)
+
+
+@pytest.mark.parametrize("kernel", [None, "blocked", "binned"])
+def test_tailcut_list_path_after_chain(mc, port, kernel):
+    """--tailcut protocol end to end: the chain stops on the device at <= z = max(50, n/2000) violating vertices, the sweep that
+    found this emitted the violators, and mcmcb200_tailcut repairs from that list (no rescan).  Colours before and after the repair,
+    counters and class sizes against the oracle (port.tailcut is pinned to the reference's tailCutting kernel in test_gpu_refgpu)."""
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    n = 300_000
+    cumul, neighs = er_graph_numpy(n, 16, seed=21)
+    nCol = int(np.diff(cumul.astype(np.int64)).max()) - 14       # a tight palette: the chain needs a few sweeps
+    z = max(50, n // 2000)
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=UNIFORM, seed=5, convergence=0, tailcut=True, kernel=kernel)
+    ch.init_colors(None)
+    c0 = port.init_colors(5, n, nCol)
+    want, sweeps, cnt, hit = port.run(cumul, neighs, nCol, EPS, c0, 5, UNIFORM, z=z)
+    assert 0 < cnt <= z and not hit
+    ch.sweep(250)
+    st = ch.status()
+    assert st.converged == 1 and st.sweep == sweeps and st.violatingVertices == cnt and st.z == z
+    assert np.array_equal(ch.get_colors(), want)
+    fixed, rounds, left = port.tailcut(cumul, neighs, nCol, want)
+    ch.tailcut(64)
+    got = ch.get_colors()
+    assert np.array_equal(got, fixed), np.flatnonzero(got != fixed)[:8]
+    st = ch.status()
+    assert st.conflictEdges == left == port.conflict_edges(cumul, neighs, fixed)
+    assert st.violatingVertices == port.violation_count(cumul, neighs, fixed)
+    assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(fixed, nCol))
+    # repairing twice changes nothing; and a colouring set by the caller (no emitted list) takes the count-pass fallback
+    ch.tailcut(64)
+    assert np.array_equal(ch.get_colors(), fixed)
+    ch.init_colors(c0)
+    f2, _, left2 = port.tailcut(cumul, neighs, nCol, c0)
+    try:
+        ch.tailcut(64)
+        assert np.array_equal(ch.get_colors(), f2) and ch.status().conflictEdges == left2
+    finally:
+        ch.close()

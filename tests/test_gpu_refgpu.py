@@ -56,7 +56,7 @@ def our_chain(mc, cumul, neighs, nCol, kernel, taboo=0, eps=EPS, tailcut=False, 
                                 seed=seed, tailcut=tailcut, epsilon=eps)
     flags = mc.FLAG_NO_EARLY_STOP | getattr(mc, KERNEL_FLAGS[kernel])
     try:
-        return mc.Chain(cumul, neighs, prm, device=0, flags=flags, stage_cap_bytes=45056 if kernel == "blocked" else 0)
+        return mc.Chain(cumul, neighs, prm, device=0, flags=flags, stage_cap_bytes=32768 if kernel == "blocked" else 0)
     except mc.McmcError as e:
         from mcmc_colorer_b200 import capi
         if kernel == "blocked" and e.code == capi.EUNSUPPORTED:
