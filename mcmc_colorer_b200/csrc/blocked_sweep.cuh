@@ -508,6 +508,15 @@ __device__ __forceinline__ void stage_tile_tma(const SweepArgs & a, const Blocke
 	tma_bulk_g2s(sm.sliceTab(buf), bl.sliceOff + (size_t)T * spt, bytesSoff, bar);
 	tma_bulk_g2s(sm.ownCol(buf), reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT), bytesOwn, bar);
 	if (bytesStage) tma_bulk_g2s_hint(sm.stageBuf(buf), static_cast<const ColT *>(bl.ecol) + a0, bytesStage, bar, polFirst);   // read once: evict_first
+#ifndef MCMCB200_PREFETCH_IDX
+#define MCMCB200_PREFETCH_IDX 1
+#endif
+	if (MCMCB200_PREFETCH_IDX) {
+		// the tile's SELL index words (2 B per edge, streamed by the mask loop with plain loads: ncu showed their first use as the
+		// kernel's largest stall, ~15 % of the samples waiting on DRAM): ask for the whole range in L2 now, while the copies fly
+		const uint32_t s0 = __ldg(bl.sliceOff + (size_t)T * spt), s1 = __ldg(bl.sliceOff + (size_t)(T + 1) * spt);
+		if (s1 > s0) bulk_prefetch_l2(bl.gidxS + s0, (s1 - s0) * (uint32_t)sizeof(uint2));
+	}
 }
 
 // per-tile views handed to the slot / heavy-list routines

@@ -99,6 +99,10 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void * dstSmem, const void * s
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
 	             :: "r"(smem_u32(dstSmem)), "l"(srcGmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+// pull a contiguous range (16-byte aligned, a multiple of 16 bytes) into L2 ahead of the loads that will stream it
+__device__ __forceinline__ void bulk_prefetch_l2(const void * srcGmem, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(srcGmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t make_policy_evict_first() {
 	uint64_t pol;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

@@ -486,14 +486,16 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool large = nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18);
 		const bool want = forceBlocked || (!forceDirect && !forceBinned && large);
 		if (want) {
-			// colour bytes a tile stages in shared memory.  Large partitions: 44 KiB, so that two pass-B CTAs and one pass-A CTA
-			// (64 KiB chunk) share an SM and the two passes overlap; smaller ones (fill/drain of the A->B pipeline would eat the
+			// colour bytes a tile stages in shared memory.  Large partitions: 32 KiB (tiles of 4 x 384 vertices on a mean-degree-16
+			// graph), so that two pass-B CTAs and one pass-A CTA (64 KiB chunk) share an SM and the two passes overlap; measured on
+			// config 3 (profiles/r02*): 24 KiB 4.38 ms, 32 KiB 3.64, 36 KiB 4.35, 44 KiB 4.01 -- short tiles keep pass B's per-tile
+			// phases short, too short ones cut pass A's runs.  Smaller partitions (fill/drain of the A->B pipeline would eat the
 			// gain; measured on config 5): the largest stage the 16-bit positions allow, passes back to back
-			uint32_t capBytes = nnzLocal >= (1ull << 29) ? 45056u : 65504u;
+			uint32_t capBytes = nnzLocal >= (1ull << 29) ? 32768u : 65504u;
 			uint32_t nbuf = 1u;
-			// pass-A work item: ~2^18 entries of one bucket when the passes overlap (fewer reloads of the 64 KiB chunk; measured
-			// 4.20 vs 4.28 ms on config 3), 2^17 back to back (pass A alone: 2.03 vs 2.23 ms at 2^19)
-			uint32_t itemEntries = nnzLocal >= (1ull << 29) ? (1u << 18) : (1u << 17);
+			// pass-A work item: 2^16 entries of one bucket when the passes overlap (the chunk reload is one bulk copy now; 2^15:
+			// 4.04 ms, 2^16: 3.64, 2^17: 3.70, 2^18: 3.81 on config 3), 2^17 back to back
+			uint32_t itemEntries = nnzLocal >= (1ull << 29) ? (1u << 16) : (1u << 17);
 			if (p->itemBits) itemEntries = 1u << p->itemBits;
 			if (p->stageCapBytes) capBytes = p->stageCapBytes;
 			if (p->stageBuffers) nbuf = p->stageBuffers;
@@ -565,7 +567,7 @@ int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned
 		src ^= 1;
 		listCount = c.nextCount;
 		if (c.flagged == 0) break;                                         // the pass found nothing to repair
-		if (c.inexact) break;
+		if (c.inexact) { ++used; break; }
 		if (c.nextFlagged == 0) { ++used; break; }
 	}
 	if (e == cudaSuccess && src == 1) e = cudaMemcpyAsync(h->d_violList[0], h->d_violList[1], sizeof(uint32_t) * (size_t)listCount, cudaMemcpyDeviceToDevice, h->stream);
@@ -585,6 +587,9 @@ int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned
 	cudaFree(d_order);
 	if (e != cudaSuccess) return cuda_fail(e, "tailcut (list)", __LINE__);
 	if (rounds) *rounds = used;
+	// a repaired vertex found every colour taken and kept a clashing one: vertices outside the list may violate now, so the
+	// remaining passes (the reference keeps going while conflicts are left, _main.cu:279) rescan the graph
+	if (c.inexact && c.nextFlagged > 0 && used < maxRounds) return 1;
 	return MCMCB200_OK;
 }
 
@@ -966,11 +971,14 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	std::vector<uint32_t> order(nCol);
 	for (uint32_t i = 0; i < nCol; ++i) order[i] = i;
 	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hh[a] < hh[b]; });
+	uint32_t usedByList = 0;
 	if (h->d_violList[0]) {
 		// ---- list-driven path (params.tailcut): the sweeps emitted the violating vertices; no rescan of the graph, no host
 		//      round trip per round.  Falls through to the full-scan path below when the list is not available. ----
-		int lrc = tailcut_from_list(h, s, cur, hist, order, maxRounds, rounds);
-		if (lrc != 1) return lrc;                                  // 1 = list unavailable / overflowed
+		uint32_t done = 0;
+		int lrc = tailcut_from_list(h, s, cur, hist, order, maxRounds, &done);
+		if (lrc != 1) { if (rounds) *rounds = done; return lrc; }  // 1 = list unavailable / overflowed / no longer exact
+		usedByList = done;
 	}
 	uint32_t * d_order = nullptr, * d_list = nullptr, * d_counters = nullptr; uint8_t * d_pending = nullptr, * d_ready = nullptr;
 	auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_list); cudaFree(d_counters); cudaFree(d_pending); cudaFree(d_ready); };
@@ -981,7 +989,7 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	if (e == cudaSuccess) e = cudaMalloc(&d_ready, std::max<uint32_t>(n, 1));
 	if (e == cudaSuccess) e = cudaMemcpy(d_order, order.data(), sizeof(uint32_t) * nCol, cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "tailcut workspace", __LINE__); }
-	uint32_t used = 0;
+	uint32_t used = usedByList;
 	for (; used < maxRounds; ++used) {                                     // while (conflictCounter > 0), _main.cu:279
 		uint32_t flagged = 0;
 		const int ce = launch_tailcut_pass(h->stream, h->colBytes, h->d_rowptr, h->d_neighs, n, nCol, cur, hist, d_order,

@@ -16,12 +16,3 @@ struct ColoringMCMCParams {
 	uint32_t tabooIteration;
 	bool     tailcut;
 };
-
-// Additions of the B200 build that have no slot in the reference struct; passed next to it.
-struct ColoringMCMCOptions {
-	uint32_t proposal = 1;     // MCMCB200_PROPOSAL_DYNAMIC: the shipped GPU variant (coloringMCMC.h:39)
-	uint32_t convergence = 1;  // conflicting edges (coloringMCMC_main.cu:169)
-	uint64_t seed = 0;
-	int      device = -1;
-	uint32_t sweepsPerCheck = 1;
-};

@@ -200,5 +200,54 @@ void ColoringMCMC_CPU<nodeW, edgeW>::saveColor(std::ofstream & outfile) {
 	for (size_t i = 0; i < C.size(); i++) outfile << i << " " << C[i] << "\n";
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ColoringLuby (cross-check): coloringLuby.cu:364-501 behaviour, log format :179-219
+// ------------------------------------------------------------------------------------------------------------------
+template <typename nodeW, typename edgeW>
+ColoringLuby<nodeW, edgeW>::ColoringLuby(Graph<nodeW, edgeW> * g, curandState *, uint64_t seed, int device)
+	: graph(g), nnodes(g->getStruct()->nNodes), seed(seed), device(device) {}
+
+template <typename nodeW, typename edgeW>
+void ColoringLuby<nodeW, edgeW>::run() {
+	auto * s = graph->getStruct();
+	C.assign(nnodes, 0u);
+	check(mcmcb200_luby_color(s->nNodes, s->nEdges, s->cumulDegs, s->neighs, seed, device, C.data(), &numOfColors, &rounds), "mcmcb200_luby_color");
+}
+
+template <typename nodeW, typename edgeW>
+void ColoringLuby<nodeW, edgeW>::saveStats(size_t it, float duration, std::ofstream & outFile) {
+	outFile << "Luby Colorer - GPU version - Report" << std::endl;
+	outFile << "-------------------------------------------" << std::endl;
+	outFile << "GRAPH INFO" << std::endl;
+	outFile << "Nodes: " << nnodes << " - Edges: " << graph->getStruct()->nEdges << std::endl;
+	outFile << "Max deg: " << graph->getMaxNodeDeg() << " - Min deg: " << graph->getMinNodeDeg() << " - Avg deg: " << graph->getMeanNodeDeg() << std::endl;
+	outFile << "Edge probability (for randomly generated graphs): " << graph->prob << std::endl;
+	outFile << "-------------------------------------------" << std::endl;
+	outFile << "EXECUTION INFO" << std::endl;
+	outFile << "Repetition: " << it << std::endl;
+	outFile << "Execution time: " << duration << std::endl;
+	outFile << "-------------------------------------------" << std::endl;
+	outFile << "Number of colors: " << numOfColors << std::endl;
+	outFile << "Color histogram:" << std::endl;
+	std::vector<size_t> histBins(numOfColors, 0);
+	for (uint32_t val : C) histBins[val - 1]++;                            // colours are 1-based (:199)
+	long sum = 0;
+	for (size_t idx = 0; idx < histBins.size(); idx++) { outFile << idx << ": " << histBins[idx] << std::endl; sum += (long)histBins[idx]; }
+	float mean = (int)sum / (float)numOfColors;
+	float variance = 0;
+	for (size_t val : histBins) variance += ((val - mean) * (val - mean));
+	variance /= (float)numOfColors;
+	outFile << "Average number of nodes for each color: " << mean << std::endl;
+	outFile << "Variance: " << variance << std::endl;
+	outFile << "StD: " << sqrtf(variance) << std::endl;
+}
+
+template <typename nodeW, typename edgeW>
+void ColoringLuby<nodeW, edgeW>::saveColor(std::ofstream & outfile) {
+	size_t idx = 0;
+	for (uint32_t val : C) outfile << idx++ << " " << val << std::endl;
+}
+
 template class ColoringMCMC<float, float>;
 template class ColoringMCMC_CPU<float, float>;
+template class ColoringLuby<float, float>;

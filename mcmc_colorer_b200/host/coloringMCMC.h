@@ -16,6 +16,15 @@
 #include "coloring.h"
 #include "graph.h"
 
+// Additions of the B200 build that have no slot in the reference struct; passed next to it.
+struct ColoringMCMCOptions {
+	uint32_t proposal = 1;     // MCMCB200_PROPOSAL_DYNAMIC: the shipped GPU variant (coloringMCMC.h:39)
+	uint32_t convergence = 1;  // conflicting edges (coloringMCMC_main.cu:169)
+	uint64_t seed = 0;
+	int      device = -1;
+	uint32_t sweepsPerCheck = 1;
+};
+
 struct mcmcb200_handle;
 struct curandStateXORWOW;                 // the reference passes curandState*; accepted and ignored (stateless Philox)
 typedef struct curandStateXORWOW curandState;
@@ -82,3 +91,26 @@ protected:
 	size_t iter{0};
 	bool maxIterReached{false};
 };
+
+// ColoringLuby<nodeW,edgeW>  graph_coloring/coloringLuby.h:30-93 (ctor(graph_d, randStates), run()/run_fast(), saveStats, saveColor,
+// getColoringGPU()->nCol): the cross-check colourer, host-driven MIS rounds on the device (mcmcb200_luby_color; run_fast's
+// dynamic parallelism does not exist on sm_100, both entry points run the same loop).  Colours are 1-based like the reference's.
+template <typename nodeW, typename edgeW> class ColoringLuby {
+public:
+	ColoringLuby(Graph<nodeW, edgeW> * inGraph_d, curandState * randStates, uint64_t seed = 0, int device = -1);
+	void run();
+	void run_fast() { run(); }
+	void saveStats(size_t it, float duration, std::ofstream & outFile);    // coloringLuby.cu:179-211
+	void saveColor(std::ofstream & outfile);                               // coloringLuby.cu:214-219
+	uint32_t getNumOfColors() const { return numOfColors; }
+	const std::vector<uint32_t> & getColors() const { return C; }
+
+protected:
+	Graph<nodeW, edgeW> * graph;
+	uint32_t nnodes;
+	uint64_t seed;
+	int device;
+	uint32_t numOfColors{0}, rounds{0};
+	std::vector<uint32_t> C;
+};
+

@@ -42,8 +42,8 @@ int main(int argc, char * argv[]) {
 
 	for (uint32_t i = 0; i < repet; i++) {
 		std::cout << "Repetition: " << i << std::endl;
-		if (commandLine.lubygpu || commandLine.greedyff || commandLine.rebalanced_greedyff)
-			std::cout << "--lubygpu/--grdffgpu/--vffgpu: not part of this build (out of the hot-path scope, see DESIGN.md)" << std::endl;
+		if (commandLine.greedyff || commandLine.rebalanced_greedyff)
+			std::cout << "--grdffgpu/--vffgpu: not part of this build (different algorithms, out of the hot-path scope, see DESIGN.md)" << std::endl;
 
 		ColoringMCMCParams params;                                       // main.cu:160-168
 		params.numColorRatio  = numColorRatio;
@@ -56,6 +56,21 @@ int main(int argc, char * argv[]) {
 		params.tailcut        = commandLine.tailcut;
 
 		try {
+			if (commandLine.lubygpu) {                                   // main.cu:90-109 (cross-check colourer)
+				ColoringLuby<float, float> colLuby(&graph_d, nullptr, seed + i, commandLine.device);
+				auto t0 = std::chrono::steady_clock::now();
+				colLuby.run_fast();
+				double duration = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+				std::cout << "LubyGPU - number of colors: " << colLuby.getNumOfColors() << std::endl;
+				std::cout << "LubyGPU elapsed time: " << duration << std::endl;
+				std::ofstream lubyFileLog, lubyFileColors;
+				lubyFileLog.open(outDir + "/" + commandLine.graphName + "-LUBY-" + std::to_string(i) + ".log");
+				colLuby.saveStats(i, duration, lubyFileLog);
+				lubyFileLog.close();
+				lubyFileColors.open(outDir + "/" + commandLine.graphName + "-LUBY-" + std::to_string(i) + "-colors.txt");
+				colLuby.saveColor(lubyFileColors);
+				lubyFileColors.close();
+			}
 			if (commandLine.mcmccpu) {                                   // main.cu:170-190
 				ColoringMCMC_CPU<float, float> mcmc_cpu(test, params, seed + i);
 				auto t0 = std::chrono::steady_clock::now();

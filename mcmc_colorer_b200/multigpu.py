@@ -65,13 +65,13 @@ def _view(ptr, nelem, typestr, device):
 class GpuEngine:
     """The B200 engine of one rank: a partitioned mcmcb200 handle plus torch views of its exchange buffers."""
 
-    def __init__(self, d_rowptr_local, d_neighs_local, nnz_local, n_global, v_begin, v_end, params, device_index):
+    def __init__(self, d_rowptr_local, d_neighs_local, nnz_local, n_global, v_begin, v_end, params, device_index, extra_flags=0, **tuning):
         import torch
         self.device = f"cuda:{device_index}"
-        flags = capi.FLAG_NO_FUSED_FINALIZE | capi.FLAG_NO_EARLY_STOP
+        flags = capi.FLAG_NO_FUSED_FINALIZE | capi.FLAG_NO_EARLY_STOP | extra_flags
         self.keep = (d_rowptr_local, d_neighs_local)
         self.chain = Chain(params=params, device=device_index, flags=flags, n_global=n_global, v_begin=v_begin, v_end=v_end,
-                           device_csr=(d_rowptr_local.data_ptr(), d_neighs_local.data_ptr(), nnz_local))
+                           device_csr=(d_rowptr_local.data_ptr(), d_neighs_local.data_ptr(), nnz_local), **tuning)
         self.n, self.nCol = n_global, params.nCol
         self.stream = torch.cuda.ExternalStream(self.chain.stream(), device=self.device)
         self.t = 0

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 from mcmc_colorer_b200 import ColoringMCMCParams
 from mcmc_colorer_b200.graphgen import er_graph_numpy
-from mcmc_colorer_b200.multigpu import DistributedSweeper, GpuEngine, partition
+from mcmc_colorer_b200.multigpu import DistributedSweeper, GpuEngine, partition, partition_by_nnz
 from oracle.pyoracle import Port
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -20,29 +20,29 @@ dev = f"cuda:{lr}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 P = Port()
 ok = True
-# (n, mean degree, proposal, fused P2P exchange, stage bytes: 45056 = the large-partition configuration, pass A || pass B)
-for n, deg, proposal, p2p, cap in [(50_001, 12, 0, False, None), (50_001, 12, 1, False, None), (300_000, 20, 0, False, None),
-                                   (300_000, 20, 1, True, None), (1_000_003, 16, 0, True, None), (1_000_003, 16, 1, True, "45056")]:
+# (n, mean degree, proposal, fused exchange (peer colour stores + device-side counter all-reduce), stage bytes: 32768 = the
+#  large-partition configuration with pass A || pass B, nnz-balanced cut points instead of equal vertex counts)
+for n, deg, proposal, p2p, cap, by_nnz in [(50_001, 12, 0, False, 0, False), (50_001, 12, 1, False, 0, True), (300_000, 20, 0, False, 0, False),
+                                           (300_000, 20, 1, True, 0, True), (1_000_003, 16, 0, True, 0, False), (1_000_003, 16, 1, True, 32768, False)]:
     cumul, neighs = er_graph_numpy(n, deg, seed=5)
     nCol = int(np.diff(cumul.astype(np.int64)).max())
     parts, chunk = partition(n, world)
+    if by_nnz:
+        parts = partition_by_nnz(cumul.astype(np.int64), world)
     vb, ve = parts[rank]
     e0, e1 = int(cumul[vb]), int(cumul[ve])
     rp = torch.from_numpy((cumul[vb:ve + 1].astype(np.int64) - e0).astype(np.int32)).to(dev)
     nb = torch.zeros(e1 - e0 + 16, dtype=torch.int32, device=dev)
     nb[: e1 - e0] = torch.from_numpy(neighs[e0:e1].astype(np.int32)).to(dev)
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=proposal, seed=11)
-    if cap:
-        os.environ["MCMCB200_STAGE_CAP_BYTES"] = cap
-    eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr)
-    os.environ.pop("MCMCB200_STAGE_CAP_BYTES", None)
+    eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr, stage_cap_bytes=cap)
     if rank == 0:
         print(f"n={n} proposal={proposal}: sweep mode {eng.chain.kernel_mode()}")
     if p2p:
         got_p2p = eng.enable_p2p(rank, world)
         if rank == 0:
-            print(f"n={n}: fused P2P exchange {'ON' if got_p2p else 'not available -> all-gather'}")
-    sw = DistributedSweeper(eng, rank, world, chunk)
+            print(f"n={n}: fused exchange {'ON' if got_p2p else 'not available -> NCCL all-gather + all-reduce'}")
+    sw = DistributedSweeper(eng, rank, world, chunk, parts=parts)
     eng.init_colors(None)
     c = P.init_colors(11, n, nCol)
     for s in range(5):
@@ -55,6 +55,14 @@ for n, deg, proposal, p2p, cap in [(50_001, 12, 0, False, None), (50_001, 12, 1,
         got = eng.colors_host()
         if not np.array_equal(got, c):
             ok = False; print(f"rank {rank}: colours differ at sweep {s + 1}: {np.flatnonzero(got != c)[:8]}")
+    sw.sweep(3)                                         # a batch: with the fused exchange these are 6 launches per rank and nothing else
+    for s in range(5, 8):
+        c, _ = P.sweep(cumul, neighs, nCol, 1e-8, c, P.tape(11, s + 1, n, proposal), proposal)
+    if not np.array_equal(eng.colors_host(), c):
+        ok = False; print(f"rank {rank}: colours differ after the 3-sweep batch")
+    st = sw.status()
+    if (st.conflictEdges, st.violatingVertices, st.sweep) != (P.conflict_edges(cumul, neighs, c), P.violation_count(cumul, neighs, c), 8):
+        ok = False; print(f"rank {rank}: counters differ after the batch: {(st.conflictEdges, st.violatingVertices, st.sweep)}")
     if not np.array_equal(eng.chain.class_sizes().astype(np.uint32), P.class_sizes(c, nCol)):
         ok = False; print(f"rank {rank}: class sizes differ")
     # sliced host interface: every rank uploads only its own colours, the slices meet on the device

@@ -489,13 +489,13 @@ def big_graph():
 @pytest.mark.parametrize("tuning", ["default", "production"])
 def test_large_graph_default_path_vs_oracle(mc, port, big_graph, tuning):
     """default: whatever mcmcb200_create picks for this size, nothing forced.  production: the configuration the library picks by
-    itself from 2^29 directed edges on (BASELINE config 3: 44 KiB stage, 2^18-entry pass-A items, pass A || pass B) -- selected
+    itself from 2^29 directed edges on (BASELINE config 3: 32 KiB stage, 2^16-entry pass-A items, pass A || pass B) -- selected
     through the mcmcb200_params tuning fields because a graph that large does not fit a test.  Two free-running sweeps, colours
     and counters against the CPU oracle."""
     n, nnz, max_deg, rowptr, neighs, cumul_h, neighs_h = big_graph
     nCol = max_deg
     prm = mc.ColoringMCMCParams(nCol=nCol, proposal=mc.PROPOSAL_UNIFORM, convergence=mc.CONVERGE_VERTICES, seed=31)
-    tune = dict(stage_cap_bytes=45056, item_bits=18) if tuning == "production" else {}
+    tune = dict(stage_cap_bytes=32768, item_bits=16) if tuning == "production" else {}
     ch = mc.Chain(params=prm, device=0, flags=mc.FLAG_NO_EARLY_STOP, n_global=n, v_begin=0, v_end=n,
                   device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz), **tune)
     assert ch.kernel_mode() == ("blocked-overlapped" if tuning == "production" else ch.kernel_mode())

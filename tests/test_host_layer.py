@@ -105,3 +105,34 @@ def test_cli_surface_and_loud_failure_without_gpu(host, tmp_path):
                             str(tmp_path / "o")], capture_output=True, text=True)
         assert r.returncode != 0 and "no usable sm_100a CUDA device" in r.stderr
         assert "Nodes: 200" in r.stdout
+
+
+def test_integration_option_a_compiles_against_reference_headers(tmp_path):
+    """INTEGRATION.md Option A: host/coloringMCMC.{h,cpp} dropped into a translation unit that uses the REFERENCE's graph.h /
+    graphCPU.cpp / coloring.h (tests/integration/option_a_main.cpp = main.cu:160-198).  Compiles, links against libmcmcb200.so and
+    -- without a B200 -- fails loudly at mcmcb200_create.  Needs the reference tree (build container only)."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("no /root/reference here")
+    import shutil
+    host_dir = os.path.join(ROOT, "mcmc_colorer_b200", "host")
+    for f in ("coloringMCMC.h", "coloringMCMC.cpp"):
+        shutil.copy(os.path.join(host_dir, f), tmp_path / f)          # away from host/graph.h and host/coloring.h
+    shutil.copy(os.path.join(ROOT, "tests", "integration", "option_a_main.cpp"), tmp_path / "option_a_main.cpp")
+    src = open(tmp_path / "coloringMCMC.cpp").read().replace('#include "../../include/mcmcb200.h"', '#include "mcmcb200.h"')
+    open(tmp_path / "coloringMCMC.cpp", "w").write(src)
+    exe = str(tmp_path / "option_a")
+    lib_dir = os.path.join(ROOT, "mcmc_colorer_b200")
+    cmd = ["g++", "-std=c++14", "-O1", "-w", "-o", exe, str(tmp_path / "option_a_main.cpp"), str(tmp_path / "coloringMCMC.cpp"),
+           ref + "/utils/fileImporter.cpp", ref + "/utils/timer.cpp", ref + "/utils/miscUtils.cpp",
+           "-I" + os.path.join(ROOT, "oracle", "shims"), "-I" + ref, "-I" + ref + "/graph", "-I" + ref + "/graph_coloring", "-I" + ref + "/utils",
+           "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lmcmcb200", "-Wl,-rpath," + lib_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    run = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "option_a ok" in run.stdout, run.stderr
+        assert os.path.exists(tmp_path / "optA-MCMC_GPU-0.log") and os.path.exists(tmp_path / "optA-MCMC_CPU-0-colors.txt")
+    else:
+        assert run.returncode == 2 and "no usable sm_100a CUDA device" in run.stderr, run.stderr
