@@ -132,6 +132,13 @@ void mcmcb200_destroy(mcmcb200_handle * h);
  * each < nCol.  Resets sweep to 0, taboo to 0 and the replay position. */
 int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors);
 
+/* The same two transfers in the device's own narrow colour format -- one byte per vertex for palettes of up to 256 colours, two
+ * above (mcmcb200_color_bytes) -- for callers that do not need the reference's uint32 layout (coloring.h:7): a quarter of the
+ * PCIe bytes, no conversion kernels.  elemBytes must equal mcmcb200_color_bytes (EINVAL otherwise); colours >= nCol are EINVAL. */
+int mcmcb200_color_bytes(mcmcb200_handle * h, uint32_t * elemBytes);
+int mcmcb200_init_colors_narrow(mcmcb200_handle * h, const void * colors /* [nGlobal] u8 or u16 */, uint32_t elemBytes);
+int mcmcb200_get_colors_narrow(mcmcb200_handle * h, void * out /* [nGlobal] u8 or u16 */, uint32_t elemBytes);
+
 /* Replay mode (parity tests): sweep k (k = 0,1,...) draws u[k*n + v] for vertex v instead of Philox.
  * sweeps == 0 or u == NULL returns to Philox. */
 int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps);

@@ -32,7 +32,7 @@ SYMBOLS = [
     "mcmcb200_stream", "mcmcb200_synchronize", "mcmcb200_last_sweep_ms", "mcmcb200_launch_count", "mcmcb200_kernel_mode", "mcmcb200_csr_from_edges", "mcmcb200_csr_free",
     "mcmcb200_strerror", "mcmcb200_last_cuda_error", "mcmcb200_abi_version", "mcmcb200_luby_color",
     "mcmcb200_ipc_export", "mcmcb200_ipc_attach", "mcmcb200_ipc_detach", "mcmcb200_init_colors_slice", "mcmcb200_init_colors_finish",
-    "mcmcb200_get_colors_slice",
+    "mcmcb200_get_colors_slice", "mcmcb200_color_bytes", "mcmcb200_init_colors_narrow", "mcmcb200_get_colors_narrow",
 ]
 
 
@@ -93,6 +93,9 @@ def lib():
     L.mcmcb200_init_colors_slice.argtypes = [vp, vp]
     L.mcmcb200_init_colors_finish.argtypes = [vp]
     L.mcmcb200_get_colors_slice.argtypes = [vp, vp]
+    L.mcmcb200_color_bytes.argtypes = [vp, u32p]
+    L.mcmcb200_init_colors_narrow.argtypes = [vp, vp, C.c_uint32]
+    L.mcmcb200_get_colors_narrow.argtypes = [vp, vp, C.c_uint32]
     L.mcmcb200_ipc_export.argtypes = [vp, vp]
     L.mcmcb200_ipc_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.mcmcb200_ipc_detach.argtypes = [vp]

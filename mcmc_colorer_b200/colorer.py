@@ -163,6 +163,27 @@ class Chain:
     def init_colors_ptr(self, host_ptr):
         capi.check(self.L.mcmcb200_init_colors(self.h, C.c_void_p(host_ptr)), "mcmcb200_init_colors")
 
+    def color_bytes(self):
+        eb = C.c_uint32()
+        capi.check(self.L.mcmcb200_color_bytes(self.h, C.byref(eb)), "mcmcb200_color_bytes")
+        return eb.value
+
+    def init_colors_narrow_ptr(self, host_ptr, elem_bytes):
+        capi.check(self.L.mcmcb200_init_colors_narrow(self.h, C.c_void_p(host_ptr), elem_bytes), "mcmcb200_init_colors_narrow")
+
+    def get_colors_narrow_ptr(self, host_ptr, elem_bytes):
+        capi.check(self.L.mcmcb200_get_colors_narrow(self.h, C.c_void_p(host_ptr), elem_bytes), "mcmcb200_get_colors_narrow")
+
+    def init_colors_narrow(self, colors):
+        a = np.ascontiguousarray(colors, np.uint8 if self.color_bytes() == 1 else np.uint16)
+        assert len(a) == self.n
+        self.init_colors_narrow_ptr(a.ctypes.data, a.itemsize)
+
+    def get_colors_narrow(self):
+        out = np.empty(self.n, np.uint8 if self.color_bytes() == 1 else np.uint16)
+        self.get_colors_narrow_ptr(out.ctypes.data, out.itemsize)
+        return out
+
     def set_tape(self, u):
         if u is None:
             capi.check(self.L.mcmcb200_set_tape(self.h, None, 0), "mcmcb200_set_tape")

@@ -390,8 +390,8 @@ int compute_class_sizes(mcmcb200_handle * h, const void * colors, unsigned long 
 	CU(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * h->p.nCol, h->stream));
 	const int blocks = std::max(1, std::min<int>(h->smCount * 4, (int)((h->nGlobal + 255) / 256)));
 	const size_t smem = sizeof(unsigned int) * h->p.nCol;
-	if (h->colBytes == 1) class_sizes_kernel<uint8_t><<<blocks, 256, smem, h->stream>>>((const uint8_t *)colors, h->nGlobal, h->p.nCol, hist);
-	else class_sizes_kernel<uint16_t><<<blocks, 256, smem, h->stream>>>((const uint16_t *)colors, h->nGlobal, h->p.nCol, hist);
+	if (h->colBytes == 1) class_sizes_kernel<uint8_t><<<blocks, 256, smem, h->stream>>>((const uint8_t *)colors, h->nGlobal, h->p.nCol, hist, h->d_state);
+	else class_sizes_kernel<uint16_t><<<blocks, 256, smem, h->stream>>>((const uint16_t *)colors, h->nGlobal, h->p.nCol, hist, h->d_state);
 	h->launches++;
 	CU(cudaGetLastError());
 	return MCMCB200_OK;
@@ -720,6 +720,38 @@ int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors) {
 	rc = read_state(h, &s); if (rc) return rc;
 	if (s.errorFlag) { h->colorsInit = false; return MCMCB200_EINVAL; }   // a colour >= nCol
 	h->colorsInit = true;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_color_bytes(mcmcb200_handle * h, uint32_t * elemBytes) {
+	if (!h || !elemBytes) return MCMCB200_EINVAL;
+	*elemBytes = (uint32_t)h->colBytes;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_init_colors_narrow(mcmcb200_handle * h, const void * colors, uint32_t elemBytes) {
+	if (!h || !colors) return MCMCB200_EINVAL;
+	if (elemBytes != (uint32_t)h->colBytes) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	int rc = reset_state(h); if (rc) return rc;
+	CU(cudaMemcpyAsync(h->d_colors[0], colors, (size_t)h->nGlobal * h->colBytes, cudaMemcpyHostToDevice, h->stream));
+	rc = compute_class_sizes(h, h->d_colors[0], h->d_hist[0]); if (rc) return rc;    // (also the colour < nCol check)
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	if (s.errorFlag) { h->colorsInit = false; return MCMCB200_EINVAL; }
+	h->colorsInit = true;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_colors_narrow(mcmcb200_handle * h, void * out, uint32_t elemBytes) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	if (elemBytes != (uint32_t)h->colBytes) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	CU(cudaMemcpyAsync(out, h->d_colors[s.sweep & 1], (size_t)h->nGlobal * h->colBytes, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
 	return MCMCB200_OK;
 }
 

@@ -788,14 +788,17 @@ __global__ void widen_colors_kernel(const ColT * src, uint32_t * dst, uint32_t n
 	if (v < n) dst[v] = (uint32_t)src[v];
 }
 
-// class sizes of a colouring (used at init only; the sweeps keep them current through deltas)
+// class sizes of a colouring (used at init only; the sweeps keep them current through deltas); also the range check of
+// colourings that arrive in the narrow device format (mcmcb200_init_colors_narrow)
 template <typename ColT>
-__global__ void class_sizes_kernel(const ColT * colors, uint32_t n, uint32_t nCol, unsigned long long * hist) {
+__global__ void class_sizes_kernel(const ColT * colors, uint32_t n, uint32_t nCol, unsigned long long * hist, DevState * st) {
 	extern __shared__ unsigned int s_h[];
 	for (uint32_t k = threadIdx.x; k < nCol; k += blockDim.x) s_h[k] = 0u;
 	__syncthreads();
-	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
-		atomicAdd(&s_h[colors[v]], 1u);
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+		const uint32_t c = colors[v];
+		if (c < nCol) atomicAdd(&s_h[c], 1u); else st->errorFlag = 1u;
+	}
 	__syncthreads();
 	for (uint32_t k = threadIdx.x; k < nCol; k += blockDim.x)
 		if (s_h[k]) atomicAdd(hist + k, (unsigned long long)s_h[k]);

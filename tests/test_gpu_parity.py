@@ -595,3 +595,30 @@ def test_tailcut_list_path_after_chain(mc, port, kernel):
         assert np.array_equal(ch.get_colors(), f2) and ch.status().conflictEdges == left2
     finally:
         ch.close()
+
+
+def test_narrow_host_interface(mc, c1_graph, port):
+    """mcmcb200_{init,get}_colors_narrow: the device's own u8 / u16 colour format at the host boundary (a quarter of the PCIe bytes of
+    the reference's uint32 layout); same results as the uint32 calls, range-checked."""
+    cumul, neighs = c1_graph
+    from mcmc_colorer_b200 import capi
+    for nCol, dt in ((137, np.uint8), (300, np.uint16)):
+        ch = make_chain(mc, cumul, neighs, nCol, seed=4)
+        assert ch.color_bytes() == np.dtype(dt).itemsize
+        c0 = port.init_colors(17, 1000, nCol)
+        ch.init_colors_narrow(c0.astype(dt))
+        st = ch.status()
+        assert (st.sweep, st.conflictEdges, st.violatingVertices) == (0, port.conflict_edges(cumul, neighs, c0), port.violation_count(cumul, neighs, c0))
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c0, nCol))
+        ch.sweep(1)
+        want, _ = port.sweep(cumul, neighs, nCol, EPS, c0, port.tape(4, 1, 1000, 0), 0)
+        got = ch.get_colors_narrow()
+        assert got.dtype == dt and np.array_equal(got.astype(np.uint32), want) and np.array_equal(ch.get_colors(), want)
+        bad = c0.astype(dt); bad[3] = nCol
+        with pytest.raises(mc.McmcError) as e:
+            ch.init_colors_narrow(bad)
+        assert e.value.code == capi.EINVAL
+        with pytest.raises(mc.McmcError) as e:                          # wrong element size for this palette
+            ch.init_colors_narrow_ptr(c0.ctypes.data, 4)
+        assert e.value.code == capi.EINVAL
+        ch.close()
