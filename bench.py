@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--item-bits", type=int, default=0, help="tuning experiments: mcmcb200_params.itemBits (0 = automatic)")
     ap.add_argument("--stage-buffers", type=int, default=0, help="tuning experiments: mcmcb200_params.stageBuffers (0 = automatic)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning experiments: the two passes of the blocked sweep back to back")
+    ap.add_argument("--ncol", type=int, default=0, help="override the palette size (default: palette_for(workload, maxDeg))")
+    ap.add_argument("--traj", type=int, default=0, help="with --quick: also run a chain of this many sweeps and report its violation trajectory")
     ap.add_argument("--quick", action="store_true", help="tuning experiments: kernel timing only (no e2e, no time-to-colouring, no CPU baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -247,7 +249,7 @@ def main():
     t_gen = time.perf_counter()
     rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev, args.workload)
     t_gen = time.perf_counter() - t_gen
-    nCol = palette_for(args.workload, max_deg)
+    nCol = args.ncol if args.ncol else palette_for(args.workload, max_deg)
     proposal = mc.PROPOSAL_UNIFORM if args.proposal == "uniform" else mc.PROPOSAL_DYNAMIC
     prm = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal,
                                 convergence=mc.CONVERGE_VERTICES if proposal == mc.PROPOSAL_UNIFORM else mc.CONVERGE_EDGES,
@@ -267,8 +269,18 @@ def main():
             ch.init_colors(None); torch.cuda.synchronize(); ch.sweep(1); ms.append(ch.last_sweep_ms())
         ch.init_colors(None); ch.sweep(10); chain_ms = ch.last_sweep_ms() / 10.0
         st = ch.status()
+        traj = []
+        if args.traj:
+            ch.init_colors(None)
+            done = 0
+            for k in [1, 2, 3, 5, 10, 20, 40, 80, 160, 250]:
+                if k > args.traj:
+                    break
+                ch.sweep(k - done); done = k
+                s_ = ch.status()
+                traj.append([k, int(s_.conflictEdges), int(s_.violatingVertices), int(s_.usedColors)])
         t = float(np.mean(ms))
-        print(json.dumps({"quick": True, "workload": args.workload, "ms_per_step": t, "min_ms": float(np.min(ms)), "frac": (8 * nnz + 12 * n + 4) / (t * 1e-3) / 1e9 / measured_peak()[0],
+        print(json.dumps({"quick": True, "traj": traj, "maxDeg": int(max_deg), "nnz": int(nnz), "workload": args.workload, "ms_per_step": t, "min_ms": float(np.min(ms)), "frac": (8 * nnz + 12 * n + 4) / (t * 1e-3) / 1e9 / measured_peak()[0],
                           "chain_ms_per_sweep": chain_ms, "kernel_mode": ch.kernel_mode(), "create_ms": create_ms, "nCol": nCol,
                           "after_10": [int(st.conflictEdges), int(st.violatingVertices)],
                           "tuning": [args.stage_cap_bytes, args.item_bits, args.stage_buffers, bool(args.no_overlap)], "lib": os.environ.get("MCMCB200_LIB", "")}))

@@ -176,7 +176,8 @@ int mcmcb200_conflicts_of(mcmcb200_handle * h, const uint32_t * colors, uint64_t
 /* Occupancy bitmask of vertex v (global id, must be owned) w.r.t. the current colouring, as built by the sweep
  * kernel: bit c of word c/32 set iff a neighbour has colour c.  words = ceil(nCol/32). */
 int mcmcb200_debug_occupancy(mcmcb200_handle * h, uint32_t v, uint32_t * maskWords);
-/* All owned vertices at once: masks[(v-vBegin)*words64 + w] (64-bit words, words64 = ceil(nCol/64)) and
+/* All owned vertices at once: masks[(v-vBegin)*words64 + w] (64-bit words; words64 = 1, 2, 4 or 8 for palettes of up to
+ * 64 / 128 / 256 / 512 colours, ceil(nCol/64) above) and
  * same[v-vBegin] = number of neighbours sharing v's colour. */
 int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t * same);
 
@@ -222,6 +223,8 @@ int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches);
 #define MCMCB200_MODE_BLOCKED 1
 #define MCMCB200_MODE_BLOCKED_OVERLAPPED 2
 #define MCMCB200_MODE_DIRECT_BINNED 3      /* one launch per sweep, thread / warp / CTA rows by degree (large skewed graphs) */
+#define MCMCB200_MODE_WIDE_BINNED 4        /* palettes above 512 colours: the degree-binned rows with colour lists / shared-memory bitmaps
+                                              instead of register masks (one table launch + one sweep launch per sweep) */
 int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode);
 
 const char * mcmcb200_strerror(int code);

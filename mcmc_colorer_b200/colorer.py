@@ -243,7 +243,7 @@ class Chain:
     def debug_all_occupancy(self):
         nloc = self.v_end - self.v_begin
         w64 = (self.nCol + 63) // 64
-        w64 = 1 if w64 <= 1 else 2 if w64 <= 2 else 4 if w64 <= 4 else 8
+        w64 = 1 if w64 <= 1 else 2 if w64 <= 2 else 4 if w64 <= 4 else 8 if w64 <= 8 else w64
         masks = np.zeros((max(nloc, 1), w64), np.uint64)
         same = np.zeros(max(nloc, 1), np.uint32)
         capi.check(self.L.mcmcb200_debug_all_occupancy(self.h, masks.ctypes.data_as(C.c_void_p),
@@ -290,7 +290,7 @@ class Chain:
         capi.check(self.L.mcmcb200_last_sweep_ms(self.h, C.byref(ms)), "mcmcb200_last_sweep_ms")
         return ms.value
 
-    KERNEL_MODES = ("direct", "blocked", "blocked-overlapped", "direct-binned")
+    KERNEL_MODES = ("direct", "blocked", "blocked-overlapped", "direct-binned", "wide-binned")
 
     def kernel_mode(self):
         """which sweep implementation the handle runs: 'direct', 'blocked' or 'blocked-overlapped' (mcmcb200_kernel_mode)"""

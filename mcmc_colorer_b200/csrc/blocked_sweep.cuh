@@ -357,7 +357,7 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 		// one 4-entry granule per lane per step: a warp reads 256 contiguous bytes of local ids and 128 of destinations, and
 		// its store covers whole 32-byte sectors wherever a run spans them (full-sector first touches need no fill in L2)
 #ifndef MCMCB200_A_KU
-#define MCMCB200_A_KU 8
+#define MCMCB200_A_KU 12     /* config 3: 8 -> 3.62 ms, 10 -> 3.52, 12 -> 3.49 per sweep (57 registers: one pass-A CTA still fits next to two pass-B CTAs); 14 no longer does */
 #endif
 		constexpr uint32_t kU = MCMCB200_A_KU;   // granules in flight per thread: 12 bytes of loads each (pass A is bound by bytes in flight)
 		const uint32_t g0 = beg >> 2, g1 = end >> 2;           // runs are padded to 4 entries: items are whole granules
@@ -443,6 +443,29 @@ __device__ __forceinline__ bool wait_part_ready(const BlockedArgs & bl, uint32_t
 		__nanosleep(100);
 	}
 }
+#ifndef MCMCB200_EARLY_TICKET
+#define MCMCB200_EARLY_TICKET 0     /* measured on config 3: 3.65 ms with, 3.64 without (the L2 prefetches compete with pass A) */
+#endif
+__device__ __forceinline__ bool part_ready_now(const BlockedArgs & bl, uint32_t T) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bl.sync + 2 + bl.tilePart[T]) : "memory");
+	return v >= bl.P;
+}
+// L2 prefetch of everything tile T streams or copies (ranges widened to 16-byte boundaries; all arrays have slack behind their end)
+template <typename ColT>
+__device__ __forceinline__ void prefetch_tile_l2(const SweepArgs & a, const BlockedArgs & bl, const ColT * cur, uint32_t T) {
+	const uint32_t TV = bl.TV, spt = TV >> 5;
+	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
+	const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
+	constexpr uint32_t alignE = 16u / (uint32_t)sizeof(ColT);
+	const uint32_t a0 = tb & ~(alignE - 1u);
+	const uint32_t bytesStage = ((te - a0) * (uint32_t)sizeof(ColT) + 15u) & ~15u;
+	if (bytesStage) bulk_prefetch_l2(static_cast<const ColT *>(bl.ecol) + a0, bytesStage);
+	bulk_prefetch_l2(bl.slotInfo + (size_t)T * TV, TV * (uint32_t)sizeof(uint16_t));
+	bulk_prefetch_l2(reinterpret_cast<const unsigned char *>(cur) + (size_t)(a.vBegin + v0) * sizeof(ColT), (nv * (uint32_t)sizeof(ColT) + 15u) & ~15u);
+	const uint32_t s0 = __ldg(bl.sliceOff + (size_t)T * spt), s1 = __ldg(bl.sliceOff + (size_t)(T + 1) * spt);
+	if (s1 > s0) bulk_prefetch_l2(bl.gidxS + s0, (s1 - s0) * (uint32_t)sizeof(uint2));
+}
 // 1 << c with PTX semantics: shift amounts >= 64 give 0 (the dummy colour sets no bit)
 __device__ __forceinline__ unsigned long long bit64_clamped(uint32_t c) {
 	unsigned long long r;
@@ -492,7 +515,7 @@ struct PassBShared {
 // the gathered neighbour colours (pass A left the tile's whole stage image contiguous in ecol) -- and complete on `bar`.
 template <int W, typename ColT>
 __device__ __forceinline__ void stage_tile_tma(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const ColT * cur,
-                                               uint32_t T, uint32_t buf, unsigned long long * bar, uint64_t polFirst) {
+                                               uint32_t T, uint32_t buf, unsigned long long * bar, uint64_t polFirst, bool prefetchIdx = true) {
 	const uint32_t TV = bl.TV, spt = TV >> 5;
 	const uint32_t v0 = T * TV, nv = min(TV, a.nLocal - v0);
 	const uint32_t tb = __ldg(bl.tileBase + T), te = __ldg(bl.tileBase + T + 1);
@@ -511,7 +534,7 @@ __device__ __forceinline__ void stage_tile_tma(const SweepArgs & a, const Blocke
 #ifndef MCMCB200_PREFETCH_IDX
 #define MCMCB200_PREFETCH_IDX 1
 #endif
-	if (MCMCB200_PREFETCH_IDX) {
+	if (MCMCB200_PREFETCH_IDX && prefetchIdx) {
 		// the tile's SELL index words (2 B per edge, streamed by the mask loop with plain loads: ncu showed their first use as the
 		// kernel's largest stall, ~15 % of the samples waiting on DRAM): ask for the whole range in L2 now, while the copies fly
 		const uint32_t s0 = __ldg(bl.sliceOff + (size_t)T * spt), s1 = __ldg(bl.sliceOff + (size_t)(T + 1) * spt);
@@ -713,8 +736,15 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 
 	// thread 0 is the producer: it takes the next tile (ascending order: the order pass A completes them in), waits until pass A
 	// has delivered the tile's part and issues the bulk copies into stage buffer `buf`; the CTA consumes the buffers in turn.
+	// (MCMCB200_EARLY_TICKET, single stage buffer) the ticket of the NEXT tile is taken while the current one is computed, and -- if
+	// pass A has already delivered its part -- everything the tile will need (stage image, slot table, colours, SELL index words) is
+	// pulled into L2 a whole tile ahead, so that the bulk copies at the end of the tile and the first index loads hit L2.
+	uint32_t nextT = 0xffffffffu; bool nextPrefetched = false;
 	auto produce = [&](uint32_t buf) {
-		uint32_t Tn = atomicAdd(bl.sync + 1, 1u);
+		uint32_t Tn;
+		bool idxDone = false;
+		if (MCMCB200_EARLY_TICKET && nextT != 0xffffffffu) { Tn = nextT; idxDone = nextPrefetched; nextT = 0xffffffffu; }
+		else Tn = atomicAdd(bl.sync + 1, 1u);
 		if (Tn < bl.numTiles) {
 			bool ok;
 			if (MCMCB200_TIMING) { const unsigned long long w0 = global_ns(); ok = wait_part_ready(bl, Tn, st); atomicAdd(bl.dbgTimes + 4, global_ns() - w0); }
@@ -724,7 +754,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		sm.tileOf[buf] = Tn;
 		if (Tn < bl.numTiles) {
 			fence_proxy_async();                                  // pass A's stores (acquired above) and this CTA's reads of the buffer precede the copies
-			stage_tile_tma<W, ColT>(a, bl, sm, cur, Tn, buf, sm.bars + buf, polFirst);
+			stage_tile_tma<W, ColT>(a, bl, sm, cur, Tn, buf, sm.bars + buf, polFirst, !idxDone);
 		} else mbar_arrive(sm.bars + buf);                        // nothing to copy: complete the phase so that the consumers see tileOf
 	};
 	if (tid == 0) for (uint32_t b = 0; b < nbuf; ++b) produce(b);
@@ -739,6 +769,11 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		tv.slot = sm.slotTab(buf); tv.soff = sm.sliceTab(buf); tv.own = sm.ownCol(buf); tv.stage = sm.stageBuf(buf); tv.snew = sm.newCol(buf);
 		tv.heavyCount = sm.ctl + 1;
 		tv.draw = (a.tape || a.countOnly) ? nullptr : sm.draw;
+		if (MCMCB200_EARLY_TICKET && nbuf == 1u && tid == 0) {
+			nextT = atomicAdd(bl.sync + 1, 1u);
+			nextPrefetched = false;
+			if (nextT < bl.numTiles && part_ready_now(bl, nextT)) { prefetch_tile_l2<ColT>(a, bl, cur, nextT); nextPrefetched = true; }
+		}
 		// the tile's draws: one Philox4x32-10 call per 4 consecutive vertices (tiles start 256-aligned), parked in shared memory
 		if (tv.draw) {
 			const uint32_t g0 = (a.vBegin + tv.v0) >> 2;

@@ -4,6 +4,7 @@
 #include "tailcut_kernel.cuh"
 #include "blocked_build.cuh"
 #include "binned_sweep.cuh"
+#include "wide_sweep.cuh"
 #include "csr_build.cuh"
 #include "luby_kernel.cuh"
 
@@ -71,6 +72,9 @@ struct mcmcb200_handle {
 	int smCount = 0;
 	BlockedLayout bl;                    // source-blocked two-pass layout (valid => the sweeps use it)
 	BinnedLayout bn;                     // degree-binned direct sweep (valid => used when bl is not)
+	bool wide = false;                   // nCol > 512: wide_sweep_kernel over the binned lists (wide_sweep.cuh)
+	float * d_wideS = nullptr, * d_wideTab = nullptr;
+	uint32_t maskWords64 = 1;            // 64-bit words of one vertex' occupancy mask (debug interface)
 	void * peerColors[2][kMaxPeers] = {};  // fused multi-GPU exchange: IPC-mapped colour buffers of every rank (own = local)
 	uint32_t * d_violList[2] = {nullptr, nullptr};   // tail cutting: violating vertices emitted by the sweeps / left by the last repair pass
 	uint32_t * d_violCount = nullptr; uint32_t violCap = 0;
@@ -208,8 +212,39 @@ cudaError_t configure_binned(mcmcb200_handle * h) {
 	}
 }
 
+cudaError_t launch_sweep_wide(mcmcb200_handle * h, const SweepArgs & a) {
+	const BinnedArgs b = make_binned_args(h->bn);
+	WideArgs wa{};
+	wide_geometry(h->p.nCol, wa);
+	wa.S = h->d_wideS; wa.tab = h->d_wideTab; wa.words64 = h->maskWords64;
+	cudaError_t e = cudaMemsetAsync(h->bn.counters, 0, 4 * sizeof(uint32_t), h->stream);
+	if (e != cudaSuccess) return e;
+	if (!a.countOnly) { wide_tables_kernel<<<(h->p.nCol + 255) / 256, 256, 0, h->stream>>>(a, wa); h->launches++; }
+	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) wide_sweep_kernel<true><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b, wa);
+	else wide_sweep_kernel<false><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b, wa);
+	return cudaGetLastError();
+}
+
+cudaError_t configure_wide(mcmcb200_handle * h) {
+	BinnedLayout & L = h->bn;
+	WideArgs wa{};
+	wide_geometry(h->p.nCol, wa);
+	L.smem = wide_smem_bytes(wa);
+	cudaError_t e = cudaFuncSetAttribute(wide_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	int o0 = 0, o1 = 0;
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, wide_sweep_kernel<false>, kThreadsBin, L.smem);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, wide_sweep_kernel<true>, kThreadsBin, L.smem);
+	if (e != cudaSuccess) return e;
+	const int o = o0 < o1 ? o0 : o1;
+	if (o < 1) { L.valid = false; return cudaSuccess; }
+	L.grid = o * h->smCount;
+	return cudaSuccess;
+}
+
 cudaError_t launch_sweep(mcmcb200_handle * h, const SweepArgs & a) {
 	h->launches++;   // (the blocked path counts its first pass itself)
+	if (h->wide) return launch_sweep_wide(h, a);
 	switch (h->W) {
 	case 1: return launch_sweep_t<1, uint8_t>(h, a);
 	case 2: return launch_sweep_t<2, uint8_t>(h, a);
@@ -279,7 +314,8 @@ int check_params(const mcmcb200_params * p, uint32_t nGlobal) {
 	if (!p || p->nCol == 0 || nGlobal == 0) return MCMCB200_EINVAL;
 	if (p->proposal > 1u || p->convergence > 1u) return MCMCB200_EINVAL;
 	if (!(p->epsilon >= 0.0f)) return MCMCB200_EINVAL;
-	if (p->nCol > 64u * kMaxColWords) return MCMCB200_EUNSUPPORTED;   // wide-palette path: not in this build
+	if (p->nCol > 65535u) return MCMCB200_EUNSUPPORTED;               // colours are at most 16 bits on the device
+	if (p->nCol > 64u * kMaxColWords && (p->flags & (MCMCB200_FLAG_FORCE_BLOCKED | MCMCB200_FLAG_FORCE_DIRECT))) return MCMCB200_EUNSUPPORTED;   // wide palettes: wide_sweep_kernel only
 	if (p->tabooIteration > 65535u) return MCMCB200_EUNSUPPORTED;
 	if (p->proposal == MCMCB200_PROPOSAL_DYNAMIC && p->nCol < 2) return MCMCB200_EINVAL;
 	if (p->reserved != 0u || p->stageBuffers > 2u || (p->itemBits && (p->itemBits < 12u || p->itemBits > 24u))) return MCMCB200_EINVAL;
@@ -313,6 +349,8 @@ int select_device(const mcmcb200_params * p, int * devOut, int * smCount) {
 int alloc_chain_state(mcmcb200_handle * h) {
 	const uint32_t nCol = h->p.nCol;
 	h->W = nCol <= 64 ? 1 : nCol <= 128 ? 2 : nCol <= 256 ? 4 : 8;
+	h->wide = nCol > 64u * kMaxColWords;
+	h->maskWords64 = h->wide ? (nCol + 63u) / 64u : (uint32_t)h->W;
 	h->colBytes = nCol <= 256 ? 1 : 2;
 	h->z = h->p.tailcut ? std::max<uint64_t>(50, h->nGlobal / 2000) : 0;   // coloringMCMC_main.cu:150-157
 	h->historyCap = std::max<uint32_t>(h->p.maxRip + 2u, 1024u);
@@ -345,12 +383,21 @@ int alloc_chain_state(mcmcb200_handle * h) {
 	CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(unsigned long long) * xchg_words(nCol), h->stream));
 	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (nCol + 2), h->stream));
 	CU(cudaMemsetAsync(h->d_history, 0, sizeof(unsigned long long) * 2 * h->historyCap, h->stream));
-	h->smemBytes = sweep_smem_bytes(nCol, h->W, h->colBytes);
-	int perSM = 0;
-	CU(sweep_occupancy(h, &perSM));
-	if (perSM < 1) return MCMCB200_EUNSUPPORTED;
-	const uint32_t numTiles = (h->nLocal + kTileV - 1) / kTileV;
-	h->gridBlocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>(numTiles, (uint32_t)(perSM * h->smCount)));
+	if (h->wide) {
+		CU(cudaMalloc(&h->d_wideS, sizeof(float) * ((size_t)nCol + 1)));
+		CU(cudaMalloc(&h->d_wideTab, sizeof(float) * ((size_t)nCol + 1)));
+		CU(cudaMemsetAsync(h->d_wideTab, 0, sizeof(float) * ((size_t)nCol + 1), h->stream));
+		wide_S_kernel<<<1, 32, 0, h->stream>>>(h->d_wideS, nCol, h->p.epsilon);
+		h->launches++;
+		CU(cudaGetLastError());
+	} else {
+		h->smemBytes = sweep_smem_bytes(nCol, h->W, h->colBytes);
+		int perSM = 0;
+		CU(sweep_occupancy(h, &perSM));
+		if (perSM < 1) return MCMCB200_EUNSUPPORTED;
+		const uint32_t numTiles = (h->nLocal + kTileV - 1) / kTileV;
+		h->gridBlocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>(numTiles, (uint32_t)(perSM * h->smCount)));
+	}
 	CU(cudaStreamSynchronize(h->stream));
 	return MCMCB200_OK;
 }
@@ -389,7 +436,7 @@ int narrow_into(mcmcb200_handle * h, const uint32_t * hostColors, void * dst) {
 int compute_class_sizes(mcmcb200_handle * h, const void * colors, unsigned long long * hist) {
 	CU(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * h->p.nCol, h->stream));
 	const int blocks = std::max(1, std::min<int>(h->smCount * 4, (int)((h->nGlobal + 255) / 256)));
-	const size_t smem = sizeof(unsigned int) * h->p.nCol;
+	const size_t smem = h->p.nCol <= 8192u ? sizeof(unsigned int) * h->p.nCol : 0;   // (palettes beyond 8 Ki colours: global atomics)
 	if (h->colBytes == 1) class_sizes_kernel<uint8_t><<<blocks, 256, smem, h->stream>>>((const uint8_t *)colors, h->nGlobal, h->p.nCol, hist, h->d_state);
 	else class_sizes_kernel<uint16_t><<<blocks, 256, smem, h->stream>>>((const uint16_t *)colors, h->nGlobal, h->p.nCol, hist, h->d_state);
 	h->launches++;
@@ -484,7 +531,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
 		const bool forceBinned = (p->flags & MCMCB200_FLAG_FORCE_BINNED) != 0;
 		const bool large = nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18);
-		const bool want = forceBlocked || (!forceDirect && !forceBinned && large);
+		const bool want = !h->wide && (forceBlocked || (!forceDirect && !forceBinned && large));
 		if (want) {
 			// colour bytes a tile stages in shared memory.  Large partitions: 32 KiB (tiles of 4 x 384 vertices on a mean-degree-16
 			// graph), so that two pass-B CTAs and one pass-A CTA (64 KiB chunk) share an SM and the two passes overlap; measured on
@@ -508,12 +555,12 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			if (forceBlocked && !h->bl.valid) return fail(MCMCB200_EUNSUPPORTED);
 		}
 		// large graph whose rows do not fit the blocked layout (hubs): degree-binned direct sweep instead of the tile-synchronous one
-		if (!h->bl.valid && !forceDirect && !forceBlocked && (forceBinned || large)) {
+		if (!h->bl.valid && !forceDirect && !forceBlocked && (forceBinned || large || h->wide)) {
 			cudaError_t e = build_binned_layout(h->bn, h->d_rowptr, h->nLocal, h->stream, &h->launches);
-			if (e == cudaSuccess && h->bn.valid) e = configure_binned(h);
+			if (e == cudaSuccess && h->bn.valid) e = h->wide ? configure_wide(h) : configure_binned(h);
 			if (e != cudaSuccess) return fail(cuda_fail(e, "build_binned_layout", __LINE__));
 			if (!h->bn.valid) free_binned_layout(h->bn);
-			if (forceBinned && !h->bn.valid) return fail(MCMCB200_EUNSUPPORTED);
+			if ((forceBinned || h->wide) && !h->bn.valid) return fail(h->nLocal == 0 && h->wide ? MCMCB200_EUNSUPPORTED : MCMCB200_ENOMEM);
 		}
 	}
 	rc = reset_state(h);
@@ -557,9 +604,9 @@ int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned
 	for (; e == cudaSuccess && used < maxRounds; ++used) {                 // while (conflictCounter > 0), _main.cu:279
 		if (listCount == 0) break;
 		if ((e = cudaMemsetAsync(h->d_tcCnt, 0, sizeof(TailcutCounters), h->stream)) != cudaSuccess) break;
-		const uint32_t lb = (listCount + 255) / 256;
+		const uint32_t lb = (uint32_t)(((uint64_t)listCount * 32u + 255u) / 256u);   // a warp per listed vertex
 		tc_filter_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_flist, h->d_tcCnt);
-		tc_rounds_kernel<ColT><<<1, 1024, 0, h->stream>>>(h->d_rowptr, h->d_neighs, nCol, cur, h->d_pending, h->d_flist, h->d_tcCnt, d_order, hist);
+		tc_rounds_kernel<ColT><<<1, kTcThreads, tc_smem_bytes(nCol), h->stream>>>(h->d_rowptr, h->d_neighs, nCol, cur, h->d_pending, h->d_flist, h->d_tcCnt, d_order, hist);
 		tc_recount_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_violList[src ^ 1], h->d_tcCnt);
 		h->launches += 3;
 		if ((e = cudaMemcpyAsync(&c, h->d_tcCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) break;
@@ -688,6 +735,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
 	free_blocked_layout(h->bl);
 	free_binned_layout(h->bn);
+	cudaFree(h->d_wideS); cudaFree(h->d_wideTab);
 	mcmcb200_ipc_detach(h);
 	cudaFree(h->d_xchg);
 	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcCnt);
@@ -957,7 +1005,7 @@ int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t
 	if (!h->colorsInit) return MCMCB200_ESTATE;
 	CU(cudaSetDevice(h->device));
 	unsigned long long * d_m = nullptr; uint32_t * d_s = nullptr;
-	const size_t nm = (size_t)std::max<uint32_t>(h->nLocal, 1) * h->W;
+	const size_t nm = (size_t)std::max<uint32_t>(h->nLocal, 1) * h->maskWords64;
 	CU(cudaMalloc(&d_m, sizeof(unsigned long long) * nm));
 	cudaError_t e = cudaMalloc(&d_s, sizeof(uint32_t) * std::max<uint32_t>(h->nLocal, 1));
 	if (e != cudaSuccess) { cudaFree(d_m); return cuda_fail(e, "cudaMalloc(dbgSame)", __LINE__); }
@@ -966,7 +1014,7 @@ int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t
 	if (!rc) rc = run_count_pass(h, h->d_colors[s.sweep & 1], h->d_countOut, d_m, d_s);
 	if (!rc) {
 		e = cudaStreamSynchronize(h->stream);
-		if (e == cudaSuccess) e = cudaMemcpy(masks, d_m, sizeof(unsigned long long) * (size_t)h->nLocal * h->W, cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess) e = cudaMemcpy(masks, d_m, sizeof(unsigned long long) * (size_t)h->nLocal * h->maskWords64, cudaMemcpyDeviceToHost);
 		if (e == cudaSuccess) e = cudaMemcpy(same, d_s, sizeof(uint32_t) * h->nLocal, cudaMemcpyDeviceToHost);
 		if (e != cudaSuccess) rc = cuda_fail(e, "debug copy", __LINE__);
 	}
@@ -976,12 +1024,12 @@ int mcmcb200_debug_all_occupancy(mcmcb200_handle * h, uint64_t * masks, uint32_t
 
 int mcmcb200_debug_occupancy(mcmcb200_handle * h, uint32_t v, uint32_t * maskWords) {
 	if (!h || !maskWords || v < h->vBegin || v >= h->vEnd) return MCMCB200_EINVAL;
-	std::vector<uint64_t> masks((size_t)h->nLocal * h->W);
+	std::vector<uint64_t> masks((size_t)h->nLocal * h->maskWords64);
 	std::vector<uint32_t> same(h->nLocal);
 	int rc = mcmcb200_debug_all_occupancy(h, masks.data(), same.data()); if (rc) return rc;
 	const uint32_t words = (h->p.nCol + 31) / 32;
 	for (uint32_t w = 0; w < words; ++w) {
-		const uint64_t m = masks[(size_t)(v - h->vBegin) * h->W + (w >> 1)];
+		const uint64_t m = masks[(size_t)(v - h->vBegin) * h->maskWords64 + (w >> 1)];
 		maskWords[w] = (uint32_t)(m >> (32 * (w & 1)));
 	}
 	return MCMCB200_OK;
@@ -1012,10 +1060,11 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 		if (lrc != 1) { if (rounds) *rounds = done; return lrc; }  // 1 = list unavailable / overflowed / no longer exact
 		usedByList = done;
 	}
-	uint32_t * d_order = nullptr, * d_list = nullptr, * d_counters = nullptr; uint8_t * d_pending = nullptr, * d_ready = nullptr;
-	auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_list); cudaFree(d_counters); cudaFree(d_pending); cudaFree(d_ready); };
+	uint32_t * d_order = nullptr, * d_list = nullptr, * d_heavy = nullptr, * d_counters = nullptr; uint8_t * d_pending = nullptr, * d_ready = nullptr;
+	auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_list); cudaFree(d_heavy); cudaFree(d_counters); cudaFree(d_pending); cudaFree(d_ready); };
 	cudaError_t e = cudaMalloc(&d_order, sizeof(uint32_t) * nCol);
 	if (e == cudaSuccess) e = cudaMalloc(&d_list, sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+	if (e == cudaSuccess) e = cudaMalloc(&d_heavy, sizeof(uint32_t) * ((size_t)n + 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(uint32_t) * 2);
 	if (e == cudaSuccess) e = cudaMalloc(&d_pending, std::max<uint32_t>(n, 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_ready, std::max<uint32_t>(n, 1));
@@ -1025,7 +1074,7 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	for (; used < maxRounds; ++used) {                                     // while (conflictCounter > 0), _main.cu:279
 		uint32_t flagged = 0;
 		const int ce = launch_tailcut_pass(h->stream, h->colBytes, h->d_rowptr, h->d_neighs, n, nCol, cur, hist, d_order,
-		                                   d_pending, d_ready, d_list, d_counters, &flagged, &h->launches);
+		                                   d_pending, d_ready, d_list, d_heavy, d_counters, &flagged, &h->launches);
 		if (ce) { cleanup(); return cuda_fail((cudaError_t)ce, "tailcut pass", __LINE__); }
 		if (flagged == 0) break;                                           // no conflicting edge left
 	}
@@ -1197,7 +1246,7 @@ int mcmcb200_last_sweep_ms(mcmcb200_handle * h, float * ms) {
 int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode) {
 	if (!h || !mode) return MCMCB200_EINVAL;
 	*mode = h->bl.valid ? (h->overlap ? MCMCB200_MODE_BLOCKED_OVERLAPPED : MCMCB200_MODE_BLOCKED)
-	                    : h->bn.valid ? MCMCB200_MODE_DIRECT_BINNED : MCMCB200_MODE_DIRECT;
+	                    : h->wide ? MCMCB200_MODE_WIDE_BINNED : h->bn.valid ? MCMCB200_MODE_DIRECT_BINNED : MCMCB200_MODE_DIRECT;
 	return MCMCB200_OK;
 }
 

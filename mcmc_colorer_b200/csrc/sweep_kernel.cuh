@@ -793,6 +793,13 @@ __global__ void widen_colors_kernel(const ColT * src, uint32_t * dst, uint32_t n
 template <typename ColT>
 __global__ void class_sizes_kernel(const ColT * colors, uint32_t n, uint32_t nCol, unsigned long long * hist, DevState * st) {
 	extern __shared__ unsigned int s_h[];
+	if (nCol > 8192u) {                                           // palettes too wide for a shared-memory histogram (launched without one)
+		for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+			const uint32_t c = colors[v];
+			if (c < nCol) atomicAdd(hist + c, 1ull); else st->errorFlag = 1u;
+		}
+		return;
+	}
 	for (uint32_t k = threadIdx.x; k < nCol; k += blockDim.x) s_h[k] = 0u;
 	__syncthreads();
 	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {

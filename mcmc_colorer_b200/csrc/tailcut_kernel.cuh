@@ -12,6 +12,64 @@
 
 namespace mcmcb200 {
 
+// rows longer than this are repaired by a whole CTA with an occupancy bitmap in shared memory (nCol bits); shorter ones by a warp
+// that re-scans the row for every candidate colour (a hub row of 10^6 neighbours times a palette of 10^3 candidates would not end)
+constexpr uint32_t kTcHeavyDeg = 2048;
+constexpr uint32_t kTcThreads = 1024;
+
+// warp: does any neighbour of the row [e0, e1) satisfy pred(u)?  (lanes stride the row, coalesced; early exit per 32 entries)
+template <typename Pred>
+__device__ __forceinline__ bool tc_warp_any(const uint32_t * __restrict__ neighs, uint32_t e0, uint32_t e1, int lane, Pred pred) {
+	for (uint32_t e = e0; e < e1; e += 32u) {
+		const bool hit = (e + lane < e1) && pred(neighs[e + lane]);
+		if (__any_sync(0xffffffffu, hit)) return true;
+	}
+	return false;
+}
+
+// the reference's colour choice (_utils.cu:89-97): keep the colour if no neighbour has it, else the first of order[0 .. nCol-2]
+// that no neighbour has, else order[nCol-1] untested.  Warp version: one row scan per candidate.  *inexact: the result clashes.
+template <typename ColT>
+__device__ __forceinline__ uint32_t tc_pick_warp(const uint32_t * __restrict__ neighs, uint32_t e0, uint32_t e1, const ColT * colors,
+                                                 uint32_t old, uint32_t nCol, const uint32_t * __restrict__ order, int lane, bool * inexact) {
+	auto occupied = [&](uint32_t c) { return tc_warp_any(neighs, e0, e1, lane, [&](uint32_t u) { return (uint32_t)colors[u] == c; }); };
+	uint32_t nodeCol = old, j = 0;
+	while (occupied(nodeCol) && j < nCol) { nodeCol = order[j]; j++; }
+	*inexact = (j == nCol) && occupied(nodeCol);
+	return nodeCol;
+}
+
+// CTA version: occupancy bitmap of the row in shared memory (bm: (nCol+31)/32 words; s_best: one word), then a parallel search
+// of the first free candidate.  Every thread of the CTA must call it; returns the same value to all.
+template <typename ColT>
+__device__ __forceinline__ uint32_t tc_pick_cta(const uint32_t * __restrict__ neighs, uint32_t e0, uint32_t e1, const ColT * colors,
+                                                uint32_t old, uint32_t nCol, const uint32_t * __restrict__ order, uint32_t * bm, uint32_t * s_best,
+                                                bool * inexact) {
+	const uint32_t words = (nCol + 31u) / 32u;
+	for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) bm[w] = 0u;
+	if (threadIdx.x == 0) *s_best = 0xffffffffu;
+	__syncthreads();
+	for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+		const uint32_t c = colors[neighs[e]], bit = 1u << (c & 31u);
+		if (!(bm[c >> 5] & bit)) atomicOr(&bm[c >> 5], bit);
+	}
+	__syncthreads();
+	auto occ = [&](uint32_t c) { return (bm[c >> 5] >> (c & 31u)) & 1u; };
+	uint32_t res;
+	if (!occ(old)) { res = old; *inexact = false; }
+	else {
+		for (uint32_t j = threadIdx.x; j + 1u < nCol; j += blockDim.x)
+			if (!occ(order[j])) { atomicMin(s_best, j); break; }
+		__syncthreads();
+		const uint32_t b = *s_best;
+		res = (b != 0xffffffffu) ? order[b] : order[nCol - 1u];
+		*inexact = (b == 0xffffffffu) && occ(res);
+	}
+	__syncthreads();                                          // bm / s_best may be reused right away
+	return res;
+}
+
+// ---- full-scan path: one reference pass over the whole graph ----
 template <typename ColT>
 __global__ void tailcut_flag_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t n,
                                     const ColT * __restrict__ colors, uint8_t * pending, uint32_t * list, uint32_t * listCount) {
@@ -27,48 +85,72 @@ __global__ void tailcut_flag_kernel(const uint32_t * __restrict__ rowptr, const 
 	if (flag) list[atomicAdd(listCount, 1u)] = v;
 }
 
+// warp per listed vertex
 __global__ void tailcut_ready_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs,
                                      const uint8_t * __restrict__ pending, const uint32_t * __restrict__ list, uint32_t listCount,
                                      uint8_t * ready) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
 	const uint32_t v = list[i];
-	if (!pending[v]) { ready[i] = 0; return; }
-	bool ok = true;
-	for (uint32_t e = rowptr[v]; e < rowptr[v + 1] && ok; ++e) {
-		const uint32_t u = neighs[e];
-		ok = !(u < v && pending[u]);
-	}
-	ready[i] = ok ? 1 : 0;
+	if (!pending[v]) { if (lane == 0) ready[i] = 0; return; }
+	const bool blocked = tc_warp_any(neighs, rowptr[v], rowptr[v + 1], lane, [&](uint32_t u) { return u < v && pending[u]; });
+	if (lane == 0) ready[i] = blocked ? 0 : 1;
 }
 
+// warp per listed vertex; rows longer than kTcHeavyDeg are handed to tailcut_apply_heavy_kernel (heavy[0] = count, then ids)
 template <typename ColT>
 __global__ void tailcut_apply_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol,
                                      ColT * colors, uint8_t * pending, const uint32_t * __restrict__ list, uint32_t listCount,
                                      const uint8_t * __restrict__ ready, const uint32_t * __restrict__ order,
-                                     unsigned long long * hist, uint32_t * remaining) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                     unsigned long long * hist, uint32_t * remaining, uint32_t * heavy) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
 	const uint32_t v = list[i];
 	if (!pending[v]) return;
-	if (!ready[i]) { atomicAdd(remaining, 1u); return; }
+	if (!ready[i]) { if (lane == 0) atomicAdd(remaining, 1u); return; }
 	const uint32_t e0 = rowptr[v], e1 = rowptr[v + 1];
-	auto occupied = [&](uint32_t c) {
-		for (uint32_t e = e0; e < e1; ++e) if ((uint32_t)colors[neighs[e]] == c) return true;
-		return false;
-	};
+	if (e1 - e0 > kTcHeavyDeg) { if (lane == 0) heavy[1u + atomicAdd(heavy, 1u)] = v; return; }
 	const uint32_t old = colors[v];
-	uint32_t nodeCol = old, j = 0;
-	while (occupied(nodeCol) && j < nCol) { nodeCol = order[j]; j++; }      // _utils.cu:91-95
-	colors[v] = (ColT)nodeCol;                                               // :97
-	pending[v] = 0;
-	if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+	bool inexact;
+	const uint32_t nodeCol = tc_pick_warp<ColT>(neighs, e0, e1, colors, old, nCol, order, lane, &inexact);
+	__syncwarp();
+	if (lane == 0) {
+		colors[v] = (ColT)nodeCol;                                           // :97
+		pending[v] = 0;
+		if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+	}
 }
 
+template <typename ColT>
+__global__ void __launch_bounds__(kTcThreads)
+tailcut_apply_heavy_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol, ColT * colors, uint8_t * pending,
+                           const uint32_t * __restrict__ order, unsigned long long * hist, const uint32_t * heavy) {
+	extern __shared__ uint32_t tc_smem[];
+	uint32_t * bm = tc_smem + 4;
+	const uint32_t cnt = heavy[0];
+	for (uint32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+		const uint32_t v = heavy[1u + k];
+		const uint32_t old = colors[v];
+		bool inexact;
+		const uint32_t nodeCol = tc_pick_cta<ColT>(neighs, rowptr[v], rowptr[v + 1], colors, old, nCol, order, bm, tc_smem, &inexact);
+		if (threadIdx.x == 0) {
+			colors[v] = (ColT)nodeCol;
+			pending[v] = 0;
+			if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+		}
+		__syncthreads();
+	}
+}
+
+inline size_t tc_smem_bytes(uint32_t nCol) { return sizeof(uint32_t) * (4 + (size_t)(nCol + 31u) / 32u); }
+
 // One reference pass.  Returns a cudaError_t as int; *flaggedOut = number of vertices the pass visited.
+// d_heavy: [1 + n] scratch for the ready hub rows of a round (may alias nothing else).
 inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t * rowptr, const uint32_t * neighs, uint32_t n,
                                uint32_t nCol, void * colors, unsigned long long * hist, const uint32_t * d_order,
-                               uint8_t * d_pending, uint8_t * d_ready, uint32_t * d_list, uint32_t * d_counters /* [2] */,
+                               uint8_t * d_pending, uint8_t * d_ready, uint32_t * d_list, uint32_t * d_heavy, uint32_t * d_counters /* [2] */,
                                uint32_t * flaggedOut, uint64_t * launches) {
 	cudaError_t e;
 	if ((e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
@@ -81,13 +163,20 @@ inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t
 	if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
 	*flaggedOut = listCount;
 	if (listCount == 0) return 0;
-	const uint32_t lb = (listCount + 255) / 256;
+	const uint32_t lb = (uint32_t)(((uint64_t)listCount * 32u + 255u) / 256u);       // warp per listed vertex
+	const size_t smem = tc_smem_bytes(nCol);
 	for (uint32_t guard = 0; guard <= listCount; ++guard) {
 		if ((e = cudaMemsetAsync(d_counters + 1, 0, sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
+		if ((e = cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
 		tailcut_ready_kernel<<<lb, 256, 0, stream>>>(rowptr, neighs, d_pending, d_list, listCount, d_ready);
-		if (colBytes == 1) tailcut_apply_kernel<uint8_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1);
-		else tailcut_apply_kernel<uint16_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1);
-		(*launches) += 2;
+		if (colBytes == 1) {
+			tailcut_apply_kernel<uint8_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy);
+			tailcut_apply_heavy_kernel<uint8_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_order, hist, d_heavy);
+		} else {
+			tailcut_apply_kernel<uint16_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy);
+			tailcut_apply_heavy_kernel<uint16_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_order, hist, d_heavy);
+		}
+		(*launches) += 3;
 		uint32_t remaining = 0;
 		if ((e = cudaMemcpyAsync(&remaining, d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return (int)e;
 		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
@@ -102,10 +191,12 @@ inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t
 // repair touches z rows instead of the whole CSR and needs no host round trip per round:
 //   tc_filter_kernel   the reference's flags (conflictCounter, _utils.cu:115: a same-coloured neighbour with a LARGER id)
 //                      for the listed vertices only -- an unlisted vertex has no same-coloured neighbour at all;
-//   tc_rounds_kernel   ONE CTA runs all rounds of the dependency-ordered repair above (ready / apply, __syncthreads between);
+//   tc_rounds_kernel   ONE CTA runs all rounds of the dependency-ordered repair above (ready / apply, __syncthreads between):
+//                      a warp per vertex, the whole CTA with a shared-memory occupancy bitmap for rows beyond kTcHeavyDeg;
 //   tc_recount_kernel  conflicts and violations of the repaired colouring, again from the listed rows only (a vertex that was
 //                      not violating can only become so if a repaired neighbour found every colour taken -- flagged `inexact`,
 //                      the caller then recounts with a full pass), and the violators that are left (the next pass's list).
+// All three walk a row with the 32 lanes of a warp (coalesced), so hub rows cost deg/32 steps.
 // ---------------------------------------------------------------------------------------------------------------
 struct TailcutCounters {
 	uint32_t flagged;            // entries of flist (this pass)
@@ -119,58 +210,76 @@ struct TailcutCounters {
 template <typename ColT>
 __global__ void tc_filter_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, const ColT * __restrict__ colors,
                                  const uint32_t * __restrict__ list, uint32_t listCount, uint8_t * pending, uint32_t * flist, TailcutCounters * cnt) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
 	const uint32_t v = list[i];
 	const uint32_t c = colors[v];
-	bool flag = false;
-	for (uint32_t e = rowptr[v]; e < rowptr[v + 1] && !flag; ++e) {
-		const uint32_t u = neighs[e];
-		flag = (u > v) && ((uint32_t)colors[u] == c);
-	}
-	if (flag) { pending[v] = 1; flist[atomicAdd(&cnt->flagged, 1u)] = v; }
+	const bool flag = tc_warp_any(neighs, rowptr[v], rowptr[v + 1], lane, [&](uint32_t u) { return (u > v) && ((uint32_t)colors[u] == c); });
+	if (flag && lane == 0) { pending[v] = 1; flist[atomicAdd(&cnt->flagged, 1u)] = v; }
 }
 
 template <typename ColT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kTcThreads)
 tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol, ColT * colors, uint8_t * pending,
                  const uint32_t * __restrict__ flist, TailcutCounters * cnt, const uint32_t * __restrict__ order, unsigned long long * hist) {
-	__shared__ uint32_t s_left;
+	extern __shared__ uint32_t tc_smem[];                        // [0] best, [1] left, [2] heavy ready this round, [4..] bitmap
+	uint32_t * bm = tc_smem + 4;
 	const uint32_t n = cnt->flagged;
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
 	for (;;) {
 		// ready: no still-pending flagged neighbour with a smaller id (the sequential loop would have visited it first)
-		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		for (uint32_t i = warp; i < n; i += nWarps) {
 			const uint32_t v = flist[i];
 			if (pending[v] != 1) continue;
-			bool ok = true;
-			for (uint32_t e = rowptr[v]; e < rowptr[v + 1] && ok; ++e) { const uint32_t u = neighs[e]; ok = !(u < v && pending[u]); }
-			if (ok) pending[v] = 3;                                // pending AND ready (still non-zero for its larger neighbours)
+			const bool blocked = tc_warp_any(neighs, rowptr[v], rowptr[v + 1], lane, [&](uint32_t u) { return u < v && pending[u]; });
+			__syncwarp();
+			if (!blocked && lane == 0) pending[v] = 3;             // pending AND ready (still non-zero for its larger neighbours)
 		}
-		if (threadIdx.x == 0) s_left = 0u;
+		if (threadIdx.x == 0) { tc_smem[1] = 0u; tc_smem[2] = 0u; }
 		__syncthreads();
 		// apply: ready vertices are pairwise non-adjacent, each sees exactly the colours the sequential loop would
-		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		for (uint32_t i = warp; i < n; i += nWarps) {
 			const uint32_t v = flist[i];
 			const uint32_t p = pending[v];
-			if (p == 1) { atomicAdd(&s_left, 1u); continue; }
+			if (p == 1) { if (lane == 0) atomicAdd(&tc_smem[1], 1u); continue; }
 			if (p != 3) continue;
 			const uint32_t e0 = rowptr[v], e1 = rowptr[v + 1];
-			auto occupied = [&](uint32_t c) {
-				for (uint32_t e = e0; e < e1; ++e) if ((uint32_t)colors[neighs[e]] == c) return true;
-				return false;
-			};
+			if (e1 - e0 > kTcHeavyDeg) { if (lane == 0) atomicAdd(&tc_smem[2], 1u); continue; }   // the whole CTA does these below
 			const uint32_t old = colors[v];
-			uint32_t nodeCol = old, j = 0;
-			while (occupied(nodeCol) && j < nCol) { nodeCol = order[j]; j++; }      // _utils.cu:91-95
-			if (j == nCol && occupied(nodeCol)) cnt->inexact = 1u;                   // every colour taken: may disturb an unlisted neighbour
-			colors[v] = (ColT)nodeCol;                                               // :97
-			if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+			bool inexact;
+			const uint32_t nodeCol = tc_pick_warp<ColT>(neighs, e0, e1, colors, old, nCol, order, lane, &inexact);
+			__syncwarp();
+			if (lane == 0) {
+				if (inexact) cnt->inexact = 1u;                        // every colour taken: may disturb an unlisted neighbour
+				colors[v] = (ColT)nodeCol;                             // :97
+				pending[v] = 4;                                        // done this round (flag drops after the barrier)
+				if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+			}
+		}
+		__syncthreads();
+		if (tc_smem[2]) {                                         // hub rows that are ready: one after the other, all threads
+			for (uint32_t i = 0; i < n; ++i) {
+				const uint32_t v = flist[i];
+				if (pending[v] != 3) continue;                        // (uniform: every thread reads the same flag)
+				const uint32_t old = colors[v];
+				bool inexact;
+				const uint32_t nodeCol = tc_pick_cta<ColT>(neighs, rowptr[v], rowptr[v + 1], colors, old, nCol, order, bm, tc_smem, &inexact);
+				if (threadIdx.x == 0) {
+					if (inexact) cnt->inexact = 1u;
+					colors[v] = (ColT)nodeCol;
+					pending[v] = 4;
+					if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+				}
+				__syncthreads();
+			}
 		}
 		__syncthreads();                                          // colour writes of this round before the flags drop
-		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t v = flist[i]; if (pending[v] == 3) pending[v] = 0; }
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t v = flist[i]; if (pending[v] == 4) pending[v] = 0; }
 		__threadfence_block();
 		__syncthreads();
-		if (s_left == 0u) break;
+		if (tc_smem[1] == 0u) break;
 		__syncthreads();
 	}
 }
@@ -178,19 +287,22 @@ tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restri
 template <typename ColT>
 __global__ void tc_recount_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, const ColT * __restrict__ colors,
                                   const uint32_t * __restrict__ list, uint32_t listCount, uint8_t * pending, uint32_t * nextList, TailcutCounters * cnt) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
 	const uint32_t v = list[i];
-	pending[v] = 0;
+	if (lane == 0) pending[v] = 0;
 	const uint32_t c = colors[v];
 	uint32_t same = 0; bool flag = false;
-	for (uint32_t e = rowptr[v]; e < rowptr[v + 1]; ++e) {
+	for (uint32_t e = rowptr[v] + lane; e < rowptr[v + 1]; e += 32u) {
 		const uint32_t u = neighs[e];
 		const bool eq = (uint32_t)colors[u] == c;
 		same += eq;
 		flag = flag || (eq && u > v);
 	}
-	if (same) {
+	same = __reduce_add_sync(0xffffffffu, same);
+	flag = __any_sync(0xffffffffu, flag);
+	if (same && lane == 0) {
 		atomicAdd(&cnt->directed, (unsigned long long)same);
 		atomicAdd(&cnt->viol, 1ull);
 		nextList[atomicAdd(&cnt->nextCount, 1u)] = v;

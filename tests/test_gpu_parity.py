@@ -622,3 +622,116 @@ def test_narrow_host_interface(mc, c1_graph, port):
             ch.init_colors_narrow_ptr(c0.ctypes.data, 4)
         assert e.value.code == capi.EINVAL
         ch.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# wide palettes (nCol > 512, up to 65 535): wide_sweep_kernel -- colour lists for thread rows, shared-memory bitmaps for
+# warp / CTA rows, tables in global memory.  Same three gates as the narrow kernels, against the same oracle.
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nCol", [513, 600, 1000, 4097, 9000, 65535])
+def test_wide_palette_counts_and_occupancy(mc, port, c1_graph, nCol):
+    cumul, neighs = c1_graph
+    n = 1000
+    ch = make_chain(mc, cumul, neighs, nCol, seed=3)
+    assert ch.kernel_mode() == "wide-binned" and ch.color_bytes() == 2
+    rng = np.random.default_rng(nCol)
+    # few distinct colours on purpose: conflicts and dense occupancy in a palette this wide need help
+    c = (rng.integers(0, 40, n) * (nCol // 40) + rng.integers(0, 2, n) * (nCol - 1 - 39 * (nCol // 40))).astype(np.uint32)
+    assert c.max() < nCol
+    ch.init_colors(c)
+    st = ch.status()
+    assert st.violatingVertices == port.violation_count(cumul, neighs, c) and st.violatingVertices > 0
+    assert st.conflictEdges == port.conflict_edges(cumul, neighs, c)
+    assert ch.conflicts_of(c) == (st.conflictEdges, st.violatingVertices)
+    masks, same = ch.debug_all_occupancy()
+    occ = unpack_masks(masks, nCol)
+    for v in list(range(0, n, 37)) + [n - 1]:
+        want, _ = port.occupancy(v, cumul, neighs, c, nCol)
+        assert np.array_equal(occ[v], want), v
+    assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c, nCol))
+    bad = c.copy(); bad[5] = nCol
+    with pytest.raises(mc.McmcError):
+        ch.init_colors(bad)
+    ch.close()
+
+
+@pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
+@pytest.mark.parametrize("nCol,taboo", [(513, 0), (600, 2), (2049, 0), (9001, 0)])
+def test_wide_palette_random_tapes_vs_port(mc, port, c1_graph, proposal, nCol, taboo):
+    """warp rows (degree ~100): bitmap occupancy, walks through the bitmap, tapes with forced overflows and tiny draws"""
+    cumul, neighs = c1_graph
+    n = 1000
+    rng = np.random.default_rng(nCol * 10 + taboo + proposal)
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, taboo=taboo, replay=True)
+    # start from ~60 colours so that most vertices conflict and the walks really run
+    c = (rng.integers(0, 60, n) * (nCol // 60)).astype(np.uint32)
+    tapes = rng.random((8, n), dtype=np.float32)
+    if proposal == DYNAMIC:
+        tapes = np.maximum(tapes, np.float32(2.0 ** -24))
+    tapes[3, ::5] = np.nextafter(np.float32(1), np.float32(0))
+    tapes[4, ::7] = tapes[4, ::7] * np.float32(1e-6)
+    ch.init_colors(c)
+    ch.set_tape(tapes)
+    tb = np.zeros(n, np.uint32) if taboo else None
+    for s in range(8):
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, EPS, c, tapes[s], proposal, taboo=tb, taboo_iter=taboo)
+        got = ch.get_colors()
+        assert np.array_equal(got, c), (s, np.flatnonzero(got != c)[:10])
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c, nCol))
+        st = ch.status()
+        assert st.conflictEdges == port.conflict_edges(cumul, neighs, c) and st.violatingVertices == port.violation_count(cumul, neighs, c)
+    ch.close()
+
+
+@pytest.mark.parametrize("proposal", [UNIFORM, DYNAMIC])
+@pytest.mark.parametrize("eps", [1e-8, 1e-4])
+def test_wide_palette_all_bins_free_running(mc, port, proposal, eps):
+    """thread rows (colour lists), warp rows and CTA rows (bitmaps), empty rows; Philox draws; eps = 1e-4 makes the epsilon
+    addends of the walk matter"""
+    n = 30_001
+    cumul, neighs = skewed_graph(n, hubs=[(0, 20_000), (257, 9_000), (258, 4_200), (700, 3_000), (9_999, 100), (29_000, 66)], seed=4)
+    nCol = 777
+    ch = make_chain(mc, cumul, neighs, nCol, proposal=proposal, seed=21, eps=eps, replay=True)
+    assert ch.kernel_mode() == "wide-binned"
+    rng = np.random.default_rng(5)
+    c = rng.integers(0, 12, n).astype(np.uint32) * 61        # 12 colours in use: every row conflicts somewhere
+    ch.init_colors(c)
+    masks, same = ch.debug_all_occupancy()
+    occ = unpack_masks(masks, nCol)
+    for v in [0, 1, 257, 258, 259, 700, 9_999, 29_000, 29_990, n - 1] + list(range(3, n, 997)):
+        assert np.array_equal(occ[v], port.occupancy(v, cumul, neighs, c, nCol)[0]), v
+    for s in range(1, 5):
+        ch.sweep(1)
+        c, _ = port.sweep(cumul, neighs, nCol, eps, c, port.tape(21, s, n, proposal), proposal)
+        got = ch.get_colors()
+        assert np.array_equal(got, c), (s, np.flatnonzero(got != c)[:10])
+    st = ch.status()
+    assert st.conflictEdges == port.conflict_edges(cumul, neighs, c) and st.violatingVertices == port.violation_count(cumul, neighs, c)
+    assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(c, nCol))
+    ch.close()
+
+
+def test_wide_palette_chain_to_proper_colouring_and_tailcut(mc, port):
+    """a free-running chain with the reference's palette rule on a graph whose maximum degree is far beyond 512 colours, stopped at
+    the tail-cut threshold and repaired; equal to the oracle's chain + its sequential tail cut"""
+    n = 20_000
+    cumul, neighs = skewed_graph(n, hubs=[(3, 2_000), (4, 1_500), (5_000, 900)], seed=11)
+    nCol = int(np.diff(cumul.astype(np.int64)).max())         # numColRatio 1.0: nCol = maxDeg (> 512)
+    assert nCol > 512
+    ch = make_chain(mc, cumul, neighs, nCol, seed=8, tailcut=True)
+    ch.init_colors(None)
+    c0 = port.init_colors(8, n, nCol)
+    z = max(50, n // 2000)
+    want, sweeps, cnt, hit = port.run(cumul, neighs, nCol, EPS, c0, 8, UNIFORM, z=z)
+    ch.sweep(250)
+    st = ch.status()
+    assert st.converged == 1 and st.sweep == sweeps and st.violatingVertices == cnt
+    assert np.array_equal(ch.get_colors(), want)
+    fixed, _, left = port.tailcut(cumul, neighs, nCol, want)
+    ch.tailcut(64)
+    assert np.array_equal(ch.get_colors(), fixed)
+    st = ch.status()
+    assert st.conflictEdges == left == 0 and st.violatingVertices == 0
+    assert np.array_equal(ch.class_sizes().astype(np.uint32), port.class_sizes(fixed, nCol))
+    ch.close()
