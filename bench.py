@@ -32,9 +32,18 @@ WORKLOADS = {
     "c3": (100_000_000, 16, "BASELINE config 3: Erdos-Renyi n=100M, mean degree 16, nCol=maxDeg"),
     "c2": (1_000_000, 32, "BASELINE config 2: Erdos-Renyi n=1M, mean degree 32, nCol=maxDeg"),
     "c5": (10_000_000, 16, "BASELINE config 5: Erdos-Renyi n=10M, mean degree 16, nCol=maxDeg"),
-    "c4": (50_000_000, 16, "BASELINE config 4: R-MAT (0.57,0.19,0.19,0.05) scale 26 trimmed to 50M vertices, edge factor 16, "
-                           "nCol=min(maxDeg,512) (numColRatio chosen so that the palette is tractable)"),
-    "c4small": (1_500_000, 16, "R-MAT (0.57,0.19,0.19,0.05) scale 21 trimmed to 1.5M vertices, edge factor 16, nCol=min(maxDeg,512)"),
+    # config 4 = "R-MAT / power-law synthetic graph with 50M vertices and a Reddit-like degree skew".  Reddit (233 K vertices, mean degree
+    # 492, maximum 21 657) has max/mean degree 44; R-MAT (0.45,0.15,0.15,0.25) at scale 26 gives max/mean ~ 100 (natural vertex ids: the
+    # hubs sit together at the low ids, which is what stresses the degree binning), and the reference's own palette rule nCol = maxDeg
+    # (numColRatio 1.0, main.cu:162) stays usable -- a few thousand colours, the wide-palette kernel -- and reaches a proper colouring.
+    "c4": (50_000_000, 16, "BASELINE config 4: R-MAT (0.45,0.15,0.15,0.25) scale 26 trimmed to 50M vertices, edge factor 16 (max/mean degree ~100, "
+                           "Reddit: 44), nCol=maxDeg"),
+    # the round-1 graph: Graph500 parameters, max/mean degree 25 000 (hub rows of ~10^6 neighbours).  No palette a sampler of this kind can
+    # use gives a proper colouring here (two adjacent hubs that start with the same colour both see every colour taken and never move), so
+    # this one is a load-balance stress test of the kernels only: nCol = 1024.
+    "c4heavy": (50_000_000, 16, "R-MAT (0.57,0.19,0.19,0.05) [Graph500] scale 26 trimmed to 50M vertices, edge factor 16, max/mean degree 25 000, nCol=1024 "
+                                "(kernel stress test; no proper colouring exists for this sampler)"),
+    "c4small": (1_500_000, 16, "R-MAT (0.57,0.19,0.19,0.05) scale 21 trimmed to 1.5M vertices, edge factor 16, nCol=1024"),
     "small": (200_000, 16, "smoke-sized Erdos-Renyi n=200k, mean degree 16"),
 }
 GRAPH_SEED = 42
@@ -91,13 +100,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-MAX_PALETTE = 512                                         # widest palette of this build (u16 colours, 8 mask words per lane)
+RMAT = {"c4": (0.45, 0.15, 0.15), "c4heavy": (0.57, 0.19, 0.19), "c4small": (0.57, 0.19, 0.19)}
 
 
 def palette_for(workload, max_deg):
     """numColRatio 1.0: nCol = maxDeg (main.cu:162); the R-MAT hubs have degree ~1e6, there the ratio is raised so that
     the palette stays tractable."""
-    return min(max_deg, MAX_PALETTE) if workload.startswith("c4") else max_deg
+    return min(max_deg, 1024) if workload in ("c4heavy", "c4small") else max_deg
 
 
 def sample_start(workload, n):
@@ -109,7 +118,8 @@ def gen_graph_device(n, deg, device, workload="c3"):
     from mcmc_colorer_b200.graphgen import er_graph_torch, rmat_graph_torch
     if workload.startswith("c4"):
         scale = max(1, (n - 1).bit_length())
-        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(scale, deg, GRAPH_SEED, n_keep=n, device=device)
+        a, b, c = RMAT[workload]
+        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(scale, deg, GRAPH_SEED, n_keep=n, a=a, b=b, c=c, device=device)
     else:
         rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=device)
     assert nnz < 2 ** 31, "this bench keeps CSR offsets in int32 tensors"
@@ -188,7 +198,7 @@ def run_reference_arm(args):
         nnz, max_deg = len(nb), int(np.diff(cumul.astype(np.int64)).max())
     else:
         rowptr, neighs, nnz, max_deg = gen_graph_device(n, deg, dev, args.workload)
-    nCol = palette_for(args.workload, max_deg)
+    nCol = args.ncol if args.ncol else palette_for(args.workload, max_deg)
     rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=max(20.0, 6.0 * (args.steps + args.warmup)),
                                                      steps=args.steps, warmup=args.warmup, v0=sample_start(args.workload, n))
     ms = 1e3 * sum(secs) / len(secs)
@@ -197,7 +207,9 @@ def run_reference_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "u32 colours / f32 CDF", "data": "synthetic",
             "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "proposal": "uniform",
                        "step": "bounded sample of one sweep: " + sample},
-            "cpu_baseline": {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample,
+                             "sample_vertices": int(m), "sample_fraction": m / n,
+                             "note": "the reference is single-threaded; the rate of the sampled vertex range stands for the whole sweep (per-vertex cost is uniform on this graph)"},
             "e2e": {"value": rate, "unit": "vertex-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "edges_per_sec": rate * nnz / n, "host_cores_available": os.cpu_count()}
     print(json.dumps(line))
@@ -218,6 +230,7 @@ def main():
     ap.add_argument("--item-bits", type=int, default=0, help="tuning experiments: mcmcb200_params.itemBits (0 = automatic)")
     ap.add_argument("--stage-buffers", type=int, default=0, help="tuning experiments: mcmcb200_params.stageBuffers (0 = automatic)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning experiments: the two passes of the blocked sweep back to back")
+    ap.add_argument("--expected-sweeps", type=int, default=0, help="mcmcb200_params.expectedSweeps of the measured handle (0 = many: blocked layout on large graphs)")
     ap.add_argument("--ncol", type=int, default=0, help="override the palette size (default: palette_for(workload, maxDeg))")
     ap.add_argument("--traj", type=int, default=0, help="with --quick: also run a chain of this many sweeps and report its violation trajectory")
     ap.add_argument("--quick", action="store_true", help="tuning experiments: kernel timing only (no e2e, no time-to-colouring, no CPU baseline)")
@@ -241,7 +254,7 @@ def main():
     dev = f"cuda:{local_rank}"
     if world > 1:
         from mcmc_colorer_b200 import multigpu
-        return multigpu.bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSampler)
+        return multigpu.bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSampler, palette_for, RMAT)
 
     n, deg, desc = WORKLOADS[args.workload]
     if args.n:
@@ -258,7 +271,7 @@ def main():
     t_create = time.perf_counter()
     ch = mc.Chain(params=prm, device=local_rank, flags=mc.FLAG_NO_EARLY_STOP | (mc.FLAG_NO_OVERLAP if args.no_overlap else 0),
                   n_global=n, v_begin=0, v_end=n, device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz),
-                  stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers)
+                  stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers, expected_sweeps=args.expected_sweeps)
     ch.synchronize()
     create_ms = 1e3 * (time.perf_counter() - t_create)   # mcmcb200_create: allocations + (blocked path) the layout build on the device
     if args.quick:
@@ -317,31 +330,42 @@ def main():
     # mcmcb200_create is timed too: `setup_ms` is the layout build a user pays once per graph); the chain stops ON THE DEVICE at
     # the threshold -- the host only polls every 4 sweeps -- and the repair works from the violator list the last sweep emitted.
     prm_tc = mc.ColoringMCMCParams(nCol=nCol, proposal=proposal, convergence=prm.convergence, seed=CHAIN_SEED, tailcut=True)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter()
-    ch_tc = mc.Chain(params=prm_tc, device=local_rank, flags=(mc.FLAG_NO_OVERLAP if args.no_overlap else 0), n_global=n, v_begin=0, v_end=n,
-                     device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz),
-                     stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers)
-    ch_tc.synchronize()
-    setup_ms = 1e3 * (time.perf_counter() - t_setup)
-    ch_tc.init_colors(None)
-    ch_tc.synchronize()
     z_tail = max(50, n // 2000)
-    t_ttc = time.perf_counter()
-    while True:
-        ch_tc.sweep(4)
-        st_ttc = ch_tc.status()
-        if st_ttc.converged or st_ttc.sweep >= 250 or time.perf_counter() - t_ttc > 5.0:
-            break
-    ttc_sweeps = int(st_ttc.sweep)
-    t_sweeps = time.perf_counter() - t_ttc
-    # the repair pass only once the chain is below the threshold (a palette that cannot get there -- config 4 at nCol = 512 --
-    # is reported as not proper; the greedy repair is not meant for hundreds of thousands of conflicts on hub rows)
-    reached = bool(st_ttc.converged)
-    ttc_rounds = ch_tc.tailcut(64) if (reached and st_ttc.conflictEdges > 0) else 0
-    st_ttc = ch_tc.status()
-    t_ttc = time.perf_counter() - t_ttc
-    ch_tc.close()
+
+    def time_to_colouring(expected_sweeps):
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter()
+        c = mc.Chain(params=prm_tc, device=local_rank, flags=(mc.FLAG_NO_OVERLAP if args.no_overlap else 0), n_global=n, v_begin=0, v_end=n,
+                     device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz), stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits,
+                     stage_buffers=args.stage_buffers, expected_sweeps=expected_sweeps)
+        c.synchronize()
+        setup = 1e3 * (time.perf_counter() - t_setup)
+        mode = c.kernel_mode()
+        c.init_colors(None)
+        c.synchronize()
+        t0 = time.perf_counter()
+        while True:
+            c.sweep(4)
+            s_ = c.status()
+            if s_.converged or s_.sweep >= 250 or time.perf_counter() - t0 > 5.0:
+                break
+        sweeps = int(s_.sweep)
+        t_sw = time.perf_counter() - t0
+        # the repair pass only once the chain is below the threshold (a palette that cannot get there is reported as not proper)
+        reached = bool(s_.converged)
+        viol_at_z = int(s_.violatingVertices)
+        rounds = c.tailcut(64) if (reached and s_.conflictEdges > 0) else 0
+        s_ = c.status()
+        t_all = time.perf_counter() - t0
+        c.close()
+        return {"sweeps": sweeps, "tailcut_rounds": int(rounds), "ms": 1e3 * t_all, "ms_sweeps": 1e3 * t_sw, "setup_ms": setup,
+                "total_ms_with_setup": setup + 1e3 * t_all, "kernel_mode": mode, "z": z_tail, "reached_z": reached, "violating_at_z": viol_at_z,
+                "proper": bool(s_.conflictEdges == 0 and s_.violatingVertices == 0), "conflictEdges_left": int(s_.conflictEdges),
+                "usedColors": int(s_.usedColors), "nCol": nCol}
+
+    ttc = time_to_colouring(args.expected_sweeps)           # layout amortised over many chains (setup reported beside it)
+    # one chain on a new graph: expectedSweeps = 8 keeps the layout-free kernels (mcmcb200.h), so the total includes a cheap create
+    ttc_one_shot = time_to_colouring(8)
     ms_per_step = float(np.mean(kernel_ms))
     value = n / (ms_per_step * 1e-3)
     alg_bytes = 8 * nnz + 12 * n + 4
@@ -399,6 +423,8 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": {"direct": "sweep_kernel (one launch per sweep)",
                                 "direct-binned": "binned_sweep_kernel (one launch per sweep; thread / warp / CTA rows by degree)",
+                                "wide-binned": "wide_tables_kernel + wide_sweep_kernel (palettes above 512 colours: thread / warp / CTA rows by degree, colour "
+                                               "lists and shared-memory bitmaps)",
                                 "blocked": "blocked_gather_kernel then blocked_sweep_kernel (two launches per sweep)",
                                 "blocked-overlapped": "blocked_gather_kernel || blocked_sweep_kernel (two launches per sweep, concurrent on two "
                                                       "streams; launch_ms = CUDA events around the pair)"}[ch.kernel_mode()],
@@ -412,15 +438,12 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks.summary(),
         "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
-        "time_to_proper_coloring": {"sweeps": ttc_sweeps, "tailcut_rounds": int(ttc_rounds), "ms": 1e3 * t_ttc, "ms_sweeps": 1e3 * t_sweeps,
-                                    "setup_ms": setup_ms, "total_ms_with_setup": setup_ms + 1e3 * t_ttc,
-                                    "z": z_tail, "reached_z": bool(reached), "proper": bool(st_ttc.conflictEdges == 0 and st_ttc.violatingVertices == 0),
-                                    "usedColors": int(st_ttc.usedColors), "nCol": nCol},
+        "time_to_proper_coloring": dict(ttc, one_shot=ttc_one_shot),
     }
     if not args.no_cpu_baseline:
         rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, v0=sample_start(args.workload, n))
         line["cpu_baseline"] = {"value": rate, "unit": "vertex-updates/s", "cores": 1, "kind": kind, "sample": sample,
-                                "host_cores_available": os.cpu_count()}
+                                "sample_vertices": int(m), "sample_fraction": m / n, "host_cores_available": os.cpu_count()}
     ch.close()
     print(json.dumps(line))
     return 0

@@ -42,7 +42,7 @@ class Params(C.Structure):
                 ("ratioFreezed", C.c_float), ("tabooIteration", C.c_uint32), ("maxRip", C.c_uint32),
                 ("tailcut", C.c_uint32), ("proposal", C.c_uint32), ("convergence", C.c_uint32),
                 ("seed", C.c_uint64), ("device", C.c_int32), ("flags", C.c_uint32),
-                ("stageCapBytes", C.c_uint32), ("itemBits", C.c_uint32), ("stageBuffers", C.c_uint32), ("reserved", C.c_uint32)]
+                ("stageCapBytes", C.c_uint32), ("itemBits", C.c_uint32), ("stageBuffers", C.c_uint32), ("expectedSweeps", C.c_uint32)]
 
 
 class Status(C.Structure):

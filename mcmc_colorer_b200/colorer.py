@@ -108,15 +108,16 @@ class Chain:
     """One Markov chain on one GPU: a mcmcb200_handle."""
 
     def __init__(self, cumulDegs=None, neighs=None, params: ColoringMCMCParams = None, device=-1, flags=0,
-                 n_global=None, v_begin=0, v_end=None, device_csr=None, stage_cap_bytes=0, item_bits=0, stage_buffers=0):
-        """stage_cap_bytes / item_bits / stage_buffers: tuning of the source-blocked sweep (mcmcb200_params), 0 = automatic."""
+                 n_global=None, v_begin=0, v_end=None, device_csr=None, stage_cap_bytes=0, item_bits=0, stage_buffers=0, expected_sweeps=0):
+        """stage_cap_bytes / item_bits / stage_buffers: tuning of the source-blocked sweep (mcmcb200_params), 0 = automatic.
+        expected_sweeps: mcmcb200_params.expectedSweeps (0 = many: build the blocked layout on large graphs)."""
         self.L = capi.lib()
         self.params = params
         p = capi.Params(nCol=params.nCol, epsilon=params.epsilon, lambda_=params.lambda_,
                         numColorRatio=params.numColorRatio, ratioFreezed=params.ratioFreezed,
                         tabooIteration=params.tabooIteration, maxRip=params.maxRip, tailcut=int(params.tailcut),
                         proposal=params.proposal, convergence=params.convergence, seed=params.seed, device=device,
-                        flags=flags, stageCapBytes=stage_cap_bytes, itemBits=item_bits, stageBuffers=stage_buffers, reserved=0)
+                        flags=flags, stageCapBytes=stage_cap_bytes, itemBits=item_bits, stageBuffers=stage_buffers, expectedSweeps=expected_sweeps)
         self.h = C.c_void_p()
         if device_csr is not None:
             d_rowptr, d_neighs, nnz_local = device_csr

@@ -265,6 +265,7 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 #pragma unroll
 				for (int k = 0; k < kBinUnroll; ++k) {
 					if (e + 32u * k < e1) {
+						MCMCB200_CHECK(c[k] < nCol && nb[k] < a.nGlobal, st);
 						ss += (c[k] == ownJ);
 						if (kWide) atomicOr(&s_wm[warp * 2 * W + (c[k] >> 5)], 1u << (c[k] & 31u));
 						else set_bit(mm, c[k]);
@@ -323,6 +324,7 @@ binned_sweep_kernel(const SweepArgs a, const BinnedArgs bn) {
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
 				if (i + k < deg) {
+					MCMCB200_CHECK(c[k] < nCol && nb[k] < a.nGlobal, st);
 					same += (c[k] == own);
 					if (kWide) s_m32[(c[k] >> 5) * kThreadsBin + tid] |= 1u << (c[k] & 31u);
 					else set_bit(m, c[k]);

@@ -249,7 +249,7 @@ done:
 
 inline BlockedArgs make_blocked_args(const BlockedLayout & L) {
 	BlockedArgs b{};
-	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap;
+	b.P = L.P; b.TV = L.TV; b.numTiles = L.numTiles; b.stageCap = L.stageCap; b.totalPadded = L.totalPadded;
 	b.srcLocal = L.srcLocal; b.ecol = L.ecol; b.gidx = L.gidx; b.gidxS = L.gidxS; b.slotInfo = L.slotInfo; b.sliceOff = L.sliceOff;
 	b.granDst = L.granDst; b.tileBase = L.tileBase;
 	b.items = L.items; b.numItems = L.numItems; b.numParts = L.numParts; b.nbuf = L.nbuf; b.tilePart = L.tilePart; b.sync = L.sync; b.dbgTimes = L.dbgTimes;

@@ -58,8 +58,11 @@ constexpr int      kThreadsA  = MCMCB200_THREADS_A;
 #define MCMCB200_HEAVY_CAP 1024
 #endif
 // palettes wider than 128 colours keep their masks in 4-8 64-bit registers per lane: those instances run 512 threads, one CTA
+#ifndef MCMCB200_REGS_B
+#define MCMCB200_REGS_B 64
+#endif
 template <int W> struct PassB { static constexpr int threads = (W <= 2) ? MCMCB200_THREADS_B : 512;
-                                static constexpr int maxRegs = (W <= 2) ? 64 : 128; };
+                                static constexpr int maxRegs = (W <= 2) ? MCMCB200_REGS_B : 128; };
 
 struct BlockedLayout {
 	bool      valid = false;
@@ -89,7 +92,7 @@ struct BlockedLayout {
 };
 
 struct BlockedArgs {
-	uint32_t P, TV, numTiles, stageCap;
+	uint32_t P, TV, numTiles, stageCap, totalPadded;
 	const uint16_t * srcLocal;
 	void * ecol;
 	const uint16_t * gidx;
@@ -374,6 +377,7 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 				const uint32_t j = j0 + k * kThreadsA;
 				if (j < g1) {
 					const uint2 d = ids[k];
+					MCMCB200_CHECK(4ull * gd[k] + 4ull <= bl.totalPadded && j < (bl.totalPadded >> 2), a.st);
 					const uint32_t c0 = chunk[d.x & 0xffffu], c1 = chunk[d.x >> 16], c2 = chunk[d.y & 0xffffu], c3 = chunk[d.y >> 16];
 					if (sizeof(ColT) == 1) st_ecol32(ecol + 4u * (size_t)gd[k], c0 | (c1 << 8) | (c2 << 16) | (c3 << 24), pol);
 					else st_ecol64(ecol + 4u * (size_t)gd[k], make_uint2(c0 | (c1 << 16), c2 | (c3 << 16)), pol);
@@ -571,13 +575,16 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 		const uint32_t hi = atomicAdd(tv.heavyCount, 1u);
 		if (hi < kHeavyCap) sm.heavy[hi] = (uint16_t)lv; else inlineHeavy = true;
 	}
+	MCMCB200_CHECK(!valid || lv < tv.nv, a.st);
 	const uint32_t own = valid ? (uint32_t)tv.own[lv] : 0u;
 	unsigned long long m[W];
 #pragma unroll
 	for (int w = 0; w < W; ++w) m[w] = 0ull;
 	uint32_t same = 0;
 	auto addc = [&](uint32_t idx) {
+		MCMCB200_CHECK(idx < bl.stageCap + 16u, a.st);
 		const uint32_t c = stage[idx];
+		MCMCB200_CHECK(c < a.nCol || (kPad && c == (uint32_t)(ColT)~(ColT)0), a.st);
 		asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(same) : "r"(c), "r"(own));   // same += (c == own)
 		if (W == 1) m[0] |= kPad ? bit64_clamped(c) : (1ull << c);
 		else {
@@ -660,6 +667,7 @@ __device__ __forceinline__ void sweep_heavy_list(const SweepArgs & a, const Bloc
 		uint32_t same = 0;
 		for (uint32_t i = lane; i < hd; i += 32) {
 			const uint32_t c = tv.stage[__ldg(bl.gidx + hb + i)];
+			MCMCB200_CHECK(__ldg(bl.gidx + hb + i) < bl.stageCap + 16u && c < a.nCol, a.st);
 			same += (c == own);
 #pragma unroll
 			for (int w = 0; w < W; ++w) m[w] |= ((int)(c >> 6) == w) ? (1ull << (c & 63u)) : 0ull;

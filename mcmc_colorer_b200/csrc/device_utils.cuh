@@ -3,6 +3,15 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// -DMCMCB200_BOUNDS_CHECK=1 builds a checking variant of the library: every index the hot kernels compute themselves (stage positions,
+// granule destinations, slot tables, palette indices, queue slots) is tested before use and a violation raises the sticky device error
+// flag 4, which every host call that reads results reports as an error.  (compute-sanitizer is not available on the pool these kernels
+// were developed on; scripts/sanitize_driver.py runs every kernel family against the checking build.)
+#ifndef MCMCB200_BOUNDS_CHECK
+#define MCMCB200_BOUNDS_CHECK 0
+#endif
+#define MCMCB200_CHECK(cond, st) do { if (MCMCB200_BOUNDS_CHECK && !(cond)) *reinterpret_cast<volatile uint32_t *>(&(st)->errorFlag) = 4u; } while (0)
+
 namespace mcmcb200 {
 
 // ---------------------------------------------------------------------------------------------

@@ -8,6 +8,8 @@
 #include "csr_build.cuh"
 #include "luby_kernel.cuh"
 
+#include <nvtx3/nvToolsExt.h>    // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx; no-ops without a tool attached
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -79,7 +81,7 @@ struct mcmcb200_handle {
 	uint32_t * d_violList[2] = {nullptr, nullptr};   // tail cutting: violating vertices emitted by the sweeps / left by the last repair pass
 	uint32_t * d_violCount = nullptr; uint32_t violCap = 0;
 	uint8_t * d_pending = nullptr;         // tail cutting: per-vertex flags (all zero between calls)
-	uint32_t * d_flist = nullptr;
+	uint32_t * d_flist = nullptr, * d_tcResume = nullptr;
 	TailcutCounters * d_tcCnt = nullptr;
 	unsigned long long * d_xchg = nullptr; // this rank's counter-exchange block (sweep_kernel.cuh: cross_rank_reduce)
 	unsigned long long * peerXchg[kMaxPeers] = {};
@@ -88,6 +90,14 @@ struct mcmcb200_handle {
 };
 
 namespace {
+
+// NVTX range over a host entry point (the reference has no tracing at all)
+struct NvtxRange {
+	explicit NvtxRange(const char * name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange &) = delete;
+	NvtxRange & operator=(const NvtxRange &) = delete;
+};
 
 template <int W, typename ColT>
 cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
@@ -318,7 +328,7 @@ int check_params(const mcmcb200_params * p, uint32_t nGlobal) {
 	if (p->nCol > 64u * kMaxColWords && (p->flags & (MCMCB200_FLAG_FORCE_BLOCKED | MCMCB200_FLAG_FORCE_DIRECT))) return MCMCB200_EUNSUPPORTED;   // wide palettes: wide_sweep_kernel only
 	if (p->tabooIteration > 65535u) return MCMCB200_EUNSUPPORTED;
 	if (p->proposal == MCMCB200_PROPOSAL_DYNAMIC && p->nCol < 2) return MCMCB200_EINVAL;
-	if (p->reserved != 0u || p->stageBuffers > 2u || (p->itemBits && (p->itemBits < 12u || p->itemBits > 24u))) return MCMCB200_EINVAL;
+	if (p->stageBuffers > 2u || (p->itemBits && (p->itemBits < 12u || p->itemBits > 24u))) return MCMCB200_EINVAL;
 	return MCMCB200_OK;
 }
 
@@ -373,6 +383,7 @@ int alloc_chain_state(mcmcb200_handle * h) {
 		h->violCap = (uint32_t)std::min<uint64_t>(h->nGlobal, 32ull * h->z + 4096ull);
 		for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_violList[i], sizeof(uint32_t) * (size_t)h->violCap));
 		CU(cudaMalloc(&h->d_flist, sizeof(uint32_t) * (size_t)h->violCap));
+		CU(cudaMalloc(&h->d_tcResume, sizeof(uint32_t) * (size_t)h->violCap));
 		CU(cudaMalloc(&h->d_violCount, sizeof(uint32_t)));
 		CU(cudaMemsetAsync(h->d_violCount, 0, sizeof(uint32_t), h->stream));
 		CU(cudaMalloc(&h->d_tcCnt, sizeof(TailcutCounters)));
@@ -484,6 +495,7 @@ int read_state(mcmcb200_handle * h, DevState * s) {
 int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uint32_t vEnd, uint64_t nnzLocal,
                   const uint32_t * cumulDegs, const uint32_t * neighs /* first owned edge */, bool deviceCsr,
                   const mcmcb200_params * p) {
+	NvtxRange nvtx_("mcmcb200_create");
 	if (!out) return MCMCB200_EINVAL;
 	*out = nullptr;
 	int rc = check_params(p, nGlobal); if (rc) return rc;
@@ -531,7 +543,9 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceDirect = (p->flags & MCMCB200_FLAG_FORCE_DIRECT) != 0, forceBlocked = (p->flags & MCMCB200_FLAG_FORCE_BLOCKED) != 0;
 		const bool forceBinned = (p->flags & MCMCB200_FLAG_FORCE_BINNED) != 0;
 		const bool large = nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18);
-		const bool want = !h->wide && (forceBlocked || (!forceDirect && !forceBinned && large));
+		// a handle that will only run a few sweeps does not amortise the layout build (mcmcb200.h: expectedSweeps)
+		const bool fewSweeps = p->expectedSweeps != 0u && p->expectedSweeps < 32u;
+		const bool want = !h->wide && (forceBlocked || (!forceDirect && !forceBinned && large && !fewSweeps));
 		if (want) {
 			// colour bytes a tile stages in shared memory.  Large partitions: 32 KiB (tiles of 4 x 384 vertices on a mean-degree-16
 			// graph), so that two pass-B CTAs and one pass-A CTA (64 KiB chunk) share an SM and the two passes overlap; measured on
@@ -546,6 +560,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			if (p->itemBits) itemEntries = 1u << p->itemBits;
 			if (p->stageCapBytes) capBytes = p->stageCapBytes;
 			if (p->stageBuffers) nbuf = p->stageBuffers;
+			NvtxRange nvtxBuild("build_blocked_layout");
 			cudaError_t e = build_blocked_layout(h->bl, h->d_rowptr, h->d_neighs, h->nLocal, nnzLocal, nGlobal, h->colBytes, capBytes, itemEntries,
 			                                     (uint32_t)(h->W <= 2 ? PassB<1>::threads : PassB<4>::threads), h->stream, &h->launches);
 			h->bl.nbuf = nbuf;
@@ -606,7 +621,8 @@ int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned
 		if ((e = cudaMemsetAsync(h->d_tcCnt, 0, sizeof(TailcutCounters), h->stream)) != cudaSuccess) break;
 		const uint32_t lb = (uint32_t)(((uint64_t)listCount * 32u + 255u) / 256u);   // a warp per listed vertex
 		tc_filter_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_flist, h->d_tcCnt);
-		tc_rounds_kernel<ColT><<<1, kTcThreads, tc_smem_bytes(nCol), h->stream>>>(h->d_rowptr, h->d_neighs, nCol, cur, h->d_pending, h->d_flist, h->d_tcCnt, d_order, hist);
+		if ((e = cudaMemsetAsync(h->d_tcResume, 0, sizeof(uint32_t) * (size_t)h->violCap, h->stream)) != cudaSuccess) break;
+		tc_rounds_kernel<ColT><<<1, kTcThreads, tc_smem_bytes(nCol), h->stream>>>(h->d_rowptr, h->d_neighs, nCol, cur, h->d_pending, h->d_flist, h->d_tcResume, h->d_tcCnt, d_order, hist);
 		tc_recount_kernel<ColT><<<lb, 256, 0, h->stream>>>(h->d_rowptr, h->d_neighs, cur, h->d_violList[src], listCount, h->d_pending, h->d_violList[src ^ 1], h->d_tcCnt);
 		h->launches += 3;
 		if ((e = cudaMemcpyAsync(&c, h->d_tcCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) break;
@@ -615,6 +631,7 @@ int tailcut_from_list_t(mcmcb200_handle * h, DevState & s, void * curV, unsigned
 		listCount = c.nextCount;
 		if (c.flagged == 0) break;                                         // the pass found nothing to repair
 		if (c.inexact) { ++used; break; }
+		if (c.changed == 0) { ++used; break; }                             // no vertex could be given another colour: further passes would repeat this one
 		if (c.nextFlagged == 0) { ++used; break; }
 	}
 	if (e == cudaSuccess && src == 1) e = cudaMemcpyAsync(h->d_violList[0], h->d_violList[1], sizeof(uint32_t) * (size_t)listCount, cudaMemcpyDeviceToDevice, h->stream);
@@ -689,6 +706,7 @@ int mcmcb200_create_device_csr(mcmcb200_handle ** out, uint32_t nGlobal, uint32_
 
 int mcmcb200_csr_from_edges(uint32_t n, uint64_t m, const uint32_t * src, const uint32_t * dst, int device,
                             uint32_t ** d_cumulDegs, uint32_t ** d_neighs, uint64_t * nnz) {
+	NvtxRange nvtx_("mcmcb200_csr_from_edges");
 	if (!d_cumulDegs || !d_neighs || !nnz || n == 0 || (m && (!src || !dst))) return MCMCB200_EINVAL;
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
@@ -738,7 +756,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_wideS); cudaFree(h->d_wideTab);
 	mcmcb200_ipc_detach(h);
 	cudaFree(h->d_xchg);
-	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcCnt);
+	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcResume); cudaFree(h->d_tcCnt);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
 	if (h->streamA) { cudaStreamSynchronize(h->streamA); cudaStreamDestroy(h->streamA); }
 	if (h->evFork) cudaEventDestroy(h->evFork);
@@ -751,6 +769,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 }
 
 int mcmcb200_init_colors(mcmcb200_handle * h, const uint32_t * colors) {
+	NvtxRange nvtx_("mcmcb200_init_colors");
 	if (!h) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));
 	int rc = reset_state(h); if (rc) return rc;
@@ -866,6 +885,7 @@ int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps) {
 }
 
 int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k) {
+	NvtxRange nvtx_("mcmcb200_sweep");
 	if (!h) return MCMCB200_EINVAL;
 	if (!h->colorsInit) return MCMCB200_ESTATE;
 	const bool split = h->split();
@@ -888,6 +908,7 @@ int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k) {
 }
 
 int mcmcb200_finalize_sweep(mcmcb200_handle * h) {
+	NvtxRange nvtx_("mcmcb200_finalize_sweep (multi-GPU: after the counter all-reduce)");
 	if (!h) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));
 	SweepArgs a = make_args(h);
@@ -900,6 +921,7 @@ int mcmcb200_finalize_sweep(mcmcb200_handle * h) {
 }
 
 int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
+	NvtxRange nvtx_("mcmcb200_status");
 	if (!h || !out) return MCMCB200_EINVAL;
 	if (!h->colorsInit) return MCMCB200_ESTATE;
 	CU(cudaSetDevice(h->device));
@@ -938,6 +960,7 @@ int mcmcb200_status(mcmcb200_handle * h, mcmcb200_status_t * out) {
 }
 
 int mcmcb200_get_colors(mcmcb200_handle * h, uint32_t * out) {
+	NvtxRange nvtx_("mcmcb200_get_colors");
 	if (!h || !out) return MCMCB200_EINVAL;
 	if (!h->colorsInit) return MCMCB200_ESTATE;
 	CU(cudaSetDevice(h->device));
@@ -1036,6 +1059,7 @@ int mcmcb200_debug_occupancy(mcmcb200_handle * h, uint32_t v, uint32_t * maskWor
 }
 
 int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds) {
+	NvtxRange nvtx_("mcmcb200_tailcut");
 	if (!h) return MCMCB200_EINVAL;
 	if (!h->colorsInit) return MCMCB200_ESTATE;
 	if (h->vBegin != 0 || h->vEnd != h->nGlobal) return MCMCB200_EUNSUPPORTED;
@@ -1065,18 +1089,20 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	cudaError_t e = cudaMalloc(&d_order, sizeof(uint32_t) * nCol);
 	if (e == cudaSuccess) e = cudaMalloc(&d_list, sizeof(uint32_t) * std::max<uint32_t>(n, 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_heavy, sizeof(uint32_t) * ((size_t)n + 1));
-	if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(uint32_t) * 2);
+	if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(uint32_t) * 3);
 	if (e == cudaSuccess) e = cudaMalloc(&d_pending, std::max<uint32_t>(n, 1));
 	if (e == cudaSuccess) e = cudaMalloc(&d_ready, std::max<uint32_t>(n, 1));
 	if (e == cudaSuccess) e = cudaMemcpy(d_order, order.data(), sizeof(uint32_t) * nCol, cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "tailcut workspace", __LINE__); }
 	uint32_t used = usedByList;
 	for (; used < maxRounds; ++used) {                                     // while (conflictCounter > 0), _main.cu:279
-		uint32_t flagged = 0;
+		uint32_t flagged = 0, changed = 0;
 		const int ce = launch_tailcut_pass(h->stream, h->colBytes, h->d_rowptr, h->d_neighs, n, nCol, cur, hist, d_order,
-		                                   d_pending, d_ready, d_list, d_heavy, d_counters, &flagged, &h->launches);
+		                                   d_pending, d_ready, d_list, d_heavy, d_counters, &flagged, &changed, &h->launches);
 		if (ce) { cleanup(); return cuda_fail((cudaError_t)ce, "tailcut pass", __LINE__); }
 		if (flagged == 0) break;                                           // no conflicting edge left
+		if (changed == 0) { ++used; break; }                               // no progress (every colour taken around the vertices that are left): the
+		                                                                   // reference would repeat this pass for ever (_main.cu:279)
 	}
 	cleanup();
 	// the colouring changed under the counters: force a recount at the next status
@@ -1090,6 +1116,7 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 
 int mcmcb200_luby_color(uint32_t n, uint64_t nnz, const uint32_t * cumulDegs, const uint32_t * neighs, uint64_t seed, int32_t device,
                         uint32_t * colorsOut, uint32_t * numColors, uint32_t * rounds) {
+	NvtxRange nvtx_("mcmcb200_luby_color");
 	if (!cumulDegs || (nnz && !neighs) || !colorsOut || n == 0) return MCMCB200_EINVAL;
 	// the same host-side CSR validation as mcmcb200_create: monotone offsets starting at 0, nnz consistent, ids < n
 	if (cumulDegs[0] != 0 || cumulDegs[n] != nnz || nnz >= 0xfffffff0ull) return MCMCB200_EINVAL;
@@ -1177,6 +1204,7 @@ int mcmcb200_ipc_export(mcmcb200_handle * h, unsigned char * handles /* [3][64] 
 }
 
 int mcmcb200_ipc_attach(mcmcb200_handle * h, uint32_t nRanks, uint32_t myRank, const unsigned char * handles /* [nRanks][3][64] */) {
+	NvtxRange nvtx_("mcmcb200_ipc_attach (fused exchange set-up)");
 	if (!h || !handles || nRanks < 2 || nRanks > (uint32_t)kMaxPeers || myRank >= nRanks) return MCMCB200_EINVAL;
 	if (!h->bl.valid) return MCMCB200_EUNSUPPORTED;
 	if (h->nPeers) return MCMCB200_ESTATE;

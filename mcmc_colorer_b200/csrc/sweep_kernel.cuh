@@ -325,6 +325,7 @@ struct WalkQueue {
 template <typename ColT>
 __device__ __forceinline__ void finish_vertex(const SweepArgs & a, ColT * __restrict__ nxt, uint32_t lv, uint32_t myOwn, uint32_t newc,
                                               int * s_hist, bool touchTaboo, ColT * nxtTile = nullptr, uint32_t tileV0 = 0) {
+	MCMCB200_CHECK(newc < a.nCol && myOwn < a.nCol && lv < a.nLocal, a.st);
 	if (touchTaboo && a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);   // coloringMCMC_CPU.cpp:526
 	if (nxtTile) nxtTile[lv - tileV0] = (ColT)newc;
 	else nxt[a.vBegin + lv] = (ColT)newc;
@@ -419,6 +420,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 					qbase = __shfl_sync(act, qbase, leader);
 					const uint32_t qi = qbase + (uint32_t)__popc(act & lt);
 					if (qi < queue->cap) {                    // park the walk; drained by dense lanes (drain_walk_queue)
+						MCMCB200_CHECK(Zn < nCol && lv < a.nLocal, a.st);
 #pragma unroll
 						for (int w = 0; w < W; ++w) queue->mask[(size_t)qi * W + w] = m[w];
 						queue->lvOwn[2 * qi] = lv; queue->lvOwn[2 * qi + 1] = myOwn;

@@ -63,6 +63,7 @@ __device__ __forceinline__ uint32_t tc_pick_cta(const uint32_t * __restrict__ ne
 		__syncthreads();
 		const uint32_t b = *s_best;
 		res = (b != 0xffffffffu) ? order[b] : order[nCol - 1u];
+		if (MCMCB200_BOUNDS_CHECK && res >= nCol) __trap();
 		*inexact = (b == 0xffffffffu) && occ(res);
 	}
 	__syncthreads();                                          // bm / s_best may be reused right away
@@ -103,7 +104,7 @@ template <typename ColT>
 __global__ void tailcut_apply_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol,
                                      ColT * colors, uint8_t * pending, const uint32_t * __restrict__ list, uint32_t listCount,
                                      const uint8_t * __restrict__ ready, const uint32_t * __restrict__ order,
-                                     unsigned long long * hist, uint32_t * remaining, uint32_t * heavy) {
+                                     unsigned long long * hist, uint32_t * remaining, uint32_t * heavy, uint32_t * changed) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
@@ -119,14 +120,14 @@ __global__ void tailcut_apply_kernel(const uint32_t * __restrict__ rowptr, const
 	if (lane == 0) {
 		colors[v] = (ColT)nodeCol;                                           // :97
 		pending[v] = 0;
-		if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+		if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(changed, 1u); }
 	}
 }
 
 template <typename ColT>
 __global__ void __launch_bounds__(kTcThreads)
 tailcut_apply_heavy_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol, ColT * colors, uint8_t * pending,
-                           const uint32_t * __restrict__ order, unsigned long long * hist, const uint32_t * heavy) {
+                           const uint32_t * __restrict__ order, unsigned long long * hist, const uint32_t * heavy, uint32_t * changed) {
 	extern __shared__ uint32_t tc_smem[];
 	uint32_t * bm = tc_smem + 4;
 	const uint32_t cnt = heavy[0];
@@ -138,7 +139,7 @@ tailcut_apply_heavy_kernel(const uint32_t * __restrict__ rowptr, const uint32_t 
 		if (threadIdx.x == 0) {
 			colors[v] = (ColT)nodeCol;
 			pending[v] = 0;
-			if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+			if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(changed, 1u); }
 		}
 		__syncthreads();
 	}
@@ -150,10 +151,11 @@ inline size_t tc_smem_bytes(uint32_t nCol) { return sizeof(uint32_t) * (4 + (siz
 // d_heavy: [1 + n] scratch for the ready hub rows of a round (may alias nothing else).
 inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t * rowptr, const uint32_t * neighs, uint32_t n,
                                uint32_t nCol, void * colors, unsigned long long * hist, const uint32_t * d_order,
-                               uint8_t * d_pending, uint8_t * d_ready, uint32_t * d_list, uint32_t * d_heavy, uint32_t * d_counters /* [2] */,
-                               uint32_t * flaggedOut, uint64_t * launches) {
+                               uint8_t * d_pending, uint8_t * d_ready, uint32_t * d_list, uint32_t * d_heavy, uint32_t * d_counters /* [3] */,
+                               uint32_t * flaggedOut, uint32_t * changedOut, uint64_t * launches) {
 	cudaError_t e;
-	if ((e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
+	*changedOut = 0;
+	if ((e = cudaMemsetAsync(d_counters, 0, 3 * sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
 	const uint32_t blocks = (n + 255) / 256;
 	if (colBytes == 1) tailcut_flag_kernel<uint8_t><<<blocks, 256, 0, stream>>>(rowptr, neighs, n, (const uint8_t *)colors, d_pending, d_list, d_counters);
 	else tailcut_flag_kernel<uint16_t><<<blocks, 256, 0, stream>>>(rowptr, neighs, n, (const uint16_t *)colors, d_pending, d_list, d_counters);
@@ -170,11 +172,11 @@ inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t
 		if ((e = cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), stream)) != cudaSuccess) return (int)e;
 		tailcut_ready_kernel<<<lb, 256, 0, stream>>>(rowptr, neighs, d_pending, d_list, listCount, d_ready);
 		if (colBytes == 1) {
-			tailcut_apply_kernel<uint8_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy);
-			tailcut_apply_heavy_kernel<uint8_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_order, hist, d_heavy);
+			tailcut_apply_kernel<uint8_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy, d_counters + 2);
+			tailcut_apply_heavy_kernel<uint8_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint8_t *)colors, d_pending, d_order, hist, d_heavy, d_counters + 2);
 		} else {
-			tailcut_apply_kernel<uint16_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy);
-			tailcut_apply_heavy_kernel<uint16_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_order, hist, d_heavy);
+			tailcut_apply_kernel<uint16_t><<<lb, 256, 0, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_list, listCount, d_ready, d_order, hist, d_counters + 1, d_heavy, d_counters + 2);
+			tailcut_apply_heavy_kernel<uint16_t><<<64, kTcThreads, smem, stream>>>(rowptr, neighs, nCol, (uint16_t *)colors, d_pending, d_order, hist, d_heavy, d_counters + 2);
 		}
 		(*launches) += 3;
 		uint32_t remaining = 0;
@@ -182,6 +184,8 @@ inline int launch_tailcut_pass(cudaStream_t stream, int colBytes, const uint32_t
 		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
 		if (remaining == 0) break;
 	}
+	if ((e = cudaMemcpyAsync(changedOut, d_counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return (int)e;
+	if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
 	return (int)cudaGetLastError();
 }
 
@@ -205,6 +209,8 @@ struct TailcutCounters {
 	uint32_t nextFlagged;        // of those, vertices the reference would flag again
 	unsigned long long directed; // sum over vertices of same-coloured neighbours (= 2 x conflicting edges)
 	unsigned long long viol;     // violating vertices
+	uint32_t changed;            // vertices the pass gave a new colour (0: the pass made no progress -- hubs with every colour taken)
+	uint32_t pad;
 };
 
 template <typename ColT>
@@ -222,7 +228,8 @@ __global__ void tc_filter_kernel(const uint32_t * __restrict__ rowptr, const uin
 template <typename ColT>
 __global__ void __launch_bounds__(kTcThreads)
 tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol, ColT * colors, uint8_t * pending,
-                 const uint32_t * __restrict__ flist, TailcutCounters * cnt, const uint32_t * __restrict__ order, unsigned long long * hist) {
+                 const uint32_t * __restrict__ flist, uint32_t * resume /* [flagged], zeroed */, TailcutCounters * cnt, const uint32_t * __restrict__ order,
+                 unsigned long long * hist) {
 	extern __shared__ uint32_t tc_smem[];                        // [0] best, [1] left, [2] heavy ready this round, [4..] bitmap
 	uint32_t * bm = tc_smem + 4;
 	const uint32_t n = cnt->flagged;
@@ -233,9 +240,20 @@ tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restri
 		for (uint32_t i = warp; i < n; i += nWarps) {
 			const uint32_t v = flist[i];
 			if (pending[v] != 1) continue;
-			const bool blocked = tc_warp_any(neighs, rowptr[v], rowptr[v + 1], lane, [&](uint32_t u) { return u < v && pending[u]; });
+			// (flags only ever drop during a pass, so the part of the row that held no pending smaller neighbour in an earlier round
+			//  need not be looked at again: a hub row is scanned once per pass, not once per round)
+			const uint32_t e1 = rowptr[v + 1];
+			uint32_t e = rowptr[v] + resume[i];
+			for (; e < e1; e += 32u) {
+				bool hit = false;
+				if (e + lane < e1) { const uint32_t u = neighs[e + lane]; hit = u < v && pending[u]; }
+				if (__any_sync(0xffffffffu, hit)) break;
+			}
 			__syncwarp();
-			if (!blocked && lane == 0) pending[v] = 3;             // pending AND ready (still non-zero for its larger neighbours)
+			if (lane == 0) {
+				if (e < e1) resume[i] = e - rowptr[v];
+				else pending[v] = 3;                               // pending AND ready (still non-zero for its larger neighbours)
+			}
 		}
 		if (threadIdx.x == 0) { tc_smem[1] = 0u; tc_smem[2] = 0u; }
 		__syncthreads();
@@ -255,7 +273,7 @@ tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restri
 				if (inexact) cnt->inexact = 1u;                        // every colour taken: may disturb an unlisted neighbour
 				colors[v] = (ColT)nodeCol;                             // :97
 				pending[v] = 4;                                        // done this round (flag drops after the barrier)
-				if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+				if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(&cnt->changed, 1u); }
 			}
 		}
 		__syncthreads();
@@ -270,7 +288,7 @@ tc_rounds_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restri
 					if (inexact) cnt->inexact = 1u;
 					colors[v] = (ColT)nodeCol;
 					pending[v] = 4;
-					if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); }
+					if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(&cnt->changed, 1u); }
 				}
 				__syncthreads();
 			}

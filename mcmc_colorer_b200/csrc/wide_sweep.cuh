@@ -39,9 +39,9 @@ __host__ inline void wide_geometry(uint32_t nCol, WideArgs & wa) {
 	wa.bmStride = wa.bmWords | 1u;
 	const uint32_t lq = wide_list_queue_bytes();
 	uint32_t budget = kWideWarpBytes > lq ? kWideWarpBytes : lq;
-	uint32_t batch = budget / (4u * wa.bmStride);
+	uint32_t batch = (budget - 128u) / (4u * wa.bmStride);          // (128 bytes: the batch's "same colour" counters)
 	if (batch > 32u) batch = 32u;
-	if (batch < 1u) { batch = 1u; budget = 4u * wa.bmStride; }
+	if (batch < 1u) { batch = 1u; budget = 4u * wa.bmStride + 128u; }
 	wa.batch = batch;
 	wa.warpBytes = (budget + 15u) & ~15u;
 }
@@ -77,6 +77,9 @@ struct WideList {                      // entries at base[j * stride], j < deg
 		for (uint32_t j = 0; j < deg; ++j) { const uint32_t c = base[j * stride]; if (c >= pos && c < best) best = c; }
 		return best;
 	}
+	template <typename F> __device__ __forceinline__ void each(uint32_t nCol, F f) const {      // occupied colours in ascending order
+		for (uint32_t c = next(0u, nCol); c < nCol; c = next(c + 1u, nCol)) f(c);
+	}
 };
 struct WideBitmap {
 	const uint32_t * w; uint32_t words;
@@ -88,10 +91,21 @@ struct WideBitmap {
 		const uint32_t c = (i << 5) + (uint32_t)(__ffs((int)bits) - 1);
 		return c < nCol ? c : nCol;
 	}
+	template <typename F> __device__ __forceinline__ void each(uint32_t nCol, F f) const {      // occupied colours in ascending order
+		for (uint32_t i = 0; i < words; ++i) {
+			uint32_t bits = w[i];
+			while (bits) {
+				const uint32_t c = (i << 5) + (uint32_t)(__ffs((int)bits) - 1);
+				bits &= bits - 1u;
+				if (c < nCol) f(c);
+			}
+		}
+	}
 };
 
 // colour write + taboo + class-size deltas (finish_vertex of sweep_kernel.cuh; the deltas go straight to the global scratch)
 __device__ __forceinline__ void finish_wide(const SweepArgs & a, uint16_t * __restrict__ nxt, uint32_t lv, uint32_t myOwn, uint32_t newc, bool touchTaboo) {
+	MCMCB200_CHECK(newc < a.nCol && myOwn < a.nCol && lv < a.nLocal, a.st);
 	if (touchTaboo && a.tabooIter) a.taboo[lv] = (uint16_t)((newc == myOwn) ? a.tabooIter : 0u);
 	nxt[a.vBegin + lv] = (uint16_t)newc;
 	if (newc != myOwn) { atomicAdd(a.scratch + 2 + myOwn, ~0ull); atomicAdd(a.scratch + 2 + newc, 1ull); }
@@ -119,6 +133,49 @@ __device__ __forceinline__ uint32_t walk_wide(const SweepArgs & a, const WideArg
 	return nCol - 1u;                                           // overflow contract: clamp to nCol-1
 }
 
+// the same walk straight over the bitmap words, 4 colours per stop test (walk_conflicting of sweep_kernel.cuh: the running sum is
+// non-decreasing, so the first crossing inside a block of 4 is located afterwards; DYNAMIC's r < 0 corner takes single steps).
+// ~4.5 instructions per colour whatever the number of occupied colours -- hub rows have nearly all of them occupied.
+template <bool kDyn>
+__device__ __forceinline__ uint32_t walk_wide(const SweepArgs & a, const WideArgs & wa, const WideBitmap & occ, float u, float x) {
+	const uint32_t nCol = a.nCol;
+	const float eps = a.eps;
+	float cdf = 0.0f;
+	const bool blocks = !kDyn || x >= 0.0f;
+	for (uint32_t i = 0; i < occ.words; ++i) {
+		uint32_t bits = occ.w[i];
+		const uint32_t base = i << 5;
+		const uint32_t lim = min(32u, nCol - base);
+		uint32_t b = 0;
+		if (blocks) {
+			for (; b + 4u <= lim; b += 4u) {
+				float q0, q1, q2, q3;
+				if (kDyn) {
+					const float * d = wa.tab + base + b;
+					q0 = (bits & 1u) ? eps : __fadd_rn(__ldg(d + 0), x); q1 = (bits & 2u) ? eps : __fadd_rn(__ldg(d + 1), x);
+					q2 = (bits & 4u) ? eps : __fadd_rn(__ldg(d + 2), x); q3 = (bits & 8u) ? eps : __fadd_rn(__ldg(d + 3), x);
+				} else {
+					q0 = (bits & 1u) ? eps : x; q1 = (bits & 2u) ? eps : x; q2 = (bits & 4u) ? eps : x; q3 = (bits & 8u) ? eps : x;
+				}
+				const float c1 = __fadd_rn(cdf, q0), c2 = __fadd_rn(c1, q1), c3 = __fadd_rn(c2, q2), c4 = __fadd_rn(c3, q3);
+				if (kDyn ? (c4 >= u) : (c4 > u)) {
+					const uint32_t first = (kDyn ? (c1 >= u) : (c1 > u)) ? 0u : (kDyn ? (c2 >= u) : (c2 > u)) ? 1u : (kDyn ? (c3 >= u) : (c3 > u)) ? 2u : 3u;
+					return base + b + first;
+				}
+				cdf = c4;
+				bits >>= 4;
+			}
+		}
+		for (; b < lim; ++b) {
+			const float q = (bits & 1u) ? eps : (kDyn ? __fadd_rn(__ldg(wa.tab + base + b), x) : x);
+			bits >>= 1;
+			cdf = __fadd_rn(cdf, q);
+			if (kDyn ? (cdf >= u) : (cdf > u)) return base + b;
+		}
+	}
+	return nCol - 1u;                                           // overflow contract: clamp to nCol-1
+}
+
 // phase 3 of one vertex up to the walk (commit_vertex of sweep_kernel.cuh with the occupancy behind `occ`).  ZnKnown: number of
 // occupied colours if the caller has it (bitmaps: popc), 0xffffffff otherwise (lists: counted here, only when it is needed).
 // Returns true when the vertex still has to WALK (u, x, Zn filled in); otherwise the vertex is finished.
@@ -134,7 +191,7 @@ __device__ __forceinline__ bool prepare_wide(const SweepArgs & a, const WideArgs
 	if (a.dbgMasks) {
 		unsigned long long * row = a.dbgMasks + (size_t)lv * wa.words64;
 		for (uint32_t w = 0; w < wa.words64; ++w) row[w] = 0ull;
-		for (uint32_t c = occ.next(0u, nCol); c < nCol; c = occ.next(c + 1u, nCol)) row[c >> 6] |= 1ull << (c & 63u);
+		occ.each(nCol, [&](uint32_t c) { row[c >> 6] |= 1ull << (c & 63u); });
 		a.dbgSame[lv] = same;
 	}
 	if (viol && a.violList != nullptr) {
@@ -151,7 +208,7 @@ __device__ __forceinline__ bool prepare_wide(const SweepArgs & a, const WideArgs
 	// Zn is only needed by conflicting vertices (and by DYNAMIC's "no free colour: no draw" rule, which a row shorter than the
 	// palette can never meet)
 	uint32_t Zn = ZnKnown;
-	if (Zn == 0xffffffffu && viol) { Zn = 0u; for (uint32_t c = occ.next(0u, nCol); c < nCol; c = occ.next(c + 1u, nCol)) ++Zn; }
+	if (Zn == 0xffffffffu && viol) { Zn = 0u; occ.each(nCol, [&](uint32_t) { ++Zn; }); }
 	const uint32_t Zp = (Zn == 0xffffffffu) ? nCol : nCol - Zn;    // (unknown: a non-conflicting list row, Zp > 0 for sure)
 	if (kDyn && Zp == 0u) { finish_wide(a, nxt, lv, myOwn, myOwn, false); return false; }   // coloringMCMC_balance.cu:111-115: no draw, taboo untouched
 	if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
@@ -168,8 +225,7 @@ __device__ __forceinline__ bool prepare_wide(const SweepArgs & a, const WideArgs
 	if (!kDyn) x = __ldg(wa.tab + Zn);
 	else {
 		float rem = 0.0f;                                           // ascending colour order, like the reference's loop (:104-107)
-		for (uint32_t c = occ.next(0u, nCol); c < nCol; c = occ.next(c + 1u, nCol))
-			rem = __fadd_rn(rem, __fsub_rn(__ldg(wa.tab + c), eps));
+		occ.each(nCol, [&](uint32_t c) { rem = __fadd_rn(rem, __fsub_rn(__ldg(wa.tab + c), eps)); });
 		x = __fdiv_rn(rem, __uint2float_rn(Zp));
 	}
 	return true;
@@ -221,6 +277,7 @@ wide_sweep_kernel(const SweepArgs a, const BinnedArgs bn, const WideArgs wa) {
 				if (e + k * kThreadsBin < e1) {
 					same += (c[k] == own);
 					const uint32_t bit = 1u << (c[k] & 31u);
+					MCMCB200_CHECK(c[k] < nCol, st);
 					if (!(s_bm[c[k] >> 5] & bit)) atomicOr(&s_bm[c[k] >> 5], bit);      // (hub rows hit the same few words: test first)
 				}
 			}
@@ -241,10 +298,14 @@ wide_sweep_kernel(const SweepArgs a, const BinnedArgs bn, const WideArgs wa) {
 		}
 	}
 
-	// ---------------- warp rows: a batch of rows per warp, one bitmap each; then the lanes commit their rows together ----------------
+	// ---------------- warp rows: a batch of rows per warp, one bitmap each.  The edges of the whole batch are walked as ONE flat
+	//                  range (lane -> (row, offset) by a binary search over the scanned row lengths), so the id loads and colour
+	//                  gathers of consecutive rows overlap -- most warp rows of a power-law graph are only a few dozen entries long,
+	//                  and row-by-row processing would pay two dependent memory latencies per row.  Then the lanes commit together ----
 	{
 		uint32_t * bms = reinterpret_cast<uint32_t *>(mineRaw);
 		const uint32_t B = wa.batch, stride = wa.bmStride;
+		uint32_t * s_same = bms + (size_t)B * stride;                 // [32]
 		for (;;) {
 			uint32_t base = 0;
 			if (lane == 0) base = atomicAdd(bn.counters + 1, B);
@@ -254,42 +315,49 @@ wide_sweep_kernel(const SweepArgs a, const BinnedArgs bn, const WideArgs wa) {
 			const bool valid = (uint32_t)lane < cntB;
 			const uint32_t lvMine = valid ? bn.list[1][base + lane] : 0u;
 			const uint32_t begMine = valid ? a.rowptr[lvMine] : 0u, endMine = valid ? a.rowptr[lvMine + 1] : 0u;
-			const uint32_t ownMine = valid ? (uint32_t)cur[a.vBegin + lvMine] : 0u;
-			uint32_t same = 0, znMine = 0;
+			const uint32_t ownMine = valid ? (uint32_t)cur[a.vBegin + lvMine] : 0xffffffffu;
+			uint32_t P = endMine - begMine;                           // inclusive scan of the row lengths
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t tt = __shfl_up_sync(0xffffffffu, P, o); if (lane >= o) P += tt; }
+			const uint32_t T = __shfl_sync(0xffffffffu, P, 31);
+			const uint32_t startMine = P - (endMine - begMine);
 			__syncwarp();
 			for (uint32_t w = lane; w < cntB * stride; w += 32u) bms[w] = 0u;
+			s_same[lane] = 0u;
 			__syncwarp();
-			for (uint32_t j = 0; j < cntB; ++j) {
-				const uint32_t e0 = __shfl_sync(0xffffffffu, begMine, j), e1 = __shfl_sync(0xffffffffu, endMine, j);
-				const uint32_t ownJ = __shfl_sync(0xffffffffu, ownMine, j);
-				uint32_t * bm = bms + (size_t)j * stride;
-				uint32_t ss = 0;
-				for (uint32_t e = e0 + lane; e < e1; e += 32u * kBinUnroll) {
-					uint32_t nb[kBinUnroll], c[kBinUnroll];
+			for (uint32_t f0 = 0; f0 < T; f0 += 32u * kBinUnroll) {
+				uint32_t nb[kBinUnroll], c[kBinUnroll], jj[kBinUnroll];
 #pragma unroll
-					for (int k = 0; k < kBinUnroll; ++k) nb[k] = (e + 32u * k < e1) ? __ldcs(a.neighs + e + 32u * k) : 0u;
+				for (int k = 0; k < kBinUnroll; ++k) {
+					const uint32_t f = f0 + 32u * k + lane;
+					uint32_t j = 0;                                   // smallest j with P_j > f
 #pragma unroll
-					for (int k = 0; k < kBinUnroll; ++k) c[k] = (e + 32u * k < e1) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
+					for (int step = 16; step; step >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, P, (int)(j + step - 1u)); if (pj <= f) j += step; }
+					j = min(j, 31u);
+					const uint32_t sj = __shfl_sync(0xffffffffu, startMine, (int)j), bj = __shfl_sync(0xffffffffu, begMine, (int)j);
+					jj[k] = j;
+					nb[k] = (f < T) ? __ldcs(a.neighs + bj + (f - sj)) : 0u;
+				}
 #pragma unroll
-					for (int k = 0; k < kBinUnroll; ++k) {
-						if (e + 32u * k < e1) {
-							ss += (c[k] == ownJ);
-							atomicOr(&bm[c[k] >> 5], 1u << (c[k] & 31u));
-						}
+				for (int k = 0; k < kBinUnroll; ++k) c[k] = (f0 + 32u * k + lane < T) ? ld_color<ColT>(cur + nb[k], polLast) : 0xfffffffeu;
+#pragma unroll
+				for (int k = 0; k < kBinUnroll; ++k) {
+					const uint32_t ownJ = __shfl_sync(0xffffffffu, ownMine, (int)jj[k]);
+					if (f0 + 32u * k + lane < T) {
+						MCMCB200_CHECK(c[k] < nCol && jj[k] < cntB && nb[k] < a.nGlobal, st);
+						if (c[k] == ownJ) atomicAdd(&s_same[jj[k]], 1u);
+						atomicOr(&bms[(size_t)jj[k] * stride + (c[k] >> 5)], 1u << (c[k] & 31u));
 					}
 				}
-				ss = __reduce_add_sync(0xffffffffu, ss);
-				__syncwarp();
-				uint32_t zn = 0;
-				for (uint32_t w = lane; w < bmWords; w += 32u) zn += (uint32_t)__popc(bm[w]);
-				zn = __reduce_add_sync(0xffffffffu, zn);
-				if ((uint32_t)lane == j) { same = ss; znMine = zn; }
 			}
 			__syncwarp();
 			if (valid) {
-				const WideBitmap occ{bms + (size_t)lane * stride, bmWords};
+				const uint32_t * bm = bms + (size_t)lane * stride;    // odd stride: word w of the 32 bitmaps sits in 32 different banks
+				uint32_t zn = 0;
+				for (uint32_t w = 0; w < bmWords; ++w) zn += (uint32_t)__popc(bm[w]);
+				const WideBitmap occ{bm, bmWords};
 				float u = 0.0f, x = 0.0f;
-				if (prepare_wide<kDyn>(a, wa, t, nxt, a.vBegin + lvMine, lvMine, ownMine, occ, same, znMine, stayW, accDirected, accViol, u, x))
+				if (prepare_wide<kDyn>(a, wa, t, nxt, a.vBegin + lvMine, lvMine, ownMine, occ, s_same[lane], zn, stayW, accDirected, accViol, u, x))
 					finish_wide(a, nxt, lvMine, ownMine, walk_wide<kDyn>(a, wa, occ, u, x), true);
 			}
 			__syncwarp();
@@ -331,7 +399,7 @@ wide_sweep_kernel(const SweepArgs a, const BinnedArgs bn, const WideArgs wa) {
 				for (int k = 0; k < 4; ++k) c[k] = (i + k < deg) ? ld_color<ColT>(cur + nb[k], polLast) : 0xffffffffu;
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					if (i + k < deg) { same += (c[k] == own); mine[(i + k) * 32u] = (uint16_t)c[k]; }
+					if (i + k < deg) { MCMCB200_CHECK(c[k] < nCol && i + k < kWideListCap, st); same += (c[k] == own); mine[(i + k) * 32u] = (uint16_t)c[k]; }
 				}
 			}
 			bool walk = false;
@@ -345,6 +413,7 @@ wide_sweep_kernel(const SweepArgs a, const BinnedArgs bn, const WideArgs wa) {
 			if (nw) {
 				if (walk) {                                           // (qn < 32 here, nw <= 32: always room)
 					const uint32_t slot = qn + (uint32_t)__popc(wm & ((1u << lane) - 1u));
+					MCMCB200_CHECK(slot < kWideQueueCap, st);
 					for (uint32_t j = 0; j < deg; ++j) q_list[j * kWideQueueCap + slot] = mine[j * 32u];
 					q_hdr[slot] = lv; q_hdr[kWideQueueCap + slot] = own; q_hdr[2 * kWideQueueCap + slot] = deg;
 					q_hdr[3 * kWideQueueCap + slot] = __float_as_uint(u); q_hdr[4 * kWideQueueCap + slot] = __float_as_uint(x);

@@ -247,7 +247,7 @@ def slice_csr_torch(rowptr, neighs, vb, ve):
     return rp, nb, e1 - e0
 
 
-def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSampler):
+def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSampler, palette_for, RMAT):
     """bench.py under torchrun (N > 1): strong scaling of the same workload, vertex-partitioned over N GPUs."""
     import json
     import torch
@@ -263,7 +263,8 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     # every rank generates the same graph on its own GPU (deterministic), keeps its rows and frees the rest
     skewed = args.workload.startswith("c4")
     if skewed:
-        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(max(1, (n - 1).bit_length()), deg, GRAPH_SEED, n_keep=n, device=dev)
+        ra, rb, rc = RMAT[args.workload]
+        rowptr64, neighs, nnz, max_deg = rmat_graph_torch(max(1, (n - 1).bit_length()), deg, GRAPH_SEED, n_keep=n, a=ra, b=rb, c=rc, device=dev)
     else:
         rowptr64, neighs, nnz, max_deg = er_graph_torch(n, deg, GRAPH_SEED, device=dev)
     # contiguous vertex ranges: equal vertex counts on Erdos-Renyi (they are nnz-balanced to a fraction of a percent and keep the
@@ -275,7 +276,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     rp, nb, nnz_local = slice_csr_torch(rowptr64, neighs, vb, ve)
     del rowptr64, neighs
     torch.cuda.empty_cache()
-    nCol = min(max_deg, 512) if skewed else max_deg      # (bench.py palette_for: R-MAT hubs have degree ~1e6)
+    nCol = getattr(args, "ncol", 0) or palette_for(args.workload, max_deg)      # (bench.py: R-MAT hubs have degree ~1e6)
     proposal = capi.PROPOSAL_UNIFORM if args.proposal == "uniform" else capi.PROPOSAL_DYNAMIC
     prm = ColoringMCMCParams(nCol=nCol, proposal=proposal, seed=CHAIN_SEED,
                              convergence=capi.CONVERGE_VERTICES if proposal == capi.PROPOSAL_UNIFORM else capi.CONVERGE_EDGES)
