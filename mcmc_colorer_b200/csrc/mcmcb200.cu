@@ -76,6 +76,9 @@ struct mcmcb200_handle {
 	BinnedLayout bn;                     // degree-binned direct sweep (valid => used when bl is not)
 	bool wide = false;                   // nCol > 512: wide_sweep_kernel over the binned lists (wide_sweep.cuh)
 	float * d_wideS = nullptr, * d_wideTab = nullptr;
+	uint8_t * d_wideFp = nullptr;                          // one-byte fingerprint of the current colouring (wide_fingerprint_kernel)
+	uint32_t * d_wideQ = nullptr, * d_wideQcta = nullptr;   // rows queued by wide_count_kernel for wide_walk_kernel
+	int wideGridCount = 0;
 	uint32_t maskWords64 = 1;            // 64-bit words of one vertex' occupancy mask (debug interface)
 	void * peerColors[2][kMaxPeers] = {};  // fused multi-GPU exchange: IPC-mapped colour buffers of every rank (own = local)
 	uint32_t * d_violList[2] = {nullptr, nullptr};   // tail cutting: violating vertices emitted by the sweeps / left by the last repair pass
@@ -103,8 +106,8 @@ template <int W, typename ColT>
 cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 	if (h->bl.valid) {
 		// source-blocked path: pass A (gather through shared memory) + pass B (tile sweep); two launches per sweep
-		const BlockedArgs b = make_blocked_args(h->bl);
-		const size_t syncBytes = sizeof(uint32_t) * (2 + (size_t)h->bl.numParts);
+		BlockedArgs b = make_blocked_args(h->bl);
+		const size_t syncBytes = sizeof(uint32_t) * (3 + (size_t)h->bl.numParts);
 		cudaStream_t sA = h->stream;
 		cudaError_t e = cudaSuccess;
 		if (h->overlap) {
@@ -120,6 +123,21 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 #endif
 		if (e == cudaSuccess && h->overlap) e = cudaEventRecord(h->evReset, sA);   // B may start as soon as the counters are clean
 		if (e != cudaSuccess) return e;
+#ifndef MCMCB200_SPLIT_A
+#define MCMCB200_SPLIT_A 0
+#endif
+		if (MCMCB200_SPLIT_A && h->overlap && h->bl.numParts >= 2u && h->bl.gridA0 > h->bl.gridA) {
+			// the first part at full occupancy (pass B cannot start before it is complete anyway: its CTAs move in as these retire),
+			// the rest with the one CTA per SM that fits next to pass B
+			BlockedArgs b0 = b;
+			b0.itemBegin = 0; b0.itemEnd = h->bl.P; b0.itemCounter = 0;
+			blocked_gather_kernel<ColT><<<h->bl.gridA0, kThreadsA, h->bl.smemA, sA>>>(a, b0);
+			h->launches++;
+			if ((e = cudaGetLastError()) != cudaSuccess) return e;
+			BlockedArgs b1 = b;
+			b1.itemBegin = h->bl.P; b1.itemEnd = h->bl.numItems; b1.itemCounter = 2u + h->bl.numParts;
+			blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b1);
+		} else
 		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b);
 		h->launches++;
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;    // (pass B must not be launched without its producer)
@@ -187,6 +205,7 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	h->overlap = aFit >= 1 && !(h->p.flags & MCMCB200_FLAG_NO_OVERLAP);
 	if (h->overlap) {
 		L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(std::min<long>(aFit, oa) * h->smCount)));
+		L.gridA0 = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.P, (uint32_t)(oa * h->smCount)));
 		if (!h->streamA) e = cudaStreamCreateWithFlags(&h->streamA, cudaStreamNonBlocking);
 		if (e == cudaSuccess && !h->evFork) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
 		if (e == cudaSuccess && !h->evReset) e = cudaEventCreateWithFlags(&h->evReset, cudaEventDisableTiming);
@@ -226,12 +245,21 @@ cudaError_t launch_sweep_wide(mcmcb200_handle * h, const SweepArgs & a) {
 	const BinnedArgs b = make_binned_args(h->bn);
 	WideArgs wa{};
 	wide_geometry(h->p.nCol, wa);
-	wa.S = h->d_wideS; wa.tab = h->d_wideTab; wa.words64 = h->maskWords64;
+	wa.S = h->d_wideS; wa.tab = h->d_wideTab; wa.words64 = h->maskWords64; wa.fp = h->d_wideFp;
+	const WideQueues wq{h->d_wideQ, h->d_wideQcta};
 	cudaError_t e = cudaMemsetAsync(h->bn.counters, 0, 4 * sizeof(uint32_t), h->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->d_wideQ, 0, 8 * sizeof(uint32_t), h->stream);
 	if (e != cudaSuccess) return e;
+	const bool walk = !a.countOnly || a.dbgMasks != nullptr;      // a plain counting pass needs no occupancy at all
 	if (!a.countOnly) { wide_tables_kernel<<<(h->p.nCol + 255) / 256, 256, 0, h->stream>>>(a, wa); h->launches++; }
-	if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) wide_sweep_kernel<true><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b, wa);
-	else wide_sweep_kernel<false><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, b, wa);
+	wide_fingerprint_kernel<<<h->smCount * 8, 256, 0, h->stream>>>(a, wa); h->launches++;
+	const bool dyn = a.proposal == MCMCB200_PROPOSAL_DYNAMIC;
+	if (dyn) wide_count_kernel<true><<<h->wideGridCount, kThreadsBin, 0, h->stream>>>(a, b, wa, wq, walk ? 0u : 1u);
+	else wide_count_kernel<false><<<h->wideGridCount, kThreadsBin, 0, h->stream>>>(a, b, wa, wq, walk ? 0u : 1u);
+	if ((e = cudaGetLastError()) != cudaSuccess || !walk) return e;
+	h->launches++;
+	if (dyn) wide_walk_kernel<true><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, wa, wq);
+	else wide_walk_kernel<false><<<h->bn.grid, kThreadsBin, h->bn.smem, h->stream>>>(a, wa, wq);
 	return cudaGetLastError();
 }
 
@@ -240,15 +268,22 @@ cudaError_t configure_wide(mcmcb200_handle * h) {
 	WideArgs wa{};
 	wide_geometry(h->p.nCol, wa);
 	L.smem = wide_smem_bytes(wa);
-	cudaError_t e = cudaFuncSetAttribute(wide_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-	int o0 = 0, o1 = 0;
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, wide_sweep_kernel<false>, kThreadsBin, L.smem);
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, wide_sweep_kernel<true>, kThreadsBin, L.smem);
+	cudaError_t e = cudaFuncSetAttribute(wide_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+	int o0 = 0, o1 = 0, c0 = 0, c1 = 0;
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, wide_walk_kernel<false>, kThreadsBin, L.smem);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, wide_walk_kernel<true>, kThreadsBin, L.smem);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c0, wide_count_kernel<false>, kThreadsBin, 0);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c1, wide_count_kernel<true>, kThreadsBin, 0);
 	if (e != cudaSuccess) return e;
-	const int o = o0 < o1 ? o0 : o1;
-	if (o < 1) { L.valid = false; return cudaSuccess; }
+	const int o = o0 < o1 ? o0 : o1, c = c0 < c1 ? c0 : c1;
+	if (o < 1 || c < 1) { L.valid = false; return cudaSuccess; }
 	L.grid = o * h->smCount;
+	h->wideGridCount = c * h->smCount;
+	// the rows the counting pass hands to the walk pass: at most every owned vertex (debug interface), hub rows separately
+	if ((e = cudaMalloc(&h->d_wideFp, (size_t)h->nGlobal + kColorPad)) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&h->d_wideQ, sizeof(uint32_t) * ((size_t)h->nLocal + 8))) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&h->d_wideQcta, sizeof(uint32_t) * ((size_t)L.n[2] + 1))) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
@@ -552,11 +587,13 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 			// config 3 (profiles/r02*): 24 KiB 4.38 ms, 32 KiB 3.64, 36 KiB 4.35, 44 KiB 4.01 -- short tiles keep pass B's per-tile
 			// phases short, too short ones cut pass A's runs.  Smaller partitions (fill/drain of the A->B pipeline would eat the
 			// gain; measured on config 5): the largest stage the 16-bit positions allow, passes back to back
-			uint32_t capBytes = nnzLocal >= (1ull << 29) ? 32768u : 65504u;
+			// (round 2, pass A with 12 granules in flight: the overlapped pair also wins on 1.6e8-edge partitions -- config 5: 0.362 ms
+			//  against 0.409 back to back -- so the threshold moved from 2^29 to 2^27 edges: 8-GPU ranks of config 3 overlap too)
+			uint32_t capBytes = nnzLocal >= (1ull << 27) ? 32768u : 65504u;
 			uint32_t nbuf = 1u;
 			// pass-A work item: 2^16 entries of one bucket when the passes overlap (the chunk reload is one bulk copy now; 2^15:
 			// 4.04 ms, 2^16: 3.64, 2^17: 3.70, 2^18: 3.81 on config 3), 2^17 back to back
-			uint32_t itemEntries = nnzLocal >= (1ull << 29) ? (1u << 16) : (1u << 17);
+			uint32_t itemEntries = nnzLocal >= (1ull << 27) ? (1u << 16) : (1u << 17);
 			if (p->itemBits) itemEntries = 1u << p->itemBits;
 			if (p->stageCapBytes) capBytes = p->stageCapBytes;
 			if (p->stageBuffers) nbuf = p->stageBuffers;
@@ -753,7 +790,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	cudaFree(h->d_history); cudaFree(h->d_countOut); cudaFree(h->d_stage32);
 	free_blocked_layout(h->bl);
 	free_binned_layout(h->bn);
-	cudaFree(h->d_wideS); cudaFree(h->d_wideTab);
+	cudaFree(h->d_wideS); cudaFree(h->d_wideTab); cudaFree(h->d_wideQ); cudaFree(h->d_wideQcta); cudaFree(h->d_wideFp);
 	mcmcb200_ipc_detach(h);
 	cudaFree(h->d_xchg);
 	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcResume); cudaFree(h->d_tcCnt);

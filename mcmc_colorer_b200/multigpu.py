@@ -284,17 +284,24 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
     fused = eng.enable_p2p(rank, world) if os.environ.get("MCMCB200_NO_P2P") is None else False
     sw = DistributedSweeper(eng, rank, world, chunk, parts=parts)
 
-    def timed_step():
+    sync_word = torch.zeros(1, device=dev)
+
+    def timed_step(k=1):
+        """k sweeps timed on the device, max over ranks.  Host barrier + synchronize on both sides; in addition the ranks meet ON THE
+        DEVICE right before the start event (a one-word all-reduce on the sweep stream), so that the start skew of the host processes
+        after dist.barrier() (tens of microseconds, against a 0.5 ms step at 8 GPUs) is not charged to the sweep."""
         eng.init_colors(None)
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(eng.stream):
+            dist.all_reduce(sync_word)
             e0.record()
-        sw.sweep(1)
+        sw.sweep(k)
         with torch.cuda.stream(eng.stream):
             e1.record()
         torch.cuda.synchronize()
+        dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)                                      # max over ranks
         return float(ms.item())
@@ -306,6 +313,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
         steps_ms = [timed_step() for _ in range(args.steps)]
     launches = eng.chain.launch_count() - l0
     ms_per_step = float(np.mean(steps_ms))
+    chain_ms = timed_step(10) / 10.0                      # ten consecutive sweeps in one timed region (steady state of a chain)
     # end to end with host buffers: every rank uploads the colours of the vertices it owns from pinned memory (H2D), the slices
     # are exchanged on the device, then sweep + exchange, global counters (D2H) and the owned slice of the result (D2H)
     n_own = ve - vb
@@ -342,7 +350,7 @@ def bench_main(args, WORKLOADS, GRAPH_SEED, CHAIN_SEED, measured_peak, ClockSamp
                        "parallelism": f"vertex partition x{world} ({'nnz-balanced' if skewed else 'equal vertex counts'}); " + ("colour exchange AND counter all-reduce + inter-rank barrier fused into the sweep kernels (peer stores / system-scope reductions over NVLink): no NCCL call, no host in the sweep loop" if fused else "NCCL all-gather of the narrow colour slices + one NCCL all-reduce of the counters per sweep"),
                        "step": "one sweep from the uniform random colouring incl. the colour exchange (max over ranks)",
                        "l2": "inputs larger than L2; no flush needed"},
-            "edges_per_sec": value * nnz / n,
+            "edges_per_sec": value * nnz / n, "chain_ms_per_sweep": chain_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": "per rank: " + eng.chain.kernel_mode() + " sweep + colour exchange + counter all-reduce"},
