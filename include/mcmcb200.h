@@ -142,6 +142,27 @@ int mcmcb200_color_bytes(mcmcb200_handle * h, uint32_t * elemBytes);
 int mcmcb200_init_colors_narrow(mcmcb200_handle * h, const void * colors /* [nGlobal] u8 or u16 */, uint32_t elemBytes);
 int mcmcb200_get_colors_narrow(mcmcb200_handle * h, void * out /* [nGlobal] u8 or u16 */, uint32_t elemBytes);
 
+/* Tail cutting of a multi-GPU chain (the reference is single-GPU; same result as mcmcb200_tailcut, i.e. as the sequential greedy
+ * repair of coloringMCMC_utils.cu:73-101 + coloringMCMC_main.cu:271-290).  Every rank repairs the violating vertices it OWNS in
+ * globally synchronised rounds; the CALLER moves the small lists between the ranks (multigpu.py: DistributedSweeper.tailcut), these
+ * calls never talk to another GPU.  Handles must be created with params.tailcut.  One pass:
+ *   begin   the owned vertices the reference would visit (a same-coloured neighbour with a larger id), from the violator list the
+ *           converging sweep emitted (first pass) or the previous pass left; `order` = colours by ascending class size
+ *   mark    the flagged vertices of ALL ranks (the ready test looks at neighbours on other ranks)
+ *   round   ready = no flagged neighbour with a smaller id is still pending; the ready owned vertices take the first colour of
+ *           `order` no neighbour has; returns the (vertex, colour) pairs decided, how many owned vertices are still waiting, and
+ *           whether a vertex found every colour taken (`inexact`: it may now clash with a vertex outside the lists)
+ *   apply   (vertex, colour) pairs decided by OTHER ranks in this round
+ *   recount local counters of the repaired colouring over the owned list; the surviving violators become the next pass's list
+ *   end     global counters (summed by the caller) become the chain's; exact = 0 forces a full recount at the next status */
+int mcmcb200_tailcut_dist_begin(mcmcb200_handle * h, const uint32_t * order /* [nCol] */, uint32_t * outFlagged, uint32_t cap, uint32_t * count);
+int mcmcb200_tailcut_dist_mark(mcmcb200_handle * h, const uint32_t * ids, uint32_t count);
+int mcmcb200_tailcut_dist_round(mcmcb200_handle * h, uint32_t * outIds, uint32_t * outCols, uint32_t cap, uint32_t * processed, uint32_t * remaining,
+                                uint32_t * inexact);
+int mcmcb200_tailcut_dist_apply(mcmcb200_handle * h, const uint32_t * ids, const uint32_t * cols, uint32_t count);
+int mcmcb200_tailcut_dist_recount(mcmcb200_handle * h, uint64_t * directedLocal, uint64_t * violLocal, uint32_t * nextFlagged);
+int mcmcb200_tailcut_dist_end(mcmcb200_handle * h, uint64_t directedGlobal, uint64_t violGlobal, uint32_t exact);
+
 /* Replay mode (parity tests): sweep k (k = 0,1,...) draws u[k*n + v] for vertex v instead of Philox.
  * sweeps == 0 or u == NULL returns to Philox. */
 int mcmcb200_set_tape(mcmcb200_handle * h, const float * u, uint32_t sweeps);

@@ -229,6 +229,38 @@ class Chain:
         capi.check(self.L.mcmcb200_tailcut(self.h, max_rounds, C.byref(r)), "mcmcb200_tailcut")
         return r.value
 
+    # ---- distributed tail cutting (mcmcb200_tailcut_dist_*): one rank's part; multigpu.DistributedSweeper.tailcut drives it ----
+    def tc_begin(self, order, cap=1 << 22):
+        o = np.ascontiguousarray(order, np.uint32)
+        out = np.empty(cap, np.uint32)
+        cnt = C.c_uint32()
+        capi.check(self.L.mcmcb200_tailcut_dist_begin(self.h, o.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt)),
+                   "mcmcb200_tailcut_dist_begin")
+        return out[:cnt.value].copy()
+
+    def tc_mark(self, ids):
+        a = np.ascontiguousarray(ids, np.uint32)
+        capi.check(self.L.mcmcb200_tailcut_dist_mark(self.h, a.ctypes.data_as(C.c_void_p), len(a)), "mcmcb200_tailcut_dist_mark")
+
+    def tc_round(self, cap=1 << 22):
+        ids, cols = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        done, left, inexact = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        capi.check(self.L.mcmcb200_tailcut_dist_round(self.h, ids.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), cap,
+                                                      C.byref(done), C.byref(left), C.byref(inexact)), "mcmcb200_tailcut_dist_round")
+        return ids[:done.value].copy(), cols[:done.value].copy(), left.value, bool(inexact.value)
+
+    def tc_apply(self, ids, cols):
+        a, b = np.ascontiguousarray(ids, np.uint32), np.ascontiguousarray(cols, np.uint32)
+        capi.check(self.L.mcmcb200_tailcut_dist_apply(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), len(a)), "mcmcb200_tailcut_dist_apply")
+
+    def tc_recount(self):
+        d, v, nf = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        capi.check(self.L.mcmcb200_tailcut_dist_recount(self.h, C.byref(d), C.byref(v), C.byref(nf)), "mcmcb200_tailcut_dist_recount")
+        return d.value, v.value, nf.value
+
+    def tc_end(self, directed, viol, exact=True):
+        capi.check(self.L.mcmcb200_tailcut_dist_end(self.h, int(directed), int(viol), 1 if exact else 0), "mcmcb200_tailcut_dist_end")
+
     def conflicts_of(self, colors):
         a, ap = capi._u32(colors)
         e, v = C.c_uint64(), C.c_uint64()

@@ -88,11 +88,11 @@ struct BlockedLayout {
 	unsigned long long * dbgTimes = nullptr;
 	uint32_t  nbuf = 1;              // stage buffers per pass-B CTA: 2 = tile T+1 is copied in (TMA) while tile T is computed
 	size_t    smemA = 0, smemB = 0;
-	int       gridA = 0, gridB = 0, gridA0 = 0;
+	int       gridA = 0, gridB = 0;
 };
 
 struct BlockedArgs {
-	uint32_t P, TV, numTiles, stageCap, totalPadded;
+	uint32_t P, TV, numTiles, stageCap;
 	const uint16_t * srcLocal;
 	void * ecol;
 	const uint16_t * gidx;
@@ -103,10 +103,13 @@ struct BlockedArgs {
 	const uint32_t * tileBase;
 	const uint32_t * items;
 	uint32_t numItems, numParts, nbuf;
-	uint32_t itemBegin, itemEnd, itemCounter;   // this launch of pass A hands out items [itemBegin, itemEnd) through sync[itemCounter]
 	const uint8_t * tilePart;
 	unsigned long long * dbgTimes;   // (MCMCB200_TIMING builds only) [0] A first start [1] A last end [2] B first start [3] B last end [4] B wait ns
 	uint32_t * sync;
+#if MCMCB200_BOUNDS_CHECK
+	uint32_t totalPadded;            // entries of srcLocal / ecol.  (Only in the checking build: pass B sits right at its 64-register cap and
+	                                 //  ptxas starts spilling when this struct grows.)
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -340,10 +343,10 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	if (MCMCB200_TIMING && tid == 0) atomicMin(bl.dbgTimes + 0, global_ns());
 	for (;;) {
 		__syncthreads();                                      // everybody is done with the previous item (and its chunk)
-		if (tid == 0) s_item = bl.itemBegin + atomicAdd(bl.sync + bl.itemCounter, 1u);
+		if (tid == 0) s_item = atomicAdd(bl.sync + 0, 1u);
 		__syncthreads();
 		const uint32_t it = s_item;
-		if (it >= bl.itemEnd) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 1, global_ns()); break; }
+		if (it >= bl.numItems) { if (MCMCB200_TIMING && tid == 0) atomicMax(bl.dbgTimes + 1, global_ns()); break; }
 		const uint32_t b = bl.items[3 * it], beg = bl.items[3 * it + 1], end = bl.items[3 * it + 2];
 		if (b != have && beg < end) {
 			// the chunk's 64 Ki colours: ONE bulk copy issued by one thread (TMA engine, no LDG/STS through the LSU pipe);

@@ -10,7 +10,11 @@
 #ifndef MCMCB200_BOUNDS_CHECK
 #define MCMCB200_BOUNDS_CHECK 0
 #endif
-#define MCMCB200_CHECK(cond, st) do { if (MCMCB200_BOUNDS_CHECK && !(cond)) *reinterpret_cast<volatile uint32_t *>(&(st)->errorFlag) = 4u; } while (0)
+#if MCMCB200_BOUNDS_CHECK
+#define MCMCB200_CHECK(cond, st) do { if (!(cond)) *reinterpret_cast<volatile uint32_t *>(&(st)->errorFlag) = 4u; } while (0)
+#else
+#define MCMCB200_CHECK(cond, st) ((void)0)
+#endif
 
 namespace mcmcb200 {
 

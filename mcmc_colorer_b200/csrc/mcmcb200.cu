@@ -85,6 +85,9 @@ struct mcmcb200_handle {
 	uint32_t * d_violCount = nullptr; uint32_t violCap = 0;
 	uint8_t * d_pending = nullptr;         // tail cutting: per-vertex flags (all zero between calls)
 	uint32_t * d_flist = nullptr, * d_tcResume = nullptr;
+	// distributed repair (mcmcb200_tailcut_dist_*): colour order, ready flags, hub rows of a round, (id, colour) pairs in and out
+	uint32_t * d_tcOrder = nullptr, * d_tcHeavy = nullptr, * d_tcIo = nullptr, * d_tcCounters = nullptr; uint8_t * d_tcReady = nullptr;
+	uint32_t tcIoCap = 0, tcFlagged = 0, tcListCount = 0; int tcSrc = 0; bool tcActive = false;
 	TailcutCounters * d_tcCnt = nullptr;
 	unsigned long long * d_xchg = nullptr; // this rank's counter-exchange block (sweep_kernel.cuh: cross_rank_reduce)
 	unsigned long long * peerXchg[kMaxPeers] = {};
@@ -106,8 +109,8 @@ template <int W, typename ColT>
 cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 	if (h->bl.valid) {
 		// source-blocked path: pass A (gather through shared memory) + pass B (tile sweep); two launches per sweep
-		BlockedArgs b = make_blocked_args(h->bl);
-		const size_t syncBytes = sizeof(uint32_t) * (3 + (size_t)h->bl.numParts);
+		const BlockedArgs b = make_blocked_args(h->bl);
+		const size_t syncBytes = sizeof(uint32_t) * (2 + (size_t)h->bl.numParts);
 		cudaStream_t sA = h->stream;
 		cudaError_t e = cudaSuccess;
 		if (h->overlap) {
@@ -123,21 +126,8 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 #endif
 		if (e == cudaSuccess && h->overlap) e = cudaEventRecord(h->evReset, sA);   // B may start as soon as the counters are clean
 		if (e != cudaSuccess) return e;
-#ifndef MCMCB200_SPLIT_A
-#define MCMCB200_SPLIT_A 0
-#endif
-		if (MCMCB200_SPLIT_A && h->overlap && h->bl.numParts >= 2u && h->bl.gridA0 > h->bl.gridA) {
-			// the first part at full occupancy (pass B cannot start before it is complete anyway: its CTAs move in as these retire),
-			// the rest with the one CTA per SM that fits next to pass B
-			BlockedArgs b0 = b;
-			b0.itemBegin = 0; b0.itemEnd = h->bl.P; b0.itemCounter = 0;
-			blocked_gather_kernel<ColT><<<h->bl.gridA0, kThreadsA, h->bl.smemA, sA>>>(a, b0);
-			h->launches++;
-			if ((e = cudaGetLastError()) != cudaSuccess) return e;
-			BlockedArgs b1 = b;
-			b1.itemBegin = h->bl.P; b1.itemEnd = h->bl.numItems; b1.itemCounter = 2u + h->bl.numParts;
-			blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b1);
-		} else
+		// (measured and dropped: the first part as a separate launch at full occupancy, the rest co-resident with pass B --
+		//  config 3 3.64 vs 3.62 ms, an 8-GPU-sized partition 0.544 vs 0.551 ms)
 		blocked_gather_kernel<ColT><<<h->bl.gridA, kThreadsA, h->bl.smemA, sA>>>(a, b);
 		h->launches++;
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;    // (pass B must not be launched without its producer)
@@ -205,7 +195,6 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	h->overlap = aFit >= 1 && !(h->p.flags & MCMCB200_FLAG_NO_OVERLAP);
 	if (h->overlap) {
 		L.gridA = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.numItems, (uint32_t)(std::min<long>(aFit, oa) * h->smCount)));
-		L.gridA0 = (int)std::max<uint32_t>(1u, std::min<uint32_t>(L.P, (uint32_t)(oa * h->smCount)));
 		if (!h->streamA) e = cudaStreamCreateWithFlags(&h->streamA, cudaStreamNonBlocking);
 		if (e == cudaSuccess && !h->evFork) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
 		if (e == cudaSuccess && !h->evReset) e = cudaEventCreateWithFlags(&h->evReset, cudaEventDisableTiming);
@@ -413,8 +402,9 @@ int alloc_chain_state(mcmcb200_handle * h) {
 	CU(cudaMalloc(&h->d_hist[1], sizeof(unsigned long long) * nCol));
 	CU(cudaMalloc(&h->d_history, sizeof(unsigned long long) * 2 * h->historyCap));
 	CU(cudaMalloc(&h->d_countOut, sizeof(unsigned long long) * 2));
-	if (h->p.tailcut && h->vBegin == 0 && h->vEnd == h->nGlobal) {
-		// room for the violators of a colouring up to 32 z away from the threshold (sweep_kernel.cuh: emitThreshold)
+	if (h->p.tailcut) {
+		// room for the violators of a colouring up to 32 z away from the threshold (sweep_kernel.cuh: emitThreshold); a partition
+		// lists the violators it owns (distributed repair: mcmcb200_tailcut_dist_*)
 		h->violCap = (uint32_t)std::min<uint64_t>(h->nGlobal, 32ull * h->z + 4096ull);
 		for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_violList[i], sizeof(uint32_t) * (size_t)h->violCap));
 		CU(cudaMalloc(&h->d_flist, sizeof(uint32_t) * (size_t)h->violCap));
@@ -794,6 +784,7 @@ void mcmcb200_destroy(mcmcb200_handle * h) {
 	mcmcb200_ipc_detach(h);
 	cudaFree(h->d_xchg);
 	cudaFree(h->d_violList[0]); cudaFree(h->d_violList[1]); cudaFree(h->d_violCount); cudaFree(h->d_pending); cudaFree(h->d_flist); cudaFree(h->d_tcResume); cudaFree(h->d_tcCnt);
+	cudaFree(h->d_tcOrder); cudaFree(h->d_tcHeavy); cudaFree(h->d_tcIo); cudaFree(h->d_tcCounters); cudaFree(h->d_tcReady);
 	if (h->h_pinned) cudaFreeHost(h->h_pinned);
 	if (h->streamA) { cudaStreamSynchronize(h->streamA); cudaStreamDestroy(h->streamA); }
 	if (h->evFork) cudaEventDestroy(h->evFork);
@@ -1148,6 +1139,184 @@ int mcmcb200_tailcut(mcmcb200_handle * h, uint32_t maxRounds, uint32_t * rounds)
 	CU(cudaMemcpyAsync(&h->d_state->convergedAt, &notConv, sizeof(notConv), cudaMemcpyHostToDevice, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	if (rounds) *rounds = used;
+	return MCMCB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Distributed tail cutting: the repair of a multi-GPU chain (the reference is single-GPU; same sequential-greedy result as
+// mcmcb200_tailcut / coloringMCMC_utils.cu:73-101).  Every rank repairs the violators it OWNS, in globally synchronised rounds:
+// a flagged vertex is ready when no flagged neighbour with a smaller id -- on any rank -- is still pending, ready vertices are
+// pairwise non-adjacent, and after each round the ranks tell each other the (vertex, colour) pairs they decided.  The caller
+// (multigpu.py DistributedSweeper.tailcut) moves the small lists between the ranks; nothing here talks to another GPU.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+int tc_dist_ready(mcmcb200_handle * h, uint32_t ioCap) {
+	if (!h->d_violList[0]) return MCMCB200_ESTATE;                // handle was not created with params.tailcut
+	if (!h->d_tcOrder) CU(cudaMalloc(&h->d_tcOrder, sizeof(uint32_t) * h->p.nCol));
+	if (!h->d_tcHeavy) CU(cudaMalloc(&h->d_tcHeavy, sizeof(uint32_t) * ((size_t)h->violCap + 1)));
+	if (!h->d_tcReady) CU(cudaMalloc(&h->d_tcReady, std::max<uint32_t>(h->violCap, 1)));
+	if (!h->d_tcCounters) CU(cudaMalloc(&h->d_tcCounters, sizeof(uint32_t) * 4));
+	if (h->tcIoCap < ioCap) {
+		cudaFree(h->d_tcIo); h->d_tcIo = nullptr; h->tcIoCap = 0;
+		CU(cudaMalloc(&h->d_tcIo, sizeof(uint32_t) * 2 * (size_t)ioCap));
+		h->tcIoCap = ioCap;
+	}
+	return MCMCB200_OK;
+}
+// rowptr indexed by GLOBAL vertex id (the repair kernels address rows by the ids in the lists)
+const uint32_t * tc_rowptr_global(const mcmcb200_handle * h) {
+	return reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(h->d_rowptr) - sizeof(uint32_t) * (uintptr_t)h->vBegin);
+}
+} // namespace
+
+int mcmcb200_tailcut_dist_begin(mcmcb200_handle * h, const uint32_t * order, uint32_t * outFlagged, uint32_t cap, uint32_t * count) {
+	if (!h || !order || !outFlagged || !count) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	int rc = tc_dist_ready(h, std::max<uint32_t>(h->violCap, 1)); if (rc) return rc;
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	if (!h->tcActive) {                                           // first pass: the list the converging sweep emitted
+		if (s.violListSweep != s.sweep || s.violListCount > h->violCap) return MCMCB200_ESTATE;
+		h->tcSrc = 0; h->tcListCount = s.violListCount; h->tcActive = true;
+	}
+	CU(cudaMemcpyAsync(h->d_tcOrder, order, sizeof(uint32_t) * h->p.nCol, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->d_tcCnt, 0, sizeof(TailcutCounters), h->stream));
+	void * cur = h->d_colors[s.sweep & 1];
+	const uint32_t lb = (uint32_t)(((uint64_t)h->tcListCount * 32u + 255u) / 256u);
+	if (h->tcListCount) {
+		if (h->colBytes == 1) tc_filter_kernel<uint8_t><<<lb, 256, 0, h->stream>>>(tc_rowptr_global(h), h->d_neighs, (const uint8_t *)cur, h->d_violList[h->tcSrc], h->tcListCount, h->d_pending, h->d_flist, h->d_tcCnt);
+		else tc_filter_kernel<uint16_t><<<lb, 256, 0, h->stream>>>(tc_rowptr_global(h), h->d_neighs, (const uint16_t *)cur, h->d_violList[h->tcSrc], h->tcListCount, h->d_pending, h->d_flist, h->d_tcCnt);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	TailcutCounters c{};
+	CU(cudaMemcpyAsync(&c, h->d_tcCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	h->tcFlagged = c.flagged;
+	if (c.flagged > cap) return MCMCB200_EINVAL;
+	CU(cudaMemcpy(outFlagged, h->d_flist, sizeof(uint32_t) * (size_t)c.flagged, cudaMemcpyDeviceToHost));
+	*count = c.flagged;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut_dist_mark(mcmcb200_handle * h, const uint32_t * ids, uint32_t count) {
+	if (!h || (count && !ids)) return MCMCB200_EINVAL;
+	if (!h->tcActive) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	if (!count) return MCMCB200_OK;
+	int rc = tc_dist_ready(h, std::max<uint32_t>(count, h->tcIoCap)); if (rc) return rc;
+	CU(cudaMemcpyAsync(h->d_tcIo, ids, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+	tc_mark_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_tcIo, count, h->d_pending);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut_dist_round(mcmcb200_handle * h, uint32_t * outIds, uint32_t * outCols, uint32_t cap, uint32_t * processed, uint32_t * remaining,
+                                uint32_t * inexact) {
+	if (!h || !outIds || !outCols || !processed || !remaining || !inexact) return MCMCB200_EINVAL;
+	if (!h->tcActive) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	*processed = 0; *remaining = 0; *inexact = 0;
+	if (h->tcFlagged == 0) return MCMCB200_OK;
+	int rc = tc_dist_ready(h, std::max<uint32_t>(h->tcFlagged, h->tcIoCap)); if (rc) return rc;
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	void * cur = h->d_colors[s.sweep & 1];
+	unsigned long long * hist = h->d_hist[s.sweep & 1];
+	const uint32_t n = h->tcFlagged, nCol = h->p.nCol;
+	const uint32_t lb = (uint32_t)(((uint64_t)n * 32u + 255u) / 256u);
+	uint32_t * d_out = h->d_tcIo, * d_outCols = h->d_tcIo + h->tcIoCap;
+	CU(cudaMemsetAsync(h->d_tcCounters, 0, 4 * sizeof(uint32_t), h->stream));      // [0] remaining [1] changed [2] processed [3] inexact
+	CU(cudaMemsetAsync(h->d_tcHeavy, 0, sizeof(uint32_t), h->stream));
+	const uint32_t * rp = tc_rowptr_global(h);
+	tailcut_ready_kernel<<<lb, 256, 0, h->stream>>>(rp, h->d_neighs, h->d_pending, h->d_flist, n, h->d_tcReady);
+	const size_t smem = tc_smem_bytes(nCol);
+	if (h->colBytes == 1) {
+		tailcut_apply_kernel<uint8_t><<<lb, 256, 0, h->stream>>>(rp, h->d_neighs, nCol, (uint8_t *)cur, h->d_pending, h->d_flist, n, h->d_tcReady, h->d_tcOrder, hist,
+		                                                          h->d_tcCounters + 0, h->d_tcHeavy, h->d_tcCounters + 1, d_out, d_outCols, h->d_tcCounters + 2, h->d_tcCounters + 3);
+		tailcut_apply_heavy_kernel<uint8_t><<<64, kTcThreads, smem, h->stream>>>(rp, h->d_neighs, nCol, (uint8_t *)cur, h->d_pending, h->d_tcOrder, hist, h->d_tcHeavy,
+		                                                                         h->d_tcCounters + 1, d_out, d_outCols, h->d_tcCounters + 2, h->d_tcCounters + 3);
+	} else {
+		tailcut_apply_kernel<uint16_t><<<lb, 256, 0, h->stream>>>(rp, h->d_neighs, nCol, (uint16_t *)cur, h->d_pending, h->d_flist, n, h->d_tcReady, h->d_tcOrder, hist,
+		                                                           h->d_tcCounters + 0, h->d_tcHeavy, h->d_tcCounters + 1, d_out, d_outCols, h->d_tcCounters + 2, h->d_tcCounters + 3);
+		tailcut_apply_heavy_kernel<uint16_t><<<64, kTcThreads, smem, h->stream>>>(rp, h->d_neighs, nCol, (uint16_t *)cur, h->d_pending, h->d_tcOrder, hist, h->d_tcHeavy,
+		                                                                          h->d_tcCounters + 1, d_out, d_outCols, h->d_tcCounters + 2, h->d_tcCounters + 3);
+	}
+	h->launches += 3;
+	CU(cudaGetLastError());
+	uint32_t cnt[4];
+	CU(cudaMemcpyAsync(cnt, h->d_tcCounters, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	if (cnt[2] > cap) return MCMCB200_EINVAL;
+	CU(cudaMemcpy(outIds, d_out, sizeof(uint32_t) * (size_t)cnt[2], cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(outCols, d_outCols, sizeof(uint32_t) * (size_t)cnt[2], cudaMemcpyDeviceToHost));
+	*processed = cnt[2]; *remaining = cnt[0]; *inexact = cnt[3];
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut_dist_apply(mcmcb200_handle * h, const uint32_t * ids, const uint32_t * cols, uint32_t count) {
+	if (!h || (count && (!ids || !cols))) return MCMCB200_EINVAL;
+	if (!h->tcActive) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	if (!count) return MCMCB200_OK;
+	for (uint32_t i = 0; i < count; ++i) if (ids[i] >= h->nGlobal || cols[i] >= h->p.nCol) return MCMCB200_EINVAL;
+	int rc = tc_dist_ready(h, std::max<uint32_t>(count, h->tcIoCap)); if (rc) return rc;
+	DevState s;
+	rc = read_state(h, &s); if (rc) return rc;
+	CU(cudaMemcpyAsync(h->d_tcIo, ids, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(h->d_tcIo + h->tcIoCap, cols, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+	if (h->colBytes == 1) tc_remote_kernel<uint8_t><<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_tcIo, h->d_tcIo + h->tcIoCap, count, (uint8_t *)h->d_colors[s.sweep & 1], h->d_pending, h->d_hist[s.sweep & 1]);
+	else tc_remote_kernel<uint16_t><<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_tcIo, h->d_tcIo + h->tcIoCap, count, (uint16_t *)h->d_colors[s.sweep & 1], h->d_pending, h->d_hist[s.sweep & 1]);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut_dist_recount(mcmcb200_handle * h, uint64_t * directedLocal, uint64_t * violLocal, uint32_t * nextFlagged) {
+	if (!h || !directedLocal || !violLocal || !nextFlagged) return MCMCB200_EINVAL;
+	if (!h->tcActive) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	void * cur = h->d_colors[s.sweep & 1];
+	CU(cudaMemsetAsync(h->d_tcCnt, 0, sizeof(TailcutCounters), h->stream));
+	if (h->tcListCount) {
+		const uint32_t lb = (uint32_t)(((uint64_t)h->tcListCount * 32u + 255u) / 256u);
+		if (h->colBytes == 1) tc_recount_kernel<uint8_t><<<lb, 256, 0, h->stream>>>(tc_rowptr_global(h), h->d_neighs, (const uint8_t *)cur, h->d_violList[h->tcSrc], h->tcListCount, h->d_pending, h->d_violList[h->tcSrc ^ 1], h->d_tcCnt);
+		else tc_recount_kernel<uint16_t><<<lb, 256, 0, h->stream>>>(tc_rowptr_global(h), h->d_neighs, (const uint16_t *)cur, h->d_violList[h->tcSrc], h->tcListCount, h->d_pending, h->d_violList[h->tcSrc ^ 1], h->d_tcCnt);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	TailcutCounters c{};
+	CU(cudaMemcpyAsync(&c, h->d_tcCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	h->tcSrc ^= 1; h->tcListCount = c.nextCount;
+	*directedLocal = c.directed; *violLocal = c.viol; *nextFlagged = c.nextFlagged;
+	return MCMCB200_OK;
+}
+
+int mcmcb200_tailcut_dist_end(mcmcb200_handle * h, uint64_t directedGlobal, uint64_t violGlobal, uint32_t exact) {
+	if (!h) return MCMCB200_EINVAL;
+	if (!h->tcActive) return MCMCB200_ESTATE;
+	CU(cudaSetDevice(h->device));
+	h->tcActive = false;
+	if (h->tcSrc == 1) CU(cudaMemcpyAsync(h->d_violList[0], h->d_violList[1], sizeof(uint32_t) * (size_t)h->tcListCount, cudaMemcpyDeviceToDevice, h->stream));
+	h->tcSrc = 0;
+	if (exact) {
+		tc_commit_global_kernel<<<1, 1, 0, h->stream>>>(h->d_state, directedGlobal, violGlobal, h->tcListCount);
+		h->launches++;
+		CU(cudaGetLastError());
+	} else {                                                       // a repaired vertex found every colour taken: recount with a full pass at the next status
+		const uint32_t stale = 0xffffffffu; const int32_t notConv = -1;
+		CU(cudaMemcpyAsync(&h->d_state->countsSweep, &stale, sizeof(stale), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(&h->d_state->convergedAt, &notConv, sizeof(notConv), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(&h->d_state->violListSweep, &stale, sizeof(stale), cudaMemcpyHostToDevice, h->stream));
+	}
+	CU(cudaStreamSynchronize(h->stream));
 	return MCMCB200_OK;
 }
 

@@ -207,7 +207,11 @@ __device__ __forceinline__ void finalize_sweep_device(const SweepArgs & a) {
 	if (threadIdx.x == 0) { st->ticket = 0; st->tileCounter = 0; }
 }
 
-__global__ void finalize_kernel(SweepArgs a) { finalize_sweep_device(a); }
+// (a chain that already stopped at its threshold: the sweep launch before this was a no-op and so is its finalize)
+__global__ void finalize_kernel(SweepArgs a) {
+	if (!a.countOnly && a.st->convergedAt >= 0) return;
+	finalize_sweep_device(a);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Sequential CDF walks.  The reference selects the first colour whose float32 running sum exceeds the draw

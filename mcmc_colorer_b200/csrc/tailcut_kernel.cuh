@@ -104,7 +104,8 @@ template <typename ColT>
 __global__ void tailcut_apply_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol,
                                      ColT * colors, uint8_t * pending, const uint32_t * __restrict__ list, uint32_t listCount,
                                      const uint8_t * __restrict__ ready, const uint32_t * __restrict__ order,
-                                     unsigned long long * hist, uint32_t * remaining, uint32_t * heavy, uint32_t * changed) {
+                                     unsigned long long * hist, uint32_t * remaining, uint32_t * heavy, uint32_t * changed,
+                                     uint32_t * outIds = nullptr, uint32_t * outCols = nullptr, uint32_t * outCount = nullptr, uint32_t * inexactFlag = nullptr) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= listCount) return;
@@ -121,13 +122,16 @@ __global__ void tailcut_apply_kernel(const uint32_t * __restrict__ rowptr, const
 		colors[v] = (ColT)nodeCol;                                           // :97
 		pending[v] = 0;
 		if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(changed, 1u); }
+		if (outIds) { const uint32_t k = atomicAdd(outCount, 1u); outIds[k] = v; outCols[k] = nodeCol; }   // (distributed repair: told to the other ranks)
+		if (inexact && inexactFlag) *inexactFlag = 1u;
 	}
 }
 
 template <typename ColT>
 __global__ void __launch_bounds__(kTcThreads)
 tailcut_apply_heavy_kernel(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ neighs, uint32_t nCol, ColT * colors, uint8_t * pending,
-                           const uint32_t * __restrict__ order, unsigned long long * hist, const uint32_t * heavy, uint32_t * changed) {
+                           const uint32_t * __restrict__ order, unsigned long long * hist, const uint32_t * heavy, uint32_t * changed,
+                           uint32_t * outIds = nullptr, uint32_t * outCols = nullptr, uint32_t * outCount = nullptr, uint32_t * inexactFlag = nullptr) {
 	extern __shared__ uint32_t tc_smem[];
 	uint32_t * bm = tc_smem + 4;
 	const uint32_t cnt = heavy[0];
@@ -140,6 +144,8 @@ tailcut_apply_heavy_kernel(const uint32_t * __restrict__ rowptr, const uint32_t 
 			colors[v] = (ColT)nodeCol;
 			pending[v] = 0;
 			if (nodeCol != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + nodeCol, 1ull); atomicAdd(changed, 1u); }
+			if (outIds) { const uint32_t k = atomicAdd(outCount, 1u); outIds[k] = v; outCols[k] = nodeCol; }
+			if (inexact && inexactFlag) *inexactFlag = 1u;
 		}
 		__syncthreads();
 	}
@@ -326,6 +332,27 @@ __global__ void tc_recount_kernel(const uint32_t * __restrict__ rowptr, const ui
 		nextList[atomicAdd(&cnt->nextCount, 1u)] = v;
 		if (flag) atomicAdd(&cnt->nextFlagged, 1u);
 	}
+}
+
+// distributed repair (multi-GPU): flags of the vertices any rank is going to visit; colours chosen by another rank
+__global__ void tc_mark_kernel(const uint32_t * __restrict__ ids, uint32_t count, uint8_t * pending) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) pending[ids[i]] = 1;
+}
+template <typename ColT>
+__global__ void tc_remote_kernel(const uint32_t * __restrict__ ids, const uint32_t * __restrict__ cols, uint32_t count, ColT * colors, uint8_t * pending,
+                                 unsigned long long * hist) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const uint32_t v = ids[i], c = cols[i], old = colors[v];
+	colors[v] = (ColT)c;
+	pending[v] = 0;
+	if (c != old) { atomicAdd(hist + old, ~0ull); atomicAdd(hist + c, 1ull); }
+}
+__global__ void tc_commit_global_kernel(DevState * st, unsigned long long directed, unsigned long long viol, uint32_t listCount) {
+	st->lastDirected = directed; st->lastViol = viol; st->countsSweep = st->sweep;
+	st->convergedAt = -1;
+	st->violListSweep = st->sweep; st->violListCount = listCount;
 }
 
 // the repaired colouring's counters become the chain's (no full recount needed); the surviving violators are its list

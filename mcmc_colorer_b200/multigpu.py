@@ -65,10 +65,12 @@ def _view(ptr, nelem, typestr, device):
 class GpuEngine:
     """The B200 engine of one rank: a partitioned mcmcb200 handle plus torch views of its exchange buffers."""
 
-    def __init__(self, d_rowptr_local, d_neighs_local, nnz_local, n_global, v_begin, v_end, params, device_index, extra_flags=0, **tuning):
+    def __init__(self, d_rowptr_local, d_neighs_local, nnz_local, n_global, v_begin, v_end, params, device_index, extra_flags=0, early_stop=False, **tuning):
+        """early_stop: let the chain stop on the device at its threshold (the --tailcut protocol: params.tailcut, then DistributedSweeper.tailcut);
+        by default the sweeps keep advancing (benchmarks, trajectory checks)."""
         import torch
         self.device = f"cuda:{device_index}"
-        flags = capi.FLAG_NO_FUSED_FINALIZE | capi.FLAG_NO_EARLY_STOP | extra_flags
+        flags = capi.FLAG_NO_FUSED_FINALIZE | (0 if early_stop else capi.FLAG_NO_EARLY_STOP) | extra_flags
         self.keep = (d_rowptr_local, d_neighs_local)
         self.chain = Chain(params=params, device=device_index, flags=flags, n_global=n_global, v_begin=v_begin, v_end=v_end,
                            device_csr=(d_rowptr_local.data_ptr(), d_neighs_local.data_ptr(), nnz_local), **tuning)
@@ -115,6 +117,9 @@ class GpuEngine:
             p1, _, _ = self.chain.device_view(capi.VIEW_COLORS_NEXT)
             self.elem_bytes = eb                      # colours are exchanged as raw bytes (u8, or u16 little endian)
             self._bufs = [_view(p0, nbytes, "|u1", self.device), _view(p1, nbytes, "|u1", self.device)]
+            self._ptrs = (p0, p1) if (self.t & 1) == 0 else (p1, p0)        # physical buffers 0 / 1 (colouring t lives in buffer t & 1)
+            if self.t & 1:
+                self._bufs.reverse()
             pc, cbytes, _ = self.chain.device_view(capi.VIEW_COUNTERS)
             self._counters = _view(pc, cbytes // 8, "<i8", self.device)
         return self._bufs
@@ -167,8 +172,41 @@ class GpuEngine:
     def status(self):
         return self.chain.status()
 
+    # distributed tail cutting: this rank's part (Chain.tc_*  ->  mcmcb200_tailcut_dist_*)
+    def class_sizes(self):
+        return self.chain.class_sizes()
+
+    def tc_begin(self, order):
+        return self.chain.tc_begin(order)
+
+    def tc_mark(self, ids):
+        self.chain.tc_mark(ids)
+
+    def tc_round(self):
+        return self.chain.tc_round()
+
+    def tc_apply(self, ids, cols):
+        self.chain.tc_apply(ids, cols)
+
+    def tc_recount(self):
+        return self.chain.tc_recount()
+
+    def tc_end(self, directed, viol, exact):
+        self.chain.tc_end(directed, viol, exact)
+
+    def sync_t(self):
+        """A chain created without FLAG_NO_EARLY_STOP stops advancing on the device once it is at its threshold, while this object
+        counts every sweep it launched: re-align the buffer parity with the device (mcmcb200_device_view only reads the state;
+        mcmcb200_status would start a counting pass, which is a collective in this driver)."""
+        self._views()
+        cur, _, _ = self.chain.device_view(capi.VIEW_COLORS_CUR)
+        par = 0 if cur == self._ptrs[0] else 1
+        if (self.t & 1) != par:
+            self.t -= 1
+
     def colors_host(self, which="cur"):
         self.chain.synchronize()
+        self.sync_t()
         buf = self._views()[(self.t if which == "cur" else self.t + 1) & 1]
         raw = buf[: self.n * self.elem_bytes].cpu().numpy()
         return (raw if self.elem_bytes == 1 else raw.view("<u2")).astype(np.uint32)
@@ -224,6 +262,59 @@ class DistributedSweeper:
             self.e.local_sweep()
             self._exchange(colours=True)
             self.e.finalize(advanced=True)
+
+    def tailcut(self, max_passes=64):
+        """Tail cutting of the N-GPU chain (the reference's --tailcut repair, coloringMCMC_main.cu:271-290, is single-GPU): the same
+        sequential-greedy result, computed by the ranks together.  Per pass: every rank flags the violating vertices it owns that
+        the reference would visit; the flagged ids are exchanged (they are few: the chain stopped at <= z = max(50, n/2000)
+        violators); then rounds -- a flagged vertex is ready when no flagged neighbour with a smaller id, on any rank, is still
+        pending; ready vertices are pairwise non-adjacent, so all ranks repair theirs at once and tell each other the (vertex,
+        colour) pairs.  Returns the number of passes.  All small exchanges go through all_gather_object (host), nothing is large."""
+        import torch.distributed as dist
+        if hasattr(self.e, "sync_t"):
+            self.e.sync_t()
+        # colours in ascending class size, computed ONCE before the passes (coloringMCMC_main.cu:272-277); ties by colour index --
+        # identical on every rank (the class sizes are global)
+        order = np.argsort(np.asarray(self.e.class_sizes(), dtype=np.int64), kind="stable").astype(np.uint32)
+        passes = 0
+        while passes < max_passes:
+            mine = np.asarray(self.e.tc_begin(order), dtype=np.uint32)
+            table = [None] * self.world
+            dist.all_gather_object(table, mine, group=self.group)
+            total = int(sum(len(t) for t in table))
+            if total == 0:
+                d, v, _ = self.e.tc_recount()
+                tot = [None] * self.world
+                dist.all_gather_object(tot, (d, v), group=self.group)
+                self.e.tc_end(sum(t[0] for t in tot), sum(t[1] for t in tot), True)
+                return passes
+            passes += 1
+            self.e.tc_mark(np.concatenate(table))
+            inexact = False
+            while True:
+                ids, cols, left, inx = self.e.tc_round()
+                got = [None] * self.world
+                dist.all_gather_object(got, (ids, cols, left, inx), group=self.group)
+                for r, (ri, rc, rl, rx) in enumerate(got):
+                    inexact = inexact or rx
+                    if r != self.rank and len(ri):
+                        self.e.tc_apply(ri, rc)
+                if sum(g[2] for g in got) == 0:
+                    break
+            d, v, nf = self.e.tc_recount()
+            tot = [None] * self.world
+            dist.all_gather_object(tot, (d, v, nf), group=self.group)
+            gd, gv, gnf = (sum(t[i] for t in tot) for i in range(3))
+            # stop: nothing left to flag, a repaired vertex found every colour taken (vertices outside the lists may violate now:
+            # full recount at the next status), or no progress is possible
+            if inexact or gnf == 0 or gnf >= total:
+                self.e.tc_end(gd, gv, not inexact)
+                return passes
+        d, v, _ = self.e.tc_recount()
+        tot = [None] * self.world
+        dist.all_gather_object(tot, (d, v), group=self.group)
+        self.e.tc_end(sum(t[0] for t in tot), sum(t[1] for t in tot), True)
+        return passes
 
     def status(self):
         """Global counters of the current colouring (runs a distributed counting pass if they are stale)."""

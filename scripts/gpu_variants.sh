@@ -1,11 +1,15 @@
 #!/bin/bash
-# gpurun -- bash scripts/gpu_variants.sh lib:capBytes[:workload] ...   (prebuilt kernel variants under variants/, chosen via MCMCB200_LIB)
-mkdir -p gpurun_out
+# gpurun -- bash scripts/gpu_variants.sh <workload> lib[:bench args] ...   -- kernel-variant matrix: one `bench.py --quick` line per prebuilt
+# library (make -C mcmc_colorer_b200/csrc OUT=$PWD/variants/libX.so EXTRA=-DMCMCB200_...=...), chosen through MCMCB200_LIB.
+# Example: bash scripts/gpu_variants.sh c3 mcmc_colorer_b200/libmcmcb200.so variants/libKU10.so "variants/libKU10.so:--stage-cap-bytes 36864"
+W=${1:-c3}; shift
+mkdir -p gpurun_out; rm -f gpurun_out/variants.jsonl
 for spec in "$@"; do
-  IFS=: read lib cap wl <<< "$spec"; wl=${wl:-c3}
-  MCMCB200_LIB=$PWD/variants/lib_$lib.so MCMCB200_STAGE_CAP_BYTES=$cap timeout 300 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/var_$lib_$cap.err | python -c "
-import sys, json
-try:
-    d = json.loads(sys.stdin.readline()); print('[$spec] ms %.3f frac %.3f chain %.3f launches/sweep %d' % (d['ms_per_step'], d['roofline']['frac'], d['chain_ms_per_sweep'], d['roofline']['launches_per_sweep']))
-except Exception as e: print('[$spec] failed', e)"
+  lib=${spec%%:*}; extra=""; [ "$spec" != "$lib" ] && extra=${spec#*:}
+  MCMCB200_LIB=$PWD/$lib timeout 300 python bench.py --workload $W --quick --steps 5 --warmup 3 $extra >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
 done
+python - <<'PY'
+import json
+for l in open('gpurun_out/variants.jsonl'):
+    d=json.loads(l); print(d['lib'].split('/')[-1], d['workload'], d['tuning'], d['kernel_mode'], round(d['ms_per_step'],3), round(d['chain_ms_per_sweep'],3), round(d['create_ms']), round(d['frac'],3))
+PY

@@ -80,6 +80,42 @@ for n, deg, proposal, p2p, cap, by_nnz in [(50_001, 12, 0, False, 0, False), (50
     if not np.array_equal(back[: ve - vb], c2[vb:ve]):
         ok = False; print(f"rank {rank}: sliced download differs")
     eng.chain.close()
+# ---- distributed tail cutting: chain with params.tailcut stops on every rank at <= z violating vertices (global count), the
+#      ranks repair their own violators in synchronised rounds; == the oracle's chain + its sequential tail cut ----
+for n, deg, p2p, slack in [(300_000, 16, False, 14), (1_000_003, 16, True, 13)]:
+    cumul, neighs = er_graph_numpy(n, deg, seed=21)
+    nCol = int(np.diff(cumul.astype(np.int64)).max()) - slack       # a tight palette: the chain needs a few sweeps
+    z = max(50, n // 2000)
+    parts, chunk = partition(n, world)
+    vb, ve = parts[rank]
+    e0, e1 = int(cumul[vb]), int(cumul[ve])
+    rp = torch.from_numpy((cumul[vb:ve + 1].astype(np.int64) - e0).astype(np.int32)).to(dev)
+    nb = torch.zeros(e1 - e0 + 16, dtype=torch.int32, device=dev)
+    nb[: e1 - e0] = torch.from_numpy(neighs[e0:e1].astype(np.int32)).to(dev)
+    prm = ColoringMCMCParams(nCol=nCol, proposal=0, convergence=0, seed=5, tailcut=True)
+    eng = GpuEngine(rp, nb, e1 - e0, n, vb, ve, prm, lr, early_stop=True)       # the chain stops on the device at the threshold
+    if p2p:
+        eng.enable_p2p(rank, world)
+    sw = DistributedSweeper(eng, rank, world, chunk, parts=parts)
+    eng.init_colors(None)
+    c0 = P.init_colors(5, n, nCol)
+    want, sweeps, cnt, hit = P.run(cumul, neighs, nCol, 1e-8, c0, 5, 0, z=z)
+    for _ in range(sweeps + 3):                                     # sweeps past the threshold are no-ops on every rank
+        sw.sweep(1)
+    st = sw.status()
+    if st.sweep != sweeps or st.violatingVertices != cnt or not np.array_equal(eng.colors_host(), want):
+        ok = False; print(f"rank {rank}: tail-cut chain differs before the repair: sweep {st.sweep} vs {sweeps}, viol {st.violatingVertices} vs {cnt}")
+    fixed, _, left = P.tailcut(cumul, neighs, nCol, want)
+    passes = sw.tailcut(64)
+    st = sw.status()
+    got = eng.colors_host()
+    if not np.array_equal(got, fixed) or st.conflictEdges != left or st.violatingVertices != P.violation_count(cumul, neighs, fixed):
+        ok = False; print(f"rank {rank}: distributed tail cut differs: {np.flatnonzero(got != fixed)[:8]}, left {st.conflictEdges} vs {left}")
+    if not np.array_equal(eng.chain.class_sizes().astype(np.uint32), P.class_sizes(fixed, nCol)):
+        ok = False; print(f"rank {rank}: class sizes differ after the distributed tail cut")
+    if rank == 0:
+        print(f"n={n}: distributed tail cut after {sweeps} sweeps ({cnt} violating <= z={z}): {passes} pass(es), {left} conflicts left, fused={eng.p2p}")
+    eng.chain.close()
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 if rank == 0:

@@ -70,3 +70,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle", "").replace("oracle's", ""), os.path.join(dp, f)
+
+
+def test_hot_kernel_resource_budget():
+    """The overlapped blocked sweep relies on exact co-residency: two pass-B CTAs (384 threads, <= 64 registers, no spills) and one pass-A
+    CTA (256 threads, <= 64 registers) fill an SM's register file.  Pass B sits right at its cap -- growing its argument struct by four
+    words once made ptxas spill and cost 3.7 % on config 3 -- so the built library is checked (cuobjdump -res-usage, no GPU needed)."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mcmc_colorer_b200", "libmcmcb200.so")
+    out = subprocess.run([cuobjdump, "-res-usage", so], capture_output=True, text=True).stdout
+    res = {m.group(1): (int(m.group(2)), int(m.group(3))) for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)}
+    passB = {k: v for k, v in res.items() if "blocked_sweep_kernelILi1Eh" in k or "blocked_sweep_kernelILi2Eh" in k}
+    passA = {k: v for k, v in res.items() if "blocked_gather_kernel" in k}
+    assert passB and passA, sorted(res)[:5]
+    for k, (reg, stack) in passB.items():
+        assert reg <= 64 and stack == 0, (k, reg, stack)
+    for k, (reg, stack) in passA.items():
+        assert reg <= 64 and stack == 0, (k, reg, stack)

@@ -82,6 +82,59 @@ class OracleEngine:
             self.t += 1
         self._counters.zero_()
 
+    # ---- distributed tail cutting: the engine's part, in numpy (same contract as mcmcb200_tailcut_dist_*) ----
+    def class_sizes(self):
+        return np.bincount(self._cur(), minlength=self.nCol).astype(np.int64)
+
+    def _row(self, v):
+        return self.neighs[self.cumul[v]:self.cumul[v + 1]]
+
+    def tc_begin(self, order):
+        c = self._cur()
+        self.order = np.asarray(order, dtype=np.uint32)
+        self.flist = [v for v in range(self.vb, self.ve) if any(u > v and c[u] == c[v] for u in self._row(v))]
+        self.pend = set()
+        return np.array(self.flist, dtype=np.uint32)
+
+    def tc_mark(self, ids):
+        self.pend = set(int(i) for i in ids)
+
+    def tc_round(self):
+        import torch
+        c = self._cur()
+        ready = [v for v in self.flist if v in self.pend and not any(u < v and int(u) in self.pend for u in self._row(v))]
+        ids, cols, inexact = [], [], False
+        for v in ready:
+            occ = set(int(c[u]) for u in self._row(v))
+            col, j = int(c[v]), 0
+            while col in occ and j < self.nCol:                      # coloringMCMC_utils.cu:91-95
+                col = int(self.order[j]); j += 1
+            inexact = inexact or (j == self.nCol and col in occ)
+            ids.append(v); cols.append(col)
+        for v, col in zip(ids, cols):
+            self.bufs[self.t & 1][v] = col
+            self.pend.discard(v)
+        left = sum(1 for v in self.flist if v in self.pend)
+        return np.array(ids, dtype=np.uint32), np.array(cols, dtype=np.uint32), left, inexact
+
+    def tc_apply(self, ids, cols):
+        for v, col in zip(ids, cols):
+            self.bufs[self.t & 1][int(v)] = int(col)
+            self.pend.discard(int(v))
+
+    def tc_recount(self):
+        c = self._cur()
+        d = v_ = nf = 0
+        for v in range(self.vb, self.ve):
+            same = [u for u in self._row(v) if c[u] == c[v]]
+            d += len(same); v_ += 1 if same else 0; nf += 1 if any(u > v for u in same) else 0
+        return d, v_, nf
+
+    def tc_end(self, directed, viol, exact):
+        self.last = (int(directed) // 2, int(viol))
+        self.counts_sweep = self.t if exact else None
+        self.hist = self.class_sizes()
+
     def status(self):
         if self.counts_sweep != self.t:
             self._local_counts(self._cur())                                    # local counting pass, like the C ABI in split mode
@@ -167,3 +220,49 @@ def test_partition_properties():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             assert all(0 <= ve - vb <= chunk for vb, ve in parts)
+
+
+def _tc_worker(rank, world, port_file, result_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    from mcmc_colorer_b200.multigpu import DistributedSweeper, partition
+    from oracle.pyoracle import Port
+    dist.init_process_group("gloo", init_method=f"file://{port_file}", rank=rank, world_size=world)
+    P = Port()
+    n = 2500
+    cumul, neighs = er_graph_numpy(n, 10, seed=9)
+    nCol = int(np.diff(cumul.astype(np.int64)).max()) - 6            # tight palette: conflicts are left after a few sweeps
+    parts, chunk = partition(n, world, align=256)
+    vb, ve = parts[rank]
+    eng = OracleEngine(P, cumul, neighs, vb, ve, chunk, world, nCol, seed=3, proposal=0)
+    sw = DistributedSweeper(eng, rank, world, chunk)
+    eng.init_colors(None)
+    sw.sweep(2)
+    before = eng.bufs[eng.t & 1][:n].numpy().astype(np.uint32).copy()
+    passes = sw.tailcut(64)
+    st = sw.status()
+    after = eng.bufs[eng.t & 1][:n].numpy().astype(np.uint32)
+    np.savez(os.path.join(result_dir, f"tc{rank}.npz"), before=before, after=after, counts=np.array([st.conflictEdges, st.violatingVertices, passes]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tailcut_matches_sequential_reference_semantics(port, tmp_path):
+    """DistributedSweeper.tailcut over two ranks == the sequential greedy repair (oracle port of coloringMCMC_utils.cu:73-101 +
+    coloringMCMC_main.cu:271-290) on the same colouring: colours, what is left, and identical replicas on both ranks."""
+    import torch.multiprocessing as mp
+    from mcmc_colorer_b200.graphgen import er_graph_numpy
+    world = 2
+    port_file = str(tmp_path / "rdzv_tc")
+    mp.spawn(_tc_worker, args=(world, port_file, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f"tc{r}.npz") for r in range(world))
+    assert np.array_equal(r0["before"], r1["before"]) and np.array_equal(r0["after"], r1["after"])
+    n = 2500
+    cumul, neighs = er_graph_numpy(n, 10, seed=9)
+    nCol = int(np.diff(cumul.astype(np.int64)).max()) - 6
+    assert port.conflict_edges(cumul, neighs, r0["before"]) > 0
+    want, rounds, left = port.tailcut(cumul, neighs, nCol, r0["before"])
+    assert np.array_equal(r0["after"], want)
+    assert int(r0["counts"][0]) == left == port.conflict_edges(cumul, neighs, want)
+    assert int(r0["counts"][1]) == port.violation_count(cumul, neighs, want)
