@@ -513,6 +513,29 @@ def test_large_graph_default_path_vs_oracle(mc, port, big_graph, tuning):
     ch.close()
 
 
+def test_expected_sweeps_keeps_the_layout_free_kernels(mc, port, big_graph):
+    """mcmcb200_params.expectedSweeps: a handle that will run only a few sweeps does not build the blocked layout (0.13 ns per edge,
+    amortised over ~30 sweeps) -- same colours from the degree-binned direct kernel, a fraction of the create time."""
+    import time
+    n, nnz, max_deg, rowptr, neighs, cumul_h, neighs_h = big_graph
+    prm = mc.ColoringMCMCParams(nCol=max_deg, proposal=mc.PROPOSAL_UNIFORM, convergence=mc.CONVERGE_VERTICES, seed=31)
+    out = {}
+    for es in (8, 0, 64):
+        t0 = time.perf_counter()
+        ch = mc.Chain(params=prm, device=0, flags=mc.FLAG_NO_EARLY_STOP, n_global=n, v_begin=0, v_end=n,
+                      device_csr=(rowptr.data_ptr(), neighs.data_ptr(), nnz), expected_sweeps=es)
+        ch.synchronize()
+        dt = time.perf_counter() - t0
+        mode = ch.kernel_mode()
+        ch.init_colors(None)
+        ch.sweep(2)
+        out[es] = (mode, dt, sha(ch.get_colors()))
+        ch.close()
+    assert out[8][0] == "direct-binned" and out[0][0].startswith("blocked") and out[64][0].startswith("blocked")
+    assert out[8][2] == out[0][2] == out[64][2]
+    assert out[8][1] < out[0][1]
+
+
 # ------------------------------------------------------------------------------------------------------------
 # north-star check 3 as a test: free-running chains vs the reference's distribution over seeds (BASELINE config 5)
 # ------------------------------------------------------------------------------------------------------------
