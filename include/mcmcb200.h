@@ -73,8 +73,8 @@ typedef struct mcmcb200_params {
 	uint32_t itemBits;        /* log2 of the entries of one pass-A work item */
 	uint32_t stageBuffers;    /* 1 or 2 stage buffers per pass-B CTA (2: the next tile is copied in while this one is computed) */
 	uint32_t expectedSweeps;  /* how many sweeps the caller expects to run on this handle, 0 = many / unknown.  The source-blocked
-	                             layout costs ~0.13 ns per directed edge to build and saves ~5 ps per edge and sweep (config 3: 0.2 s
-	                             against 8 ms per sweep), so a handle that will run fewer than 32 sweeps (one short chain to a proper
+	                             layout costs ~0.09 ns per directed edge to build and saves ~6 ps per edge and sweep (config 3: 0.14 s
+	                             against 9 ms per sweep), so a handle that will run fewer than 16 sweeps (one short chain to a proper
 	                             colouring) keeps the direct kernels, which need no layout */
 } mcmcb200_params;
 

@@ -17,6 +17,9 @@ inline void free_blocked_layout(BlockedLayout & L) {
 #define BLK_CU(call) do { err = (call); if (err != cudaSuccess) goto done; } while (0)
 
 // Returns cudaSuccess with L.valid == false when the layout does not apply (hub rows larger than a tile, > 2^31 edges...).
+#ifndef MCMCB200_BUILD_BY_SORT
+#define MCMCB200_BUILD_BY_SORT 0     /* 1: always the sort-based construction (the path of graphs with more than 4096 source chunks) */
+#endif
 inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_rowptr, const uint32_t * d_neighs, uint32_t nLocal,
                                         uint64_t nnzLocal, uint32_t nGlobal, int colBytes, uint32_t stageCapBytes, uint32_t itemEntries, uint32_t roundV,
                                         cudaStream_t stream, uint64_t * launches) {
@@ -40,6 +43,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	uint32_t * d_v32[2] = {nullptr, nullptr};
 	uint32_t * d_words = nullptr, * d_runStart = nullptr, * d_stageOff = nullptr;
 	uint32_t numSlices = 0, sellTotal = 0;
+	bool tileLocal = false; size_t tlSmem = 0;
 
 	BLK_CU(cudaMalloc(&d_tmp, 2 * sizeof(uint32_t)));
 	// ---- tile size: a multiple of 128 vertices whose worst tile (edges + run padding) fits the stage.  Pass B walks a tile in
@@ -82,6 +86,14 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	// ---- bin the directed edges by source chunk (stable radix sort of (chunk, edge id)) ----
 	BLK_CU(cudaMalloc(&d_tileE, sizeof(uint32_t) * ((size_t)numTiles + 1)));
 	blk_tile_edge_starts_kernel<<<(numTiles + 1 + 255) / 256, 256, 0, stream>>>(d_rowptr, nLocal, TV, numTiles, d_tileE); (*launches)++;
+	// tile-local construction (blocked_sweep.cuh: blk_tile_hist_kernel / blk_tile_rank_kernel) whenever the per-warp counters fit
+	tileLocal = P <= kTileLocalMaxP && !MCMCB200_BUILD_BY_SORT;
+	tlSmem = sizeof(uint32_t) * (size_t)P * kTileLocalWarps;
+	if (tileLocal && tlSmem > 48 * 1024) {
+		BLK_CU(cudaFuncSetAttribute(blk_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlSmem));
+		BLK_CU(cudaFuncSetAttribute(blk_tile_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlSmem));
+	}
+	if (!tileLocal) {
 	for (int i = 0; i < 2; ++i) {
 		BLK_CU(cudaMalloc(&d_keys[i], sizeof(uint16_t) * (size_t)nnz));
 		BLK_CU(cudaMalloc(&d_vals[i], sizeof(uint32_t) * (size_t)nnz));
@@ -100,6 +112,7 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 		cudaFree(d_cub); d_cub = nullptr;
 	}
 	cudaFree(d_keys[1]); d_keys[1] = nullptr; cudaFree(d_vals[1]); d_vals[1] = nullptr;
+	}
 
 	// ---- run lengths per (bucket, tile), padded to 4; three exclusive scans ----
 	BLK_CU(cudaMalloc(&d_cnt, sizeof(uint32_t) * cells));
@@ -108,14 +121,18 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&d_gs, sizeof(uint32_t) * cells));
 	BLK_CU(cudaMalloc(&d_plenT, sizeof(uint32_t) * cells));
 	BLK_CU(cudaMalloc(&d_scanT, sizeof(uint32_t) * cells));
-	BLK_CU(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * cells, stream));
-	blk_run_count_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_tileE, numTiles, d_cnt); (*launches)++;
+	if (tileLocal) {
+		blk_tile_hist_kernel<<<(numTiles + kTileLocalWarps - 1) / kTileLocalWarps, kTileLocalWarps * 32, tlSmem, stream>>>(d_neighs, d_tileE, numTiles, P, d_cnt); (*launches)++;
+	} else {
+		BLK_CU(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * cells, stream));
+		blk_run_count_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_tileE, numTiles, d_cnt); (*launches)++;
+	}
 	blk_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_cnt, P, numTiles, d_plen, d_plenT); (*launches)++;
 	{
 		size_t need = 0;
 		BLK_CU(cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt, d_us, (int)cells, stream));
 		BLK_CU(cudaMalloc(&d_cub, need));
-		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_cnt, d_us, (int)cells, stream));
+		if (!tileLocal) BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_cnt, d_us, (int)cells, stream));
 		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_plen, d_gs, (int)cells, stream));
 		BLK_CU(cub::DeviceScan::ExclusiveSum(d_cub, need, d_plenT, d_scanT, (int)cells, stream)); (*launches) += 6;
 	}
@@ -142,8 +159,13 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMemsetAsync(L.srcLocal, 0, sizeof(uint16_t) * ((size_t)L.totalPadded + 16), stream));
 	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
 	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
-	blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
-	                                                                d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
+	if (tileLocal) {
+		blk_tile_rank_kernel<<<(numTiles + kTileLocalWarps - 1) / kTileLocalWarps, kTileLocalWarps * 32, tlSmem, stream>>>(
+			d_neighs, d_tileE, numTiles, P, d_runStart, d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
+	} else {
+		blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
+		                                                                d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
+	}
 	BLK_CU(cudaMalloc(&L.ecol, (size_t)colBytes * ((size_t)L.totalPadded + 16)));
 	BLK_CU(cudaMemsetAsync(L.ecol, 0, (size_t)colBytes * ((size_t)L.totalPadded + 16), stream));
 	// ---- SELL-32-sigma copy of gidx for the light rows: per tile, vertices by descending degree; 32-slot slices interleaved ----

@@ -207,6 +207,68 @@ __global__ void blk_fill_entries_kernel(const uint16_t * keys, const uint32_t * 
 	gidx[e] = (uint16_t)((scanT[(size_t)T * P] & alignMask) + stageOff[(size_t)T * (P + 1) + b] + r);
 }
 
+// ---- tile-local construction (P <= kTileLocalMaxP source chunks): a WARP per destination tile walks the tile's contiguous CSR slice in
+//      order and keeps one counter per source chunk in shared memory -- run lengths in a first pass; in a second pass the position of
+//      every edge inside its (chunk, tile) run = the counter before it, which is exactly the rank a stable sort by chunk would give it.
+//      No global sort of the 1.6e9 edges, no per-edge tile search, and both outputs are written (nearly) in order: the sort-based
+//      construction spent 110 ms of config 3's 207 ms in one kernel that gathered neighs[e] and scattered gidx[e] at random
+//      (2 x 51 GB of 32-byte sectors for 2-byte payloads); this one reads the CSR twice. ----
+constexpr uint32_t kTileLocalMaxP = 4096;       // 16 KiB of counters per warp at most
+constexpr int kTileLocalWarps = 4;
+
+__global__ void __launch_bounds__(kTileLocalWarps * 32)
+blk_tile_hist_kernel(const uint32_t * __restrict__ neighs, const uint32_t * __restrict__ tileE, uint32_t numTiles, uint32_t P, uint32_t * cnt /* [P][numTiles] */) {
+	extern __shared__ uint32_t s_tl[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t * h = s_tl + (size_t)warp * P;
+	const uint32_t T = blockIdx.x * kTileLocalWarps + warp;
+	if (T >= numTiles) return;                                   // (no CTA barrier below)
+	for (uint32_t b = lane; b < P; b += 32) h[b] = 0u;
+	__syncwarp();
+	const uint32_t e0 = tileE[T], e1 = tileE[T + 1];
+	for (uint32_t e = e0; e < e1; e += 32u) {
+		const bool active = e + lane < e1;
+		const uint32_t b = active ? (__ldcs(neighs + e + lane) >> kChunkBits) : 0xffffffffu;
+		const uint32_t mask = __match_any_sync(0xffffffffu, b);
+		if (active && lane == __ffs((int)mask) - 1) h[b] += (uint32_t)__popc(mask);
+		__syncwarp();
+	}
+	for (uint32_t b = lane; b < P; b += 32) cnt[(size_t)b * numTiles + T] = h[b];
+}
+
+__global__ void __launch_bounds__(kTileLocalWarps * 32)
+blk_tile_rank_kernel(const uint32_t * __restrict__ neighs, const uint32_t * __restrict__ tileE, uint32_t numTiles, uint32_t P,
+                     const uint32_t * __restrict__ runStart /* [T][b] */, const uint32_t * __restrict__ stageOff /* [T][P+1] */,
+                     const uint32_t * __restrict__ scanT /* [T][b] */, uint32_t alignMask, uint16_t * srcLocal, uint16_t * gidx) {
+	extern __shared__ uint32_t s_tl[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t * h = s_tl + (size_t)warp * P;
+	const uint32_t T = blockIdx.x * kTileLocalWarps + warp;
+	if (T >= numTiles) return;
+	for (uint32_t b = lane; b < P; b += 32) h[b] = 0u;
+	__syncwarp();
+	const uint32_t e0 = tileE[T], e1 = tileE[T + 1];
+	const uint32_t base = __ldg(scanT + (size_t)T * P) & alignMask;     // pass B copies the tile's block from the 16-byte boundary below its first entry
+	const uint32_t * rs = runStart + (size_t)T * P;
+	const uint32_t * so = stageOff + (size_t)T * (P + 1);
+	const uint32_t lt = (1u << lane) - 1u;
+	for (uint32_t e = e0; e < e1; e += 32u) {
+		const bool active = e + lane < e1;
+		const uint32_t nb = active ? __ldcs(neighs + e + lane) : 0xffffffffu;
+		const uint32_t b = active ? (nb >> kChunkBits) : 0xffffffffu;
+		const uint32_t mask = __match_any_sync(0xffffffffu, b);
+		uint32_t r = 0;
+		if (active) r = h[b] + (uint32_t)__popc(mask & lt);              // edges of the same chunk earlier in CSR order, in this tile
+		__syncwarp();
+		if (active && lane == __ffs((int)mask) - 1) h[b] += (uint32_t)__popc(mask);
+		__syncwarp();
+		if (active) {
+			srcLocal[__ldg(rs + b) + r] = (uint16_t)(nb & (kChunkV - 1u));
+			gidx[e + lane] = (uint16_t)(base + __ldg(so + b) + r);
+		}
+	}
+}
+
 // pass-A work items: item (part p, bucket b) = the entries of bucket b that belong to tiles [partStart[p], partStart[p+1])
 __global__ void blk_items_kernel(const uint32_t * gs /* [P][numTiles] */, uint32_t P, uint32_t numTiles, const uint32_t * partStart, uint32_t numParts,
                                  uint32_t total, uint32_t * items, uint8_t * tilePart) {

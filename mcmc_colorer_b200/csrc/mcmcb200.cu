@@ -569,7 +569,7 @@ int create_common(mcmcb200_handle ** out, uint32_t nGlobal, uint32_t vBegin, uin
 		const bool forceBinned = (p->flags & MCMCB200_FLAG_FORCE_BINNED) != 0;
 		const bool large = nnzLocal >= (1ull << 22) && nGlobal >= (1u << 18);
 		// a handle that will only run a few sweeps does not amortise the layout build (mcmcb200.h: expectedSweeps)
-		const bool fewSweeps = p->expectedSweeps != 0u && p->expectedSweeps < 32u;
+		const bool fewSweeps = p->expectedSweeps != 0u && p->expectedSweeps < 16u;
 		const bool want = !h->wide && (forceBlocked || (!forceDirect && !forceBinned && large && !fewSweeps));
 		if (want) {
 			// colour bytes a tile stages in shared memory.  Large partitions: 32 KiB (tiles of 4 x 384 vertices on a mean-degree-16
