@@ -89,10 +89,8 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	// tile-local construction (blocked_sweep.cuh: blk_tile_hist_kernel / blk_tile_rank_kernel) whenever the per-warp counters fit
 	tileLocal = P <= kTileLocalMaxP && !MCMCB200_BUILD_BY_SORT;
 	tlSmem = sizeof(uint32_t) * (size_t)P * kTileLocalWarps;
-	if (tileLocal && tlSmem > 48 * 1024) {
-		BLK_CU(cudaFuncSetAttribute(blk_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlSmem));
-		BLK_CU(cudaFuncSetAttribute(blk_tile_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlSmem));
-	}
+	if (tileLocal && tlSmem > 48 * 1024) BLK_CU(cudaFuncSetAttribute(blk_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlSmem));
+	if (tileLocal) BLK_CU(cudaFuncSetAttribute(blk_tile_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blk_tile_rank_smem(P, stageCap) + 16)));
 	if (!tileLocal) {
 	for (int i = 0; i < 2; ++i) {
 		BLK_CU(cudaMalloc(&d_keys[i], sizeof(uint16_t) * (size_t)nnz));
@@ -160,8 +158,8 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	BLK_CU(cudaMalloc(&L.gidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
 	BLK_CU(cudaMemsetAsync(L.gidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), stream));
 	if (tileLocal) {
-		blk_tile_rank_kernel<<<(numTiles + kTileLocalWarps - 1) / kTileLocalWarps, kTileLocalWarps * 32, tlSmem, stream>>>(
-			d_neighs, d_tileE, numTiles, P, d_runStart, d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
+		blk_tile_rank_kernel<<<numTiles, 32, blk_tile_rank_smem(P, stageCap) + 16, stream>>>(
+			d_neighs, d_tileE, numTiles, P, stageCap, d_runStart, d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
 	} else {
 		blk_fill_entries_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(d_keys[0], d_vals[0], nnz, d_neighs, d_tileE, numTiles, P, d_us, d_gs,
 		                                                                d_stageOff, d_scanT, (uint32_t)(16 / colBytes) - 1u, L.srcLocal, L.gidx); (*launches)++;
@@ -235,6 +233,8 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 			cut(tail - 2 * (tail / 4)); cut(tail / 4); cut(tail / 4);
 			if (ps.back() < numTiles) ps.push_back(numTiles);
 		} else {
+			// (few parts: e.g. one rank of an 8-GPU run.  A short first part -- K/4, K/8, K/16 tiles -- so that pass B need not wait for
+			//  half of pass A was measured slower on such a partition: 0.563 / 0.570 / 0.575 vs 0.540 ms, its small items pay the chunk reload)
 			while (ps.back() < numTiles) cut(K);
 		}
 		L.numParts = (uint32_t)ps.size() - 1;

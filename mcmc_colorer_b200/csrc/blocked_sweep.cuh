@@ -236,36 +236,62 @@ blk_tile_hist_kernel(const uint32_t * __restrict__ neighs, const uint32_t * __re
 	for (uint32_t b = lane; b < P; b += 32) cnt[(size_t)b * numTiles + T] = h[b];
 }
 
-__global__ void __launch_bounds__(kTileLocalWarps * 32)
-blk_tile_rank_kernel(const uint32_t * __restrict__ neighs, const uint32_t * __restrict__ tileE, uint32_t numTiles, uint32_t P,
+// second pass: ONE warp per CTA and tile.  The tile's source-local ids are first put in STAGE ORDER in shared memory (position =
+// the run's offset in the tile's stage image + rank), then every run leaves as whole 8-byte granules -- 4 stores per 16-entry run
+// instead of 16 scattered 2-byte ones (the 2-byte scatter made the first version of this kernel 96 ms on config 3).
+__host__ __device__ inline size_t blk_tile_rank_smem(uint32_t P, uint32_t stageCap) { return sizeof(uint32_t) * (size_t)P + sizeof(uint16_t) * ((size_t)stageCap + 16); }
+
+__global__ void __launch_bounds__(32)
+blk_tile_rank_kernel(const uint32_t * __restrict__ neighs, const uint32_t * __restrict__ tileE, uint32_t numTiles, uint32_t P, uint32_t stageCap,
                      const uint32_t * __restrict__ runStart /* [T][b] */, const uint32_t * __restrict__ stageOff /* [T][P+1] */,
                      const uint32_t * __restrict__ scanT /* [T][b] */, uint32_t alignMask, uint16_t * srcLocal, uint16_t * gidx) {
-	extern __shared__ uint32_t s_tl[];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t * h = s_tl + (size_t)warp * P;
-	const uint32_t T = blockIdx.x * kTileLocalWarps + warp;
+	extern __shared__ __align__(16) uint32_t s_tl[];
+	const int lane = threadIdx.x;
+	uint32_t * h = s_tl;
+	uint16_t * sbuf = reinterpret_cast<uint16_t *>(s_tl + P);     // (P * 4 bytes: 8-byte aligned for even P; odd P is padded below)
+	if (P & 1u) sbuf += 2;
+	const uint32_t T = blockIdx.x;
 	if (T >= numTiles) return;
+	const uint32_t * rs = runStart + (size_t)T * P;
+	const uint32_t * so = stageOff + (size_t)T * (P + 1);
+	const uint32_t tot = __ldg(so + P);                           // padded entries of the tile's stage image (<= stageCap)
 	for (uint32_t b = lane; b < P; b += 32) h[b] = 0u;
+	for (uint32_t i = lane; 2u * i < tot; i += 32) reinterpret_cast<uint32_t *>(sbuf)[i] = 0u;    // run padding stays 0
 	__syncwarp();
 	const uint32_t e0 = tileE[T], e1 = tileE[T + 1];
 	const uint32_t base = __ldg(scanT + (size_t)T * P) & alignMask;     // pass B copies the tile's block from the 16-byte boundary below its first entry
-	const uint32_t * rs = runStart + (size_t)T * P;
-	const uint32_t * so = stageOff + (size_t)T * (P + 1);
 	const uint32_t lt = (1u << lane) - 1u;
-	for (uint32_t e = e0; e < e1; e += 32u) {
-		const bool active = e + lane < e1;
-		const uint32_t nb = active ? __ldcs(neighs + e + lane) : 0xffffffffu;
-		const uint32_t b = active ? (nb >> kChunkBits) : 0xffffffffu;
-		const uint32_t mask = __match_any_sync(0xffffffffu, b);
-		uint32_t r = 0;
-		if (active) r = h[b] + (uint32_t)__popc(mask & lt);              // edges of the same chunk earlier in CSR order, in this tile
-		__syncwarp();
-		if (active && lane == __ffs((int)mask) - 1) h[b] += (uint32_t)__popc(mask);
-		__syncwarp();
-		if (active) {
-			srcLocal[__ldg(rs + b) + r] = (uint16_t)(nb & (kChunkV - 1u));
-			gidx[e + lane] = (uint16_t)(base + __ldg(so + b) + r);
+	constexpr int kU = 8;                                         // chunks of 32 edges loaded ahead (one warp per SM sub-partition: latency is everything)
+	for (uint32_t eb = e0; eb < e1; eb += 32u * kU) {
+		uint32_t nbv[kU];
+#pragma unroll
+		for (int u = 0; u < kU; ++u) { const uint32_t e = eb + 32u * u + lane; nbv[u] = (e < e1) ? __ldcs(neighs + e) : 0xffffffffu; }
+#pragma unroll
+		for (int u = 0; u < kU; ++u) {
+			const uint32_t e = eb + 32u * u + lane;
+			const bool active = e < e1;
+			const uint32_t nb = nbv[u];
+			const uint32_t b = active ? (nb >> kChunkBits) : 0xffffffffu;
+			const uint32_t mask = __match_any_sync(0xffffffffu, b);
+			uint32_t r = 0;
+			if (active) r = h[b] + (uint32_t)__popc(mask & lt);          // edges of the same chunk earlier in CSR order, in this tile
+			__syncwarp();
+			if (active && lane == __ffs((int)mask) - 1) h[b] += (uint32_t)__popc(mask);
+			__syncwarp();
+			if (active) {
+				const uint32_t pos = __ldg(so + b) + r;
+				sbuf[pos] = (uint16_t)(nb & (kChunkV - 1u));
+				gidx[e] = (uint16_t)(base + pos);
+			}
 		}
+	}
+	__syncwarp();
+	// runs out: lane per source chunk, whole granules (runs are padded to 4 entries = 8 bytes, both here and in srcLocal)
+	for (uint32_t b = lane; b < P; b += 32) {
+		const uint32_t p0 = __ldg(so + b), p1 = __ldg(so + b + 1);
+		const uint2 * src = reinterpret_cast<const uint2 *>(sbuf + p0);
+		uint2 * dst = reinterpret_cast<uint2 *>(srcLocal + __ldg(rs + b));
+		for (uint32_t g = 0; g < ((p1 - p0) >> 2); ++g) dst[g] = src[g];
 	}
 }
 
