@@ -274,6 +274,7 @@ def main():
                   stage_cap_bytes=args.stage_cap_bytes, item_bits=args.item_bits, stage_buffers=args.stage_buffers, expected_sweeps=args.expected_sweeps)
     ch.synchronize()
     create_ms = 1e3 * (time.perf_counter() - t_create)   # mcmcb200_create: allocations + (blocked path) the layout build on the device
+    layout_bytes = ch.layout_bytes()
     if args.quick:
         for _ in range(args.warmup):
             ch.init_colors(None); ch.sweep(1); ch.synchronize()
@@ -416,7 +417,8 @@ def main():
         "config": {"workload": desc, "n": n, "nnz_directed": nnz, "nCol": nCol, "maxDeg": max_deg, "proposal": args.proposal,
                    "step": "one sweep from the uniform random colouring (all vertices active)",
                    "l2": "inputs (CSR %.1f GB) larger than L2; no flush needed" % ((4 * nnz + 4 * n) / 1e9),
-                   "graph_gen_s": round(t_gen, 2), "create_ms": round(create_ms, 1)},
+                   "graph_gen_s": round(t_gen, 2), "create_ms": round(create_ms, 1), "layout_bytes": int(layout_bytes),
+                   "csr_bytes": int(4 * (n + 1) + 4 * nnz)},
         "edges_per_sec": value * nnz / n,
         "chain_ms_per_sweep": chain_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

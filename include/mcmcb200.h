@@ -250,6 +250,9 @@ int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches);
 #define MCMCB200_MODE_WIDE_BINNED 4        /* palettes above 512 colours: the degree-binned rows with colour lists / shared-memory bitmaps
                                               instead of register masks (one table launch + one sweep launch per sweep) */
 int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode);
+/* Device memory held by the sweep layout built at create time, on top of the CSR and the colour buffers: the source-blocked layout
+ * (about 8.7 bytes per directed edge), the degree-bin lists, the wide-palette tables and queues; 0 for the small-graph kernel. */
+int mcmcb200_layout_bytes(mcmcb200_handle * h, uint64_t * bytes);
 
 const char * mcmcb200_strerror(int code);
 const char * mcmcb200_last_cuda_error(void);

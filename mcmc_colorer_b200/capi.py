@@ -34,7 +34,7 @@ SYMBOLS = [
     "mcmcb200_ipc_export", "mcmcb200_ipc_attach", "mcmcb200_ipc_detach", "mcmcb200_init_colors_slice", "mcmcb200_init_colors_finish",
     "mcmcb200_get_colors_slice", "mcmcb200_color_bytes", "mcmcb200_init_colors_narrow", "mcmcb200_get_colors_narrow",
     "mcmcb200_tailcut_dist_begin", "mcmcb200_tailcut_dist_mark", "mcmcb200_tailcut_dist_round", "mcmcb200_tailcut_dist_apply",
-    "mcmcb200_tailcut_dist_recount", "mcmcb200_tailcut_dist_end",
+    "mcmcb200_tailcut_dist_recount", "mcmcb200_tailcut_dist_end", "mcmcb200_layout_bytes",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
     L.mcmcb200_tailcut_dist_apply.argtypes = [vp, vp, vp, C.c_uint32]
     L.mcmcb200_tailcut_dist_recount.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), u32p]
     L.mcmcb200_tailcut_dist_end.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32]
+    L.mcmcb200_layout_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mcmcb200_ipc_export.argtypes = [vp, vp]
     L.mcmcb200_ipc_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.mcmcb200_ipc_detach.argtypes = [vp]

@@ -323,6 +323,11 @@ class Chain:
         capi.check(self.L.mcmcb200_last_sweep_ms(self.h, C.byref(ms)), "mcmcb200_last_sweep_ms")
         return ms.value
 
+    def layout_bytes(self):
+        b = C.c_uint64()
+        capi.check(self.L.mcmcb200_layout_bytes(self.h, C.byref(b)), "mcmcb200_layout_bytes")
+        return b.value
+
     KERNEL_MODES = ("direct", "blocked", "blocked-overlapped", "direct-binned", "wide-binned")
 
     def kernel_mode(self):

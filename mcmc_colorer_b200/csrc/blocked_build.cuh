@@ -258,6 +258,11 @@ inline cudaError_t build_blocked_layout(BlockedLayout & L, const uint32_t * d_ro
 	}
 	cudaFree(L.order); L.order = nullptr;                        // construction only
 	L.P = P; L.TV = TV; L.numTiles = numTiles; L.stageCap = stageCap;
+	L.bytes = sizeof(uint16_t) * ((size_t)L.totalPadded + 16) + (size_t)colBytes * ((size_t)L.totalPadded + 16)       // srcLocal, ecol
+	        + sizeof(uint32_t) * ((size_t)(L.totalPadded >> 2) + 16) + sizeof(uint16_t) * ((size_t)nnz + 16)            // granDst, gidx
+	        + sizeof(uint2) * ((size_t)sellTotal + 64) + sizeof(uint16_t) * (size_t)numTiles * TV                       // gidxS, slotInfo
+	        + sizeof(uint32_t) * ((size_t)numSlices + 8) + sizeof(uint32_t) * ((size_t)numTiles + 1)                    // sliceOff, tileBase
+	        + sizeof(uint32_t) * 3 * (size_t)L.numItems + numTiles;                                                      // items, tilePart
 	L.valid = true;
 done:
 	cudaFree(d_tmp); cudaFree(d_tileE); cudaFree(d_keys[0]); cudaFree(d_keys[1]); cudaFree(d_vals[0]); cudaFree(d_vals[1]); cudaFree(d_cub);

@@ -88,6 +88,7 @@ struct BlockedLayout {
 	unsigned long long * dbgTimes = nullptr;
 	uint32_t  nbuf = 1;              // stage buffers per pass-B CTA: 2 = tile T+1 is copied in (TMA) while tile T is computed
 	size_t    smemA = 0, smemB = 0;
+	size_t    bytes = 0;             // device memory the layout holds (mcmcb200_layout_bytes)
 	int       gridA = 0, gridB = 0;
 };
 

@@ -1484,6 +1484,16 @@ int mcmcb200_kernel_mode(mcmcb200_handle * h, int * mode) {
 	return MCMCB200_OK;
 }
 
+int mcmcb200_layout_bytes(mcmcb200_handle * h, uint64_t * bytes) {
+	if (!h || !bytes) return MCMCB200_EINVAL;
+	uint64_t b = 0;
+	if (h->bl.valid) b += h->bl.bytes;
+	if (h->bn.valid) b += sizeof(uint32_t) * ((uint64_t)h->bn.n[0] + h->bn.n[1] + h->bn.n[2] + 3);
+	if (h->wide) b += (uint64_t)h->nGlobal + kColorPad + sizeof(uint32_t) * ((uint64_t)h->nLocal + 8 + h->bn.n[2] + 1) + 2 * sizeof(float) * ((uint64_t)h->p.nCol + 1);
+	*bytes = b;
+	return MCMCB200_OK;
+}
+
 int mcmcb200_launch_count(mcmcb200_handle * h, uint64_t * launches) {
 	if (!h || !launches) return MCMCB200_EINVAL;
 	*launches = h->launches;
