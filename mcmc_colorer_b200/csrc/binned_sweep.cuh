@@ -56,8 +56,13 @@ inline void free_binned_layout(BinnedLayout & L) {
 
 inline cudaError_t build_binned_layout(BinnedLayout & L, const uint32_t * d_rowptr, uint32_t nLocal, cudaStream_t stream, uint64_t * launches) {
 	L = BinnedLayout{};
-	if (nLocal == 0) return cudaSuccess;
 	cudaError_t err = cudaSuccess;
+	if (nLocal == 0) {                                            // an empty partition (a rank of a very skewed graph): three empty lists
+		for (int b = 0; b < 3; ++b) if ((err = cudaMalloc(&L.list[b], sizeof(uint32_t))) != cudaSuccess) { free_binned_layout(L); return err; }
+		if ((err = cudaMalloc(&L.counters, 4 * sizeof(uint32_t))) != cudaSuccess) { free_binned_layout(L); return err; }
+		L.valid = true;
+		return cudaSuccess;
+	}
 	uint32_t * d_num = nullptr;
 	void * d_tmp = nullptr; size_t tmpBytes = 0;
 	const uint32_t lo[3] = {0u, kBinThreadMax + 1u, kBinWarpMax + 1u}, hi[3] = {kBinThreadMax, kBinWarpMax, 0xffffffffu};

@@ -334,6 +334,32 @@ def test_empty_and_tiny_graphs(mc, port):
     ch.init_colors(None)
     assert ch.status().converged == 1
     ch.close()
+    # the same corner cases on the wide-palette kernels: no edges at all, and a triangle (2 colours in use out of 700)
+    ch = make_chain(mc, np.zeros(11, np.uint32), np.zeros(0, np.uint32), 700, seed=1)
+    assert ch.kernel_mode() == "wide-binned"
+    ch.init_colors(np.arange(10, dtype=np.uint32) * 60)
+    st = ch.status()
+    assert st.converged == 1 and st.conflictEdges == 0 and st.violatingVertices == 0
+    ch.close()
+    for proposal in (UNIFORM, DYNAMIC):
+        ch = make_chain(mc, cumul, neighs, 700, proposal=proposal, seed=3, replay=True)
+        c = np.array([5, 5, 699], np.uint32)
+        ch.init_colors(c)
+        assert ch.status().conflictEdges == 1
+        for s in range(1, 4):
+            ch.sweep(1)
+            c, _ = port.sweep(cumul, neighs, 700, EPS, c, port.tape(3, s, 3, proposal), proposal)
+            assert np.array_equal(ch.get_colors(), c)
+        ch.close()
+    # an EMPTY partition (a rank of a very skewed graph balanced by edges) must be creatable on every kernel family
+    import ctypes as C
+    from mcmc_colorer_b200 import capi
+    for nCol in (4, 700):
+        prm = mc.ColoringMCMCParams(nCol=nCol, seed=1)
+        ch = mc.Chain(np.zeros(1, np.uint32), np.zeros(0, np.uint32), prm, device=0, flags=capi.FLAG_NO_FUSED_FINALIZE, n_global=1024, v_begin=512, v_end=512)
+        ch.init_colors(np.zeros(1024, np.uint32))
+        ch.sweep(1)
+        ch.close()
 
 
 def test_argument_errors(mc, c1_graph):
