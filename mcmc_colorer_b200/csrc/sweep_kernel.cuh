@@ -310,6 +310,22 @@ __device__ __forceinline__ uint32_t walk_conflicting(const unsigned long long (&
 	return nCol - 1u;                                       // overflow contract: clamp to nCol-1
 }
 
+// DYNAMIC: r = (sum over the occupied colours, ascending, of dist[c] - eps) / Zp   (coloringMCMC_balance.cu:104-109,124)
+template <int W>
+__device__ __forceinline__ float dynamic_reminder(const unsigned long long (&m)[W], uint32_t Zp, float eps, const float * s_dist) {
+	float rem = 0.0f;
+#pragma unroll
+	for (int w = 0; w < W; ++w) {
+		unsigned long long bits = m[w];
+		while (bits) {
+			const int b = __ffsll((long long)bits) - 1;
+			bits &= bits - 1ull;
+			rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
+		}
+	}
+	return __fdiv_rn(rem, __uint2float_rn(Zp));
+}
+
 // Deferred CDF walks: conflicting vertices are parked in shared memory and walked later by densely packed lanes
 // (in the first sweeps ~1/3 of the vertices conflict, later almost none: without the queue nearly every warp would
 // run the full walk for a handful of active lanes).
@@ -401,18 +417,6 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 				float freeW = 0.0f, r = 0.0f;
 				if (!isDyn) {                                 // (1 - eps*Zv) / Zvcomp, coloringMCMC_CPU.cpp:416
 					freeW = s_dist[Zn];                       // fill_proposal_table: (1 - eps*Zn) / Zp, Zp >= 1 here
-				} else {                                      // reminder / Zp, coloringMCMC_balance.cu:104-109,124
-					float rem = 0.0f;
-#pragma unroll
-					for (int w = 0; w < W; ++w) {
-						unsigned long long bits = m[w];
-						while (bits) {
-							const int b = __ffsll((long long)bits) - 1;
-							bits &= bits - 1ull;
-							rem = __fadd_rn(rem, __fsub_rn(s_dist[w * 64 + b], eps));
-						}
-					}
-					r = __fdiv_rn(rem, __uint2float_rn(Zp));
 				}
 				if (queue != nullptr) {
 					// one atomic per converged group of lanes instead of one per lane
@@ -428,10 +432,11 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 #pragma unroll
 						for (int w = 0; w < W; ++w) queue->mask[(size_t)qi * W + w] = m[w];
 						queue->lvOwn[2 * qi] = lv; queue->lvOwn[2 * qi + 1] = myOwn;
-						queue->uw[2 * qi] = u; queue->uw[2 * qi + 1] = isDyn ? r : freeW;
+						queue->uw[2 * qi] = u; queue->uw[2 * qi + 1] = freeW;           // (DYNAMIC: r is computed by the dense lanes of the drain)
 						return;
 					}
 				}
+				if (isDyn) r = dynamic_reminder<W>(m, nCol - Zn, eps, s_dist);
 				newc = walk_conflicting<W, isDyn>(m, nCol, eps, freeW, r, s_dist, u);
 			}
 			finish_vertex<ColT>(a, nxt, lv, myOwn, newc, s_hist, true, nxtTile, tileV0);
@@ -452,7 +457,14 @@ __device__ __forceinline__ void drain_walk_queue(const SweepArgs & a, ColT * __r
 #pragma unroll
 		for (int w = 0; w < W; ++w) m[w] = q.mask[(size_t)i * W + w];
 		const uint32_t lv = q.lvOwn[2 * i], own = q.lvOwn[2 * i + 1];
-		const float u = q.uw[2 * i], x = q.uw[2 * i + 1];
+		const float u = q.uw[2 * i];
+		float x = q.uw[2 * i + 1];
+		if (kDyn) {                                               // the reminder of a parked vertex: here the lanes are dense
+			uint32_t Zn = 0;
+#pragma unroll
+			for (int w = 0; w < W; ++w) Zn += __popcll(m[w]);
+			x = dynamic_reminder<W>(m, a.nCol - Zn, a.eps, s_dist);
+		}
 		const uint32_t newc = walk_conflicting<W, kDyn>(m, a.nCol, a.eps, x, x, s_dist, u);
 		finish_vertex<ColT>(a, nxt, lv, own, newc, s_hist, true, nxtTile, tileV0);
 	}
