@@ -219,6 +219,9 @@ int mcmcb200_finalize_sweep(mcmcb200_handle * h);
 int mcmcb200_init_colors_slice(mcmcb200_handle * h, const uint32_t * ownedColors);
 int mcmcb200_init_colors_finish(mcmcb200_handle * h);
 int mcmcb200_get_colors_slice(mcmcb200_handle * h, uint32_t * out /* [vEnd - vBegin] */);
+/* The sliced transfers in the device's narrow colour format (elemBytes = mcmcb200_color_bytes): no staging, no conversion. */
+int mcmcb200_init_colors_slice_narrow(mcmcb200_handle * h, const void * ownedColors /* [vEnd - vBegin] u8 or u16 */, uint32_t elemBytes);
+int mcmcb200_get_colors_slice_narrow(mcmcb200_handle * h, void * out /* [vEnd - vBegin] u8 or u16 */, uint32_t elemBytes);
 
 /* Fused exchange (one box, NVLink/NVSwitch): no collective library call and no host in the sweep loop.  The sweep kernel
  * itself stores every finished tile's new colours into ALL ranks' colour replicas through peer pointers, and the last CTA of

@@ -35,6 +35,7 @@ SYMBOLS = [
     "mcmcb200_get_colors_slice", "mcmcb200_color_bytes", "mcmcb200_init_colors_narrow", "mcmcb200_get_colors_narrow",
     "mcmcb200_tailcut_dist_begin", "mcmcb200_tailcut_dist_mark", "mcmcb200_tailcut_dist_round", "mcmcb200_tailcut_dist_apply",
     "mcmcb200_tailcut_dist_recount", "mcmcb200_tailcut_dist_end", "mcmcb200_layout_bytes",
+    "mcmcb200_init_colors_slice_narrow", "mcmcb200_get_colors_slice_narrow",
 ]
 
 
@@ -105,6 +106,8 @@ def lib():
     L.mcmcb200_tailcut_dist_recount.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), u32p]
     L.mcmcb200_tailcut_dist_end.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32]
     L.mcmcb200_layout_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mcmcb200_init_colors_slice_narrow.argtypes = [vp, vp, C.c_uint32]
+    L.mcmcb200_get_colors_slice_narrow.argtypes = [vp, vp, C.c_uint32]
     L.mcmcb200_ipc_export.argtypes = [vp, vp]
     L.mcmcb200_ipc_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.mcmcb200_ipc_detach.argtypes = [vp]

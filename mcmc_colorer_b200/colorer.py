@@ -289,6 +289,12 @@ class Chain:
                    "mcmcb200_device_view")
         return ptr.value, nbytes.value, eb.value
 
+    def init_colors_slice_narrow_ptr(self, host_ptr, elem_bytes):
+        capi.check(self.L.mcmcb200_init_colors_slice_narrow(self.h, C.c_void_p(host_ptr), elem_bytes), "mcmcb200_init_colors_slice_narrow")
+
+    def get_colors_slice_narrow_ptr(self, host_ptr, elem_bytes):
+        capi.check(self.L.mcmcb200_get_colors_slice_narrow(self.h, C.c_void_p(host_ptr), elem_bytes), "mcmcb200_get_colors_slice_narrow")
+
     def init_colors_slice_ptr(self, host_ptr):
         capi.check(self.L.mcmcb200_init_colors_slice(self.h, C.c_void_p(host_ptr)), "mcmcb200_init_colors_slice")
 

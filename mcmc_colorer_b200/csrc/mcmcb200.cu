@@ -867,6 +867,32 @@ int mcmcb200_init_colors_slice(mcmcb200_handle * h, const uint32_t * ownedColors
 	return MCMCB200_OK;
 }
 
+int mcmcb200_init_colors_slice_narrow(mcmcb200_handle * h, const void * ownedColors, uint32_t elemBytes) {
+	if (!h || !ownedColors) return MCMCB200_EINVAL;
+	if (elemBytes != (uint32_t)h->colBytes) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	int rc = reset_state(h); if (rc) return rc;
+	h->colorsInit = false;
+	if (h->nLocal)   // straight into the owned slice of the replica; the range check happens in _finish (class-size pass over the whole colouring)
+		CU(cudaMemcpyAsync(static_cast<unsigned char *>(h->d_colors[0]) + (size_t)h->vBegin * h->colBytes, ownedColors, (size_t)h->nLocal * h->colBytes,
+		                   cudaMemcpyHostToDevice, h->stream));
+	return MCMCB200_OK;
+}
+
+int mcmcb200_get_colors_slice_narrow(mcmcb200_handle * h, void * out, uint32_t elemBytes) {
+	if (!h || !out) return MCMCB200_EINVAL;
+	if (!h->colorsInit) return MCMCB200_ESTATE;
+	if (elemBytes != (uint32_t)h->colBytes) return MCMCB200_EINVAL;
+	CU(cudaSetDevice(h->device));
+	DevState s;
+	int rc = read_state(h, &s); if (rc) return rc;
+	if (h->nLocal)
+		CU(cudaMemcpyAsync(out, static_cast<const unsigned char *>(h->d_colors[s.sweep & 1]) + (size_t)h->vBegin * h->colBytes, (size_t)h->nLocal * h->colBytes,
+		                   cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return MCMCB200_OK;
+}
+
 int mcmcb200_init_colors_finish(mcmcb200_handle * h) {
 	if (!h) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));

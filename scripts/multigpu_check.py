@@ -79,6 +79,19 @@ for n, deg, proposal, p2p, cap, by_nnz in [(50_001, 12, 0, False, 0, False), (50
     eng.chain.get_colors_slice_ptr(back.ctypes.data)
     if not np.array_equal(back[: ve - vb], c2[vb:ve]):
         ok = False; print(f"rank {rank}: sliced download differs")
+    # the same two transfers in the device's narrow colour format
+    eb = eng.chain.color_bytes()
+    ndt = np.uint8 if eb == 1 else np.uint16
+    own_n = np.ascontiguousarray(c[vb:ve].astype(ndt)) if ve > vb else np.zeros(1, ndt)
+    eng.init_colors_slice(own_n.ctypes.data, sw, eb)
+    st = sw.status()
+    if (st.conflictEdges, st.violatingVertices, st.sweep) != (P.conflict_edges(cumul, neighs, c), P.violation_count(cumul, neighs, c), 0):
+        ok = False; print(f"rank {rank}: narrow sliced init counters differ")
+    sw.sweep(1)
+    back_n = np.zeros(max(ve - vb, 1), dtype=ndt)
+    eng.chain.get_colors_slice_narrow_ptr(back_n.ctypes.data, eb)
+    if not np.array_equal(back_n[: ve - vb].astype(np.uint32), c2[vb:ve]):
+        ok = False; print(f"rank {rank}: narrow sliced download differs")
     eng.chain.close()
 # ---- distributed tail cutting: chain with params.tailcut stops on every rank at <= z violating vertices (global count), the
 #      ranks repair their own violators in synchronised rounds; == the oracle's chain + its sequential tail cut ----
