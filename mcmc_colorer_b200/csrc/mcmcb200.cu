@@ -1189,7 +1189,8 @@ int tc_dist_ready(mcmcb200_handle * h, uint32_t ioCap) {
 	}
 	return MCMCB200_OK;
 }
-// rowptr indexed by GLOBAL vertex id (the repair kernels address rows by the ids in the lists)
+// rowptr indexed by GLOBAL vertex id (the repair kernels address rows by the ids in the lists; only ids in [vBegin, vEnd) -- the
+// vertices this rank listed itself -- are ever used as a row index, so every access stays inside the allocation)
 const uint32_t * tc_rowptr_global(const mcmcb200_handle * h) {
 	return reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(h->d_rowptr) - sizeof(uint32_t) * (uintptr_t)h->vBegin);
 }
@@ -1231,6 +1232,7 @@ int mcmcb200_tailcut_dist_mark(mcmcb200_handle * h, const uint32_t * ids, uint32
 	if (!h->tcActive) return MCMCB200_ESTATE;
 	CU(cudaSetDevice(h->device));
 	if (!count) return MCMCB200_OK;
+	for (uint32_t i = 0; i < count; ++i) if (ids[i] >= h->nGlobal) return MCMCB200_EINVAL;
 	int rc = tc_dist_ready(h, std::max<uint32_t>(count, h->tcIoCap)); if (rc) return rc;
 	CU(cudaMemcpyAsync(h->d_tcIo, ids, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
 	tc_mark_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_tcIo, count, h->d_pending);
