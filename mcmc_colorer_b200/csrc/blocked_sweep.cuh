@@ -649,7 +649,7 @@ struct TileView {
 // ---- phases 1'+2+3 for one slot (thread per vertex): occupancy mask straight from the stage buffer through the static SELL
 //      index words (u16: where each edge's colour sits in this tile's stage), then commit_vertex.  A warp's 32 rows are one
 //      slice of uniform width, so the mask loop is warp-uniform and branch free. ----
-template <int W, typename ColT, bool kDyn>
+template <int W, typename ColT, bool kDyn, bool kPlain>
 __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const TileView<W, ColT> & tv,
                                            uint32_t t, ColT * __restrict__ nxt, uint32_t slot, int lane, float stayW,
                                            const WalkQueue<W> * wq, unsigned long long & accDirected, unsigned long long & accViol) {
@@ -730,7 +730,7 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 		light = true;
 	}
 	if (light)
-		commit_vertex<W, ColT, kDyn>(a, t, nxt, a.vBegin + tv.v0 + lv, tv.v0 + lv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
+		commit_vertex<W, ColT, kDyn, kPlain>(a, t, nxt, a.vBegin + tv.v0 + lv, tv.v0 + lv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
 		                             wq, tv.snew, tv.v0, tv.draw);
 	if (wq != nullptr) {                                      // this warp walks 32 parked vertices at a time: dense lanes, no CTA barrier
 		__syncwarp();
@@ -745,7 +745,7 @@ __device__ __forceinline__ void sweep_slot(const SweepArgs & a, const BlockedArg
 }
 
 // warp per heavy vertex (deg > kLightMaxDeg): lanes stride the row through the plain CSR-order index array
-template <int W, typename ColT, bool kDyn>
+template <int W, typename ColT, bool kDyn, bool kPlain>
 __device__ __forceinline__ void sweep_heavy_list(const SweepArgs & a, const BlockedArgs & bl, const PassBShared<W, ColT> & sm, const TileView<W, ColT> & tv,
                                                  uint32_t t, ColT * __restrict__ nxt, uint32_t nHeavy, int warp, int nWarps, int lane, float stayW,
                                                  unsigned long long & accDirected, unsigned long long & accViol) {
@@ -769,7 +769,7 @@ __device__ __forceinline__ void sweep_heavy_list(const SweepArgs & a, const Bloc
 		for (int w = 0; w < W; ++w) m[w] = warp_reduce_or64(m[w]);
 		same = __reduce_add_sync(0xffffffffu, same);
 		if (lane == 0)
-			commit_vertex<W, ColT, kDyn>(a, t, nxt, gv, tv.v0 + hv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
+			commit_vertex<W, ColT, kDyn, kPlain>(a, t, nxt, gv, tv.v0 + hv, own, m, same, sm.S, sm.dist, sm.hist, stayW, accDirected, accViol,
 			                             nullptr, tv.snew, tv.v0, tv.draw);
 	}
 }
@@ -791,7 +791,7 @@ __device__ __forceinline__ void write_out_tile(const SweepArgs & a, uint32_t t, 
 	}
 }
 
-template <int W, typename ColT, bool kDyn>
+template <int W, typename ColT, bool kDyn, bool kPlain = false>
 __global__ void __launch_bounds__(PassB<W>::threads) __maxnreg__(PassB<W>::maxRegs)
 blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -884,7 +884,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		if (useQueue && lane == 0) *wq.count = 0u;
 		__syncthreads();                                      // draws are in; the previous tile's write-out has left s_new (nbuf == 1)
 		for (uint32_t g = 0; g < tv.nv; g += kT)
-			sweep_slot<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
+			sweep_slot<W, ColT, kDyn, kPlain>(a, bl, sm, tv, t, nxt, g + tid, lane, stayW, useQueue ? &wq : nullptr, accDirected, accViol);
 		if (useQueue) {
 			__syncwarp();
 			const uint32_t qn = min(*wq.count, wq.cap);
@@ -893,7 +893,7 @@ blocked_sweep_kernel(const SweepArgs a, const BlockedArgs bl) {
 		}
 		__syncthreads();
 		const uint32_t nHeavy = min(sm.ctl[1], kHeavyCap);
-		sweep_heavy_list<W, ColT, kDyn>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
+		sweep_heavy_list<W, ColT, kDyn, kPlain>(a, bl, sm, tv, t, nxt, nHeavy, warp, kT / 32, lane, stayW, accDirected, accViol);
 		__syncthreads();                                      // the tile is finished: everybody has read the heavy list and the stage buffer, s_new is complete
 		if (tid == 0) { sm.ctl[1] = 0u; produce(buf); }       // refill this buffer (nbuf == 2: the other one is already in flight)
 		if (!a.countOnly) write_out_tile<ColT>(a, t, nxt, tv.snew, tv.v0, tv.nv, (uint32_t)tid, (uint32_t)kT);

@@ -132,7 +132,12 @@ cudaError_t launch_sweep_t(mcmcb200_handle * h, const SweepArgs & a) {
 		h->launches++;
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;    // (pass B must not be launched without its producer)
 		if (h->overlap && (e = cudaStreamWaitEvent(h->stream, h->evReset, 0)) != cudaSuccess) return e;
-		if (a.proposal == MCMCB200_PROPOSAL_DYNAMIC) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+		// the plain production sweep (no replay tape, no taboo, no debug masks, not a count-only pass) has its own instances
+		const bool plain = W <= 2 && !a.countOnly && !a.tape && !a.tabooIter && !a.dbgMasks;
+		const bool dyn = a.proposal == MCMCB200_PROPOSAL_DYNAMIC;
+		if (plain && dyn) blocked_sweep_kernel<W, ColT, true, (W <= 2)><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+		else if (plain) blocked_sweep_kernel<W, ColT, false, (W <= 2)><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
+		else if (dyn) blocked_sweep_kernel<W, ColT, true><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 		else blocked_sweep_kernel<W, ColT, false><<<h->bl.gridB, PassB<W>::threads, h->bl.smemB, h->stream>>>(a, b);
 #if MCMCB200_TIMING
 		{ unsigned long long tm[8]; cudaStreamSynchronize(h->stream); cudaStreamSynchronize(sA); cudaMemcpy(tm, h->bl.dbgTimes, sizeof(tm), cudaMemcpyDeviceToHost);
@@ -168,6 +173,8 @@ cudaError_t configure_blocked_t(mcmcb200_handle * h) {
 	e = cudaFuncSetAttribute(blocked_gather_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemA);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, true, (W <= 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(blocked_sweep_kernel<W, ColT, false, (W <= 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemB);
 	if (e != cudaSuccess) return e;
 	int oa = 0, ob0 = 0, ob1 = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, blocked_gather_kernel<ColT>, kThreadsA, L.smemA);

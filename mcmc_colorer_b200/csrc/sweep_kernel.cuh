@@ -357,7 +357,9 @@ __device__ __forceinline__ void finish_vertex(const SweepArgs & a, ColT * __rest
 // colour count, taboo gate, draw, proposal, colour write, class-size deltas.
 //   v = global vertex id, lv = local (owned) index, m = occupancy mask, same = #neighbours with v's colour.
 // ---------------------------------------------------------------------------------------------
-template <int W, typename ColT, bool kDyn>
+// kPlain: the instance for the plain production sweep -- the caller guarantees no replay tape, no taboo, no debug masks and not a
+// count-only pass, so their (warp-uniform, but issued per vertex) tests are compiled out: 5 % of pass B's instructions on config 3.
+template <int W, typename ColT, bool kDyn, bool kPlain = false>
 __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, ColT * __restrict__ nxt, uint32_t v, uint32_t lv,
                                               uint32_t myOwn, const unsigned long long (&m)[W], uint32_t same,
                                               const float * s_S, const float * s_dist, int * s_hist, float stayW,
@@ -370,7 +372,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 	const bool viol = same > 0u;                              // occ[C[v]]  (violation_count, coloringMCMC_CPU.cpp:342-348)
 	accDirected += same;
 	accViol += viol ? 1ull : 0ull;
-	if (a.dbgMasks) {
+	if (!kPlain && a.dbgMasks) {
 #pragma unroll
 		for (int w = 0; w < W; ++w) a.dbgMasks[(size_t)lv * W + w] = m[w];
 		a.dbgSame[lv] = same;
@@ -386,10 +388,10 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 			if (idx < a.violCap) a.violList[idx] = v;
 		}
 	}
-	if (a.countOnly) return;
+	if (!kPlain && a.countOnly) return;
 	uint32_t newc = myOwn;
 	bool tabooed = false;
-	if (a.tabooIter) {                                        // TABOO gate, coloringMCMC_CPU.cpp:496-501
+	if (!kPlain && a.tabooIter) {                             // TABOO gate, coloringMCMC_CPU.cpp:496-501
 		const uint32_t tb = a.taboo[lv];
 		if (tb > 0u) { a.taboo[lv] = (uint16_t)(tb - 1u); tabooed = true; }
 	}
@@ -402,7 +404,7 @@ __device__ __forceinline__ void commit_vertex(const SweepArgs & a, uint32_t t, C
 			newc = myOwn;                                     // coloringMCMC_balance.cu:111-115: no draw, taboo untouched
 		} else {
 			float u;
-			if (a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
+			if (!kPlain && a.tape) u = a.tape[(size_t)(t - a.tapeBase) * a.nGlobal + v];
 			else if (drawTab) u = draw_to_uniform(drawTab[lv - tileV0], isDyn);      // the tile's Philox words, one call per 4 vertices
 			else u = draw_to_uniform(philox_draw(a.seed, t + 1u, v, 0u), isDyn);
 			const bool stay = !viol || Zp == 0u;              // :472-478 / :402-411
