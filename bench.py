@@ -441,7 +441,9 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks.summary(),
         "after_10_chain_sweeps": {"conflictEdges": int(st.conflictEdges), "violatingVertices": int(st.violatingVertices)},
-        "time_to_proper_coloring": dict(ttc, one_shot=ttc_one_shot),
+        "time_to_proper_coloring": dict(ttc, one_shot=ttc_one_shot,
+                                        setup_note="setup_ms = wall time of mcmcb200_create: layout-construction kernels (75 ms on config 3) + ~30 cudaMalloc/"
+                                                   "cudaFree of GB-sized buffers; 90-140 ms on an idle box (profiles/r02_create_times.jsonl), more on a shared one"),
     }
     if not args.no_cpu_baseline:
         rate, kind, sample, secs, m = cpu_reference_rate(rowptr, neighs, n, nnz, nCol, target_seconds=12.0, v0=sample_start(args.workload, n))

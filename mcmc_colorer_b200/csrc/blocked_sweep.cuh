@@ -406,8 +406,9 @@ __device__ __forceinline__ void st_ecol64(void * p, uint2 v, unsigned long long 
 // ------------------------------------------------------------------------------------------------------------------
 // pass A: ecol[pos] = cur[bucket * 65536 + srcLocal[pos]]  -- the gather runs out of shared memory
 // ------------------------------------------------------------------------------------------------------------------
+// (64 registers at most: one pass-A CTA must fit next to two pass-B CTAs -- 2 x 384 x 64 + 256 x 64 registers = the whole file)
 template <typename ColT>
-__global__ void __launch_bounds__(kThreadsA)
+__global__ void __launch_bounds__(kThreadsA, 4)
 blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	ColT * chunk = reinterpret_cast<ColT *>(smem_raw);
@@ -453,7 +454,7 @@ blocked_gather_kernel(const SweepArgs a, const BlockedArgs bl) {
 		// one 4-entry granule per lane per step: a warp reads 256 contiguous bytes of local ids and 128 of destinations, and
 		// its store covers whole 32-byte sectors wherever a run spans them (full-sector first touches need no fill in L2)
 #ifndef MCMCB200_A_KU
-#define MCMCB200_A_KU 12     /* config 3: 8 -> 3.62 ms, 10 -> 3.52, 12 -> 3.49 per sweep (57 registers: one pass-A CTA still fits next to two pass-B CTAs); 14 no longer does */
+#define MCMCB200_A_KU 13     /* config 3: 8 -> 3.62 ms, 10 -> 3.52, 12 -> 3.49, 13 -> 3.40 (with the plain pass-B instances), 14 -> 3.42, 15 -> 3.45, 16 (spills) -> 3.66 per sweep */
 #endif
 		constexpr uint32_t kU = MCMCB200_A_KU;   // granules in flight per thread: 12 bytes of loads each (pass A is bound by bytes in flight)
 		const uint32_t g0 = beg >> 2, g1 = end >> 2;           // runs are padded to 4 entries: items are whole granules
