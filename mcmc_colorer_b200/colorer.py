@@ -230,7 +230,8 @@ class Chain:
         return r.value
 
     # ---- distributed tail cutting (mcmcb200_tailcut_dist_*): one rank's part; multigpu.DistributedSweeper.tailcut drives it ----
-    def tc_begin(self, order, cap=1 << 22):
+    def tc_begin(self, order, cap=None):
+        cap = max(1, min(self.n, 1 << 26)) if cap is None else cap
         o = np.ascontiguousarray(order, np.uint32)
         out = np.empty(cap, np.uint32)
         cnt = C.c_uint32()
@@ -242,7 +243,8 @@ class Chain:
         a = np.ascontiguousarray(ids, np.uint32)
         capi.check(self.L.mcmcb200_tailcut_dist_mark(self.h, a.ctypes.data_as(C.c_void_p), len(a)), "mcmcb200_tailcut_dist_mark")
 
-    def tc_round(self, cap=1 << 22):
+    def tc_round(self, cap=None):
+        cap = max(1, min(self.n, 1 << 26)) if cap is None else cap
         ids, cols = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
         done, left, inexact = C.c_uint32(), C.c_uint32(), C.c_uint32()
         capi.check(self.L.mcmcb200_tailcut_dist_round(self.h, ids.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), cap,

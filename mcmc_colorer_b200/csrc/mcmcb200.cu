@@ -457,6 +457,7 @@ int reset_state(mcmcb200_handle * h) {
 	CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * (h->p.nCol + 2), h->stream));
 	if (h->d_taboo) CU(cudaMemsetAsync(h->d_taboo, 0, sizeof(uint16_t) * std::max<size_t>(h->nLocal, 1), h->stream));
 	h->hostSweepUpper = 0; h->tapeBase = 0; h->pendingCountOnly = false;
+	h->tcActive = false;                                          // (a distributed repair that was left half-way does not survive a new colouring)
 	return MCMCB200_OK;
 }
 
@@ -952,6 +953,7 @@ int mcmcb200_sweep(mcmcb200_handle * h, uint32_t k) {
 	const bool split = h->split();
 	if (split && k != 1) return MCMCB200_EINVAL;
 	CU(cudaSetDevice(h->device));
+	h->tcActive = false;                                          // a sweep ends any distributed repair in progress
 	CU(cudaEventRecord(h->ev0, h->stream));
 	for (uint32_t i = 0; i < k; ++i) {
 		if (h->tapeSweeps && (h->hostSweepUpper - h->tapeBase) >= h->tapeSweeps) {
