@@ -48,7 +48,8 @@ WORKLOADS = {
 }
 GRAPH_SEED = 42
 # measured DRAM traffic of one sweep (ncu dram__bytes_read.sum + dram__bytes_write.sum, both launches), bytes
-TRAFFIC = {"c3": 13.56e9}
+TRAFFIC = {"c3": (14.93e9, "profiles/r02_ncu_blocked_kernels_c3.md (ncu dram__bytes of both kernels of one sweep: 7.48 + 1.73 + 5.62 + 0.10 GB)"),
+           "c4": (11.59e9, "profiles/r02_config4_wide_palette.md (ncu dram__bytes of the four kernels of one sweep)")}
 CHAIN_SEED = 1
 
 
@@ -422,7 +423,8 @@ def main():
         "edges_per_sec": value * nnz / n,
         "chain_ms_per_sweep": chain_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC.get(args.workload), "traffic_source": "profiles/r01g_ncu_blocked_kernels_c3.md (ncu dram__bytes of both kernels of one sweep)" if args.workload in TRAFFIC else None,
+                     "traffic": TRAFFIC[args.workload][0] if args.workload in TRAFFIC and args.proposal == "uniform" and not args.ncol else None,
+                     "traffic_source": TRAFFIC[args.workload][1] if args.workload in TRAFFIC and args.proposal == "uniform" and not args.ncol else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": {"direct": "sweep_kernel (one launch per sweep)",
                                 "direct-binned": "binned_sweep_kernel (one launch per sweep; thread / warp / CTA rows by degree)",
