@@ -67,6 +67,34 @@ def our_chain(mc, cumul, neighs, nCol, kernel, taboo=0, eps=EPS, tailcut=False, 
 # ------------------------------------------------------------------------------------------------------------
 # DYNAMIC proposal: tape replay against the reference's selectStarColoringBalanceDynamic
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nCol,taboo,eps", [(600, 0, 1e-8), (700, 2, 1e-4)])
+def test_dynamic_tape_replay_vs_reference_kernel_wide_palettes(mc, rg, port, c1_graph, nCol, taboo, eps):
+    """the same replay on the wide-palette kernels (more than 512 colours): the reference kernel takes any palette up to the number of
+    vertices (its class-size arrays have n entries, coloringMCMC_main.cu:29-33,211-214: nCol > n overruns them); the chain starts from
+    8 colours so that nearly every vertex conflicts and walks"""
+    cumul, neighs = c1_graph
+    n = 1000
+    h = rg.create(cumul, neighs, nCol, prob=0.1, eps=eps, taboo_iter=taboo, curand_seed=99 + nCol)
+    prm = mc.ColoringMCMCParams(nCol=nCol, proposal=mc.PROPOSAL_DYNAMIC, convergence=mc.CONVERGE_EDGES, tabooIteration=taboo, seed=0, epsilon=eps)
+    ch = mc.Chain(cumul, neighs, prm, device=0, flags=mc.FLAG_NO_EARLY_STOP)
+    assert ch.kernel_mode() == "wide-binned"
+    rng = np.random.default_rng(nCol)
+    c0 = (rng.integers(0, 8, n) * (nCol // 8)).astype(np.uint32)
+    rg.set_colors(h, c0)
+    ch.init_colors(c0)
+    for s in range(8):
+        u = rg.peek_draws(h, n)
+        rg.step_dynamic(h, prefill=True)
+        ch.set_tape(u[None, :])
+        ch.sweep(1)
+        want = rg.get_colors(h, n)
+        got = ch.get_colors()
+        assert np.array_equal(got, want), (nCol, taboo, s, np.flatnonzero(got != want)[:8])
+        assert np.array_equal(ch.class_sizes().astype(np.uint32), np.bincount(want, minlength=nCol).astype(np.uint32))
+    ch.close()
+    rg.destroy(h)
+
+
 @pytest.mark.parametrize("kernel", ["direct", "blocked", "binned"])
 @pytest.mark.parametrize("nCol,taboo,eps", [(137, 0, 1e-8), (60, 0, 1e-8), (45, 3, 1e-8), (200, 0, 1e-8), (89, 0, 1e-4), (300, 2, 1e-4)])
 def test_dynamic_tape_replay_vs_reference_kernel(mc, rg, port, c1_graph, kernel, nCol, taboo, eps):

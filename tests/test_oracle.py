@@ -229,3 +229,26 @@ def test_port_matches_reference_live(port, ref):
             assert ov == ov2 and np.array_equal(c, ref.get_colors(h, n))
             if ti:
                 assert np.array_equal(taboo, ref.get_taboo(h, n))
+
+
+def test_port_matches_reference_live_wide_palettes(port, ref):
+    """The same live pin for palettes above 512 colours (the wide-palette GPU kernels are compared with the port): the unmodified
+    reference CPU colourer takes any nCol (its scratch is nCol-sized per vertex), so port == reference there too -- start from few
+    colours so that most vertices conflict and the long CDF walks really run."""
+    g = ref.graph_simulate(250, 0.08, srand=4242)
+    cumul, neighs = ref.graph_csr(g)
+    n = 250
+    rng = np.random.default_rng(9)
+    for nCol, ti in [(513, 0), (700, 2), (4097, 0)]:
+        h = ref.mcmc(g, nCol, 1, taboo_iter=ti)
+        c = (rng.integers(0, 6, n) * (nCol // 6)).astype(np.uint32)
+        ref.set_colors(h, c)
+        taboo = np.zeros(n, np.uint32) if ti else None
+        for s in range(6):
+            u = rng.random(n, dtype=np.float32)
+            if s == 3:
+                u[rng.integers(0, n, 20)] = np.nextafter(np.float32(1), np.float32(0))
+            before, ov = ref.sweep_tape(h, u)
+            assert before == port.violation_count(cumul, neighs, c)
+            c, ov2 = port.sweep(cumul, neighs, nCol, 1e-8, c, u, UNIFORM, taboo=taboo, taboo_iter=ti)
+            assert ov == ov2 and np.array_equal(c, ref.get_colors(h, n))
